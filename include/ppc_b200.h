@@ -1,0 +1,142 @@
+/*
+ * ppc_b200.h -- C ABI of libparticlephysicsc_b200.so, the B200-native drop-in for the solver hot path of
+ * isekar0/ParticlePhysicsC.
+ *
+ * Part 1 declares the reference's OWN entry points with their own signatures; the library exports exactly
+ * these symbols, so the reference's main.c and particlesDraw link against it unchanged (the reference has no
+ * FFI layer: its boundary is the plain C link interface).  Each declaration cites the
+ * reference interface it replaces (paths relative to the reference root).
+ *
+ * Part 2 declares the additional ppc_* entry points a headless harness needs (when to copy back, parity
+ * exporters, timing).  Nothing in this header mentions torch or CUDA types; pointers and sizes only.
+ *
+ * Include order: when building against the reference's own headers (includes/structs.h, <raylib.h>) include
+ * those FIRST; this header then reuses their types.  Stand-alone (tests, headless harness) it defines
+ * layout-identical Color / Vector2 / struct Particles_t / struct Pair itself.
+ */
+#ifndef PPC_B200_H
+#define PPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- types: reference includes/structs.h:9-26 and Raylib's Color / Vector2 -------------------------------- */
+#ifndef RAYLIB_H
+#define PPC_B200_OWN_RAYLIB_TYPES 1
+typedef struct Color {
+    unsigned char r, g, b, a;
+} Color;
+typedef struct Vector2 {
+    float x, y;
+} Vector2;
+#endif
+
+#ifndef STRUCTS_H
+#define PPC_B200_OWN_STRUCTS 1
+struct Particles_t { /* 72 bytes; field order is part of the ABI (includes/structs.h:9-22) */
+    float *v_x, *v_y;
+    float *p_x, *p_y;
+    Color *colors;
+    float *mass;
+    float *radius;
+    size_t length; /* particles processed by the solver: [0, length) */
+    size_t size;   /* capacity of the seven arrays */
+};
+struct Pair { /* includes/structs.h:24-26 */
+    int i, j;
+};
+#endif
+
+/* =====================================================================================================
+ * Part 1 -- the reference's entry points (drop-in).
+ * ===================================================================================================== */
+
+/* includes/particles_arrays.h:17, src/particles_arrays.c:145-194.  Seven host arrays of num_particles_init
+ * elements (page-locked so copy-back is a straight DMA), zero-filled; length = 0.  Returned BY VALUE.
+ * Allocation failure: message on stderr and exit(EXIT_FAILURE), as the reference. */
+struct Particles_t particlesCreate( size_t num_particles_init );
+
+/* includes/particles_arrays.h:16, src/particles_arrays.c:134-143.  Frees the seven arrays and the device
+ * mirror; does not touch the struct's fields (as the reference). */
+void particlesFree( struct Particles_t *particles );
+
+/* includes/particles_arrays.h:18, src/particles_arrays.c:257-278.  Bug-compatible: grows x2 when
+ * length + num_particles >= size; each copy increments length FIRST and writes slot `length`, so slot 0 is
+ * never written and the newest particle is dormant until the next add.  Colour BLUE, zero velocity. */
+void particlesAddParticle( struct Particles_t *particles, const Vector2 particle_i_position, const float particle_i_mass,
+                           const float particle_i_radius, uint8_t num_particles );
+
+/* includes/particles_arrays.h:19, src/particles_arrays.c:280-291.  Zeroes slot `length`, decrements length. */
+void particlesRemoveParticle( struct Particles_t *particles );
+
+/* includes/particles_solver.h:9, src/particles_solver.c:16-43.  Kinematic update + drag + gravity kick (+ colour). */
+void particlesUpdate( struct Particles_t *particles, const float time_step );
+
+/* includes/particles_solver.h:10, src/particles_solver.c:197-393.  Wall pass, uniform grid, pair search, contact
+ * resolution.  No-op when length < 2 (src/particles_solver.c:204-205). */
+void particlesCollisionsCheck_Grid( struct Particles_t *particles, const uint16_t window_width, const uint16_t window_height,
+                                    float time_step );
+
+/* =====================================================================================================
+ * Part 2 -- harness extensions.
+ * ===================================================================================================== */
+
+/* When the host arrays of struct Particles_t are made current. */
+enum {
+    PPC_SYNC_EVERY_CALL = 0, /* after every particlesUpdate / particlesCollisionsCheck_Grid (fully transparent) */
+    PPC_SYNC_FRAME      = 1, /* after every particlesCollisionsCheck_Grid: what main.c needs (default)          */
+    PPC_SYNC_MANUAL     = 2  /* headless: only ppc_download() copies back ("only when a frame is drawn")        */
+};
+/* which arrays ppc_download / the automatic copy-back move */
+enum { PPC_DL_POS = 1, PPC_DL_VEL = 2, PPC_DL_COLOR = 4, PPC_DL_ALL = 7 };
+
+void ppc_set_device( int cuda_device );                               /* before the first particlesCreate; default 0 or $PPC_DEVICE */
+void ppc_set_sync_policy( struct Particles_t *p, int policy );
+void ppc_set_download_mask( struct Particles_t *p, unsigned mask );   /* arrays moved by the automatic copy-back */
+void ppc_request_colors( struct Particles_t *p );                     /* MANUAL policy: the next particlesUpdate also computes colours */
+void ppc_host_modified( struct Particles_t *p );                      /* caller wrote the host arrays directly: re-upload at next call */
+void ppc_download( struct Particles_t *p, unsigned mask );            /* make host arrays current now (blocking) */
+void ppc_synchronize( struct Particles_t *p );                        /* wait for all queued device work */
+
+/* n x { particlesUpdate(dt); particlesCollisionsCheck_Grid(W, H, dt); } without touching host memory;
+ * colours are computed on the last substep iff color_last. */
+void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t window_height, float time_step, int n, int color_last );
+
+/* Named integer options; returns 0 on success, -1 for an unknown name.
+ *   "sort"     0 = counting sort on the cell key (default), 1 = LSD radix sort
+ *   "stash"    per-thread contact stash: 1 = on (default), 0 = off (streaming path only; test hook)
+ *   "resolve"  1 = resolve contacts (default), 0 = walls + grid only
+ *   "collide"  0 = auto, 1 = global-memory kernel, 2 = shared-memory tile kernel */
+int ppc_set_option( struct Particles_t *p, const char *name, long long value );
+
+/* ---- parity exporters: state of the LAST grid build (all return 0 on success, -1 if no grid was built) ---- */
+typedef struct ppc_grid_info {
+    float    max_radius, cell_size; /* src/particles_solver.c:231-244 */
+    int      cols, rows;            /* :247-248 */
+    uint64_t cells, n;
+} ppc_grid_info;
+int     ppc_debug_grid_info( struct Particles_t *p, ppc_grid_info *out );
+int     ppc_debug_keys( struct Particles_t *p, uint32_t *keys_by_index /* n */ );      /* :280-291 */
+int     ppc_debug_sorted_order( struct Particles_t *p, uint32_t *order /* n */ );      /* stable ascending (key, index) */
+int     ppc_debug_cell_start( struct Particles_t *p, uint32_t *cell_start /* cells+1 */ );
+/* candidate pairs (i, j) in the reference's list order (:311-383); returns the count, writes min(count, max_pairs) */
+int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
+
+/* ---- timing ---- */
+void              *ppc_stream( struct Particles_t *p );                /* the cudaStream_t all work is queued on */
+unsigned long long ppc_kernel_launches( void );                        /* kernels launched by this library so far */
+void               ppc_profile( struct Particles_t *p, int enable );   /* per-stage CUDA-event timing (serialises) */
+int                ppc_profile_stages( void );
+const char        *ppc_profile_stage_name( int stage );
+int                ppc_profile_read( struct Particles_t *p, int stage, double *total_ms, unsigned long long *launches );
+void               ppc_profile_reset( struct Particles_t *p );
+const char        *ppc_version( void );
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPC_B200_H */

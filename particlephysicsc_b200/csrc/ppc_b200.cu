@@ -1,0 +1,728 @@
+// ppc_b200.cu -- the C-ABI shim: the reference's entry points (include/ppc_b200.h part 1) over a device-resident
+// particle store, plus the headless-harness extensions (part 2).
+//
+// The caller-visible struct Particles_t keeps its 72-byte layout and its seven host arrays (reference
+// includes/structs.h:9-22); it has no room for a handle, so the device mirror lives in a side table keyed by the
+// address of the `mass` array (the app holds exactly one instance, reference src/main.c:57).
+//
+// Data movement at the boundary:
+//   host -> device : only the slots that entered the processed range [0, length) since the last solver call
+//   device -> host : p_x, p_y, v_x, v_y, colors when the sync policy says the host arrays must be current
+//   per substep    : nothing
+//
+// There is no CPU fallback: every entry point needs a CUDA device and aborts loudly without one.
+#include "../../include/ppc_b200.h"
+
+#include "ppc_collide.cuh"
+#include "ppc_common.cuh"
+#include "ppc_grid.cuh"
+#include "ppc_radix.cuh"
+#include "ppc_scan.cuh"
+
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+namespace ppc {
+unsigned long long g_launches = 0;
+
+enum Stage { ST_INTEGRATE = 0, ST_SCAN, ST_SORT, ST_GATHER, ST_COLLIDE, ST_UPLOAD, ST_DOWNLOAD, ST_MISC, ST_COUNT };
+static const char *k_stage_names[ ST_COUNT ] = { "integrate_walls_keys", "cell_scan", "cell_sort", "canonical_gather",
+                                                 "collide",              "upload",    "download",  "misc" };
+
+struct Store {
+    // identity / host side
+    const void *host_key   = nullptr;   // particles->mass
+    bool        owns_host  = false;
+    size_t      cap        = 0;   // capacity of host and device arrays (particles->size)
+    size_t      n          = 0;   // particles resident on the device: API indices [0, n)
+    bool        dirty_all  = true;
+    float       max_radius = 6.0f;   // reference src/particles_solver.c:231
+    bool        max_radius_dirty = true;
+    // policy
+    int      sync_policy   = PPC_SYNC_FRAME;
+    unsigned dl_mask       = PPC_DL_ALL;
+    bool     colour_wanted = false;
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0;
+    // pending particlesUpdate (fused into the next collisions check)
+    bool  pending = false;
+    float pending_dt = 0.0f;
+    bool  pending_colour = false;
+    // device
+    cudaStream_t stream = nullptr;
+    ParticleSet  set[ 2 ] = {};
+    int          cur = 0;
+    float       *api_f[ 6 ] = {};   // px, py, vx, vy, mass, radius in API order (staging for upload / download)
+    uchar4      *api_col = nullptr;
+    uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
+    uint32_t    *cell_count = nullptr, *cell_start = nullptr;
+    size_t       cells_cap = 0;
+    uint32_t    *scratch = nullptr;
+    size_t       scratch_words = 0;
+    uint32_t    *d_word = nullptr;   // one word for small reductions
+    // last grid
+    bool     grid_valid = false, pre_valid = false;
+    GridDims grid = {};
+    // profiling
+    bool               profiling = false;
+    cudaEvent_t        ev0 = nullptr, ev1 = nullptr;
+    double             stage_ms[ ST_COUNT ] = {};
+    unsigned long long stage_launches[ ST_COUNT ] = {};
+};
+
+static std::vector<Store *> g_stores;
+static int                  g_device = -1;
+
+static void select_device() {
+    if ( g_device < 0 ) {
+        const char *e = getenv( "PPC_DEVICE" );
+        g_device      = e ? atoi( e ) : 0;
+    }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount( &count );
+    if ( err != cudaSuccess || count == 0 ) {
+        fprintf( stderr, "particlephysicsc_b200: no CUDA device available (%s); this library has no CPU fallback\n",
+                 err == cudaSuccess ? "device count is 0" : cudaGetErrorString( err ) );
+        abort();
+    }
+    PPC_CK( cudaSetDevice( g_device ) );
+}
+
+template <class T>
+static T *dev_alloc( size_t count ) {
+    T *p = nullptr;
+    PPC_CK( cudaMalloc( &p, ( count ? count : 1 ) * sizeof( T ) ) );
+    return p;
+}
+
+struct StageTimer {
+    Store *st;
+    int    stage;
+    unsigned long long l0;
+    StageTimer( Store *s, int g ) : st( s ), stage( g ), l0( g_launches ) {
+        if ( st->profiling )
+            PPC_CK( cudaEventRecord( st->ev0, st->stream ) );
+    }
+    ~StageTimer() {
+        if ( st->profiling ) {
+            PPC_CK( cudaEventRecord( st->ev1, st->stream ) );
+            PPC_CK( cudaEventSynchronize( st->ev1 ) );
+            float ms = 0;
+            PPC_CK( cudaEventElapsedTime( &ms, st->ev0, st->ev1 ) );
+            st->stage_ms[ stage ] += ms;
+            st->stage_launches[ stage ] += g_launches - l0;
+        }
+    }
+};
+
+// ---- device storage -------------------------------------------------------------------------------------------
+static void free_particle_arrays( Store *st ) {
+    for ( int s = 0; s < 2; s++ ) {
+        cudaFree( st->set[ s ].pv );
+        cudaFree( st->set[ s ].rm );
+        cudaFree( st->set[ s ].gid );
+        cudaFree( st->set[ s ].key );
+        cudaFree( st->set[ s ].col );
+        st->set[ s ] = ParticleSet{};
+    }
+    for ( int a = 0; a < 6; a++ ) {
+        cudaFree( st->api_f[ a ] );
+        st->api_f[ a ] = nullptr;
+    }
+    cudaFree( st->api_col );
+    cudaFree( st->slot_of );
+    cudaFree( st->sort_keys_a );
+    cudaFree( st->sort_keys_b );
+    cudaFree( st->sort_vals_b );
+    cudaFree( st->scratch );
+    st->api_col = nullptr;
+    st->slot_of = st->sort_keys_a = st->sort_keys_b = st->sort_vals_b = st->scratch = nullptr;
+    st->scratch_words = 0;
+}
+
+// (Re)allocate the per-particle device arrays for `cap` particles, keeping the first `keep` storage slots.
+static void resize_particle_arrays( Store *st, size_t cap, size_t keep ) {
+    ParticleSet old[ 2 ] = { st->set[ 0 ], st->set[ 1 ] };
+    for ( int s = 0; s < 2; s++ ) {
+        st->set[ s ].pv  = dev_alloc<float4>( cap );
+        st->set[ s ].rm  = dev_alloc<float2>( cap );
+        st->set[ s ].gid = dev_alloc<uint32_t>( cap );
+        st->set[ s ].key = dev_alloc<uint32_t>( cap );
+        st->set[ s ].col = dev_alloc<uchar4>( cap );
+    }
+    if ( keep && old[ st->cur ].pv ) {   // only the current set holds live data between calls
+        const ParticleSet &o = old[ st->cur ], &d = st->set[ st->cur ];
+        PPC_CK( cudaMemcpyAsync( d.pv, o.pv, keep * sizeof( float4 ), cudaMemcpyDeviceToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( d.rm, o.rm, keep * sizeof( float2 ), cudaMemcpyDeviceToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( d.gid, o.gid, keep * sizeof( uint32_t ), cudaMemcpyDeviceToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( d.key, o.key, keep * sizeof( uint32_t ), cudaMemcpyDeviceToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( d.col, o.col, keep * sizeof( uchar4 ), cudaMemcpyDeviceToDevice, st->stream ) );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+    }
+    for ( int s = 0; s < 2; s++ ) {
+        cudaFree( old[ s ].pv );
+        cudaFree( old[ s ].rm );
+        cudaFree( old[ s ].gid );
+        cudaFree( old[ s ].key );
+        cudaFree( old[ s ].col );
+    }
+    for ( int a = 0; a < 6; a++ ) {
+        cudaFree( st->api_f[ a ] );
+        st->api_f[ a ] = dev_alloc<float>( cap );
+    }
+    cudaFree( st->api_col );
+    cudaFree( st->slot_of );
+    cudaFree( st->sort_keys_a );
+    cudaFree( st->sort_keys_b );
+    cudaFree( st->sort_vals_b );
+    st->api_col     = dev_alloc<uchar4>( cap );
+    st->slot_of     = dev_alloc<uint32_t>( cap );
+    st->sort_keys_a = dev_alloc<uint32_t>( cap );
+    st->sort_keys_b = dev_alloc<uint32_t>( cap );
+    st->sort_vals_b = dev_alloc<uint32_t>( cap );
+    st->cap         = cap;
+    st->pre_valid   = false;
+}
+
+static void ensure_scratch( Store *st, size_t words ) {
+    if ( words <= st->scratch_words )
+        return;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    cudaFree( st->scratch );
+    st->scratch       = dev_alloc<uint32_t>( words );
+    st->scratch_words = words;
+}
+
+static void ensure_cells( Store *st, size_t cells ) {
+    if ( cells + 1 <= st->cells_cap )
+        return;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    cudaFree( st->cell_count );
+    cudaFree( st->cell_start );
+    st->cells_cap  = cells + 1 + cells / 8;
+    st->cell_count = dev_alloc<uint32_t>( st->cells_cap );
+    st->cell_start = dev_alloc<uint32_t>( st->cells_cap );
+}
+
+static Store *new_store( const struct Particles_t *p, bool owns_host ) {
+    select_device();
+    Store *st     = new Store();
+    st->host_key  = p->mass;
+    st->owns_host = owns_host;
+    PPC_CK( cudaStreamCreateWithFlags( &st->stream, cudaStreamNonBlocking ) );
+    PPC_CK( cudaEventCreate( &st->ev0 ) );
+    PPC_CK( cudaEventCreate( &st->ev1 ) );
+    st->d_word = dev_alloc<uint32_t>( 4 );
+    resize_particle_arrays( st, p->size, 0 );
+    g_stores.push_back( st );
+    return st;
+}
+
+// Find the device mirror of a caller's struct; adopt arrays we did not allocate (a harness that filled its own).
+static Store *store_of( struct Particles_t *p ) {
+    for ( Store *st : g_stores )
+        if ( st->host_key == p->mass )
+            return st;
+    Store *st     = new_store( p, false );
+    st->dirty_all = true;
+    return st;
+}
+
+// ---- host <-> device ------------------------------------------------------------------------------------------
+static float *const *host_float_arrays( struct Particles_t *p, float *out[ 6 ] ) {
+    out[ 0 ] = p->p_x, out[ 1 ] = p->p_y, out[ 2 ] = p->v_x, out[ 3 ] = p->v_y, out[ 4 ] = p->mass, out[ 5 ] = p->radius;
+    return out;
+}
+
+// Upload API indices [first, first+count) from the host arrays into storage slots of the same numbers.
+static void upload_range( Store *st, struct Particles_t *p, size_t first, size_t count ) {
+    if ( count == 0 )
+        return;
+    StageTimer T( st, ST_UPLOAD );
+    float     *h[ 6 ];
+    host_float_arrays( p, h );
+    for ( int a = 0; a < 6; a++ )
+        PPC_CK( cudaMemcpyAsync( st->api_f[ a ] + first, h[ a ] + first, count * sizeof( float ), cudaMemcpyHostToDevice, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->api_col + first, p->colors + first, count * sizeof( uchar4 ), cudaMemcpyHostToDevice, st->stream ) );
+    PPC_LAUNCH( k_pack_upload, div_up( count, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->api_f[ 0 ],
+                st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, first, count );
+    // the host buffers may be pageable (adopted arrays) or rewritten by the caller right after we return
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+}
+
+static void refresh_max_radius( Store *st ) {
+    if ( !st->max_radius_dirty )
+        return;
+    StageTimer     T( st, ST_MISC );
+    const float    floor_r = 6.0f;   // reference src/particles_solver.c:231
+    uint32_t       bits;
+    memcpy( &bits, &floor_r, 4 );
+    PPC_CK( cudaMemcpyAsync( st->d_word, &bits, 4, cudaMemcpyHostToDevice, st->stream ) );
+    if ( st->n ) {
+        const unsigned blocks = st->n < (size_t)148 * 8 * STREAM_THREADS ? div_up( st->n, STREAM_THREADS ) : 148u * 8u;
+        PPC_LAUNCH( k_max_radius, blocks, STREAM_THREADS, 0, st->stream, st->set[ st->cur ].rm, st->n, st->d_word );
+    }
+    PPC_CK( cudaMemcpyAsync( &bits, st->d_word, 4, cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    memcpy( &st->max_radius, &bits, 4 );
+    st->max_radius_dirty = false;
+}
+
+// Bring the device mirror in line with what the caller did to the host struct since the last call.
+static void absorb_host_changes( Store *st, struct Particles_t *p ) {
+    if ( p->size != st->cap ) {   // arrays were re-sized behind our back (adopted arrays only)
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        resize_particle_arrays( st, p->size, 0 );
+        st->dirty_all = true;
+    }
+    if ( p->length > st->cap ) {
+        fprintf( stderr, "particlephysicsc_b200: length %zu exceeds size %zu\n", p->length, p->size );
+        abort();
+    }
+    if ( !st->dirty_all && p->length < st->n )   // shrunk without particlesRemoveParticle: host arrays are the truth
+        st->dirty_all = true;
+    if ( st->dirty_all ) {
+        st->pending = false;
+        st->n       = p->length;
+        upload_range( st, p, 0, st->n );
+        st->dirty_all        = false;
+        st->grid_valid       = false;
+        st->pre_valid        = false;
+        st->max_radius_dirty = true;
+    } else if ( p->length > st->n ) {
+        const size_t first = st->n, count = p->length - st->n;
+        upload_range( st, p, first, count );
+        st->n = p->length;
+        if ( !st->max_radius_dirty )
+            for ( size_t k = first; k < first + count; k++ )   // reference :231-236, incrementally
+                if ( p->radius[ k ] > st->max_radius )
+                    st->max_radius = p->radius[ k ];
+        st->pre_valid = false;
+    }
+}
+
+// ---- the substep ----------------------------------------------------------------------------------------------
+static void launch_integrate( Store *st, const StepParams &P ) {
+    StageTimer T( st, ST_INTEGRATE );
+    if ( P.do_walls_keys )
+        PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( (size_t)P.grid.cells + 1 ) * sizeof( uint32_t ), st->stream ) );
+    PPC_LAUNCH( k_integrate_walls_keys, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->cell_count,
+                st->n, P );
+}
+
+// particlesUpdate on its own (no collisions check follows, or the host wants to look at the result).
+static void flush_pending_update( Store *st ) {
+    if ( !st->pending )
+        return;
+    st->pending = false;
+    if ( st->n == 0 )
+        return;
+    StepParams P   = {};
+    P.dt_update    = st->pending_dt;
+    P.do_integrate = 1;
+    P.do_colour    = st->pending_colour ? 1 : 0;
+    launch_integrate( st, P );
+    st->pre_valid = false;
+}
+
+static int bits_for( uint32_t cells ) {
+    int b = 0;
+    while ( b < 32 && ( ( cells - 1 ) >> b ) != 0 )
+        b++;
+    return b > 0 ? b : 1;
+}
+
+// One collisions check (reference src/particles_solver.c:197-393), with the pending particlesUpdate fused in.
+static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
+    const size_t n = st->n;
+    if ( n < 2 ) {   // reference :204-205: not even the wall pass runs
+        flush_pending_update( st );
+        return;
+    }
+    refresh_max_radius( st );
+    GridDims G;
+    G.cell_size = 2.0f * st->max_radius;                                // :244
+    G.cols      = (int)ceilf( (float)W / G.cell_size );                 // :247
+    G.rows      = (int)ceilf( (float)H / G.cell_size );                 // :248
+    if ( G.cols < 1 || G.rows < 1 ) {
+        fprintf( stderr, "particlephysicsc_b200: window %ux%u gives an empty grid\n", (unsigned)W, (unsigned)H );
+        abort();
+    }
+    G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
+    ensure_cells( st, G.cells );
+    ensure_scratch( st, radix_scratch_words( n ) + scan_scratch_words( (size_t)G.cells + 1 ) + scan_scratch_words( n + 1 ) + 64 );
+
+    StepParams P    = {};
+    P.do_integrate  = st->pending ? 1 : 0;
+    P.dt_update     = st->pending_dt;
+    P.do_colour     = ( st->pending && st->pending_colour ) ? 1 : 0;
+    P.do_walls_keys = 1;
+    P.wall_w        = (float)(int)W;
+    P.wall_h        = (float)(int)H;
+    P.grid          = G;
+    st->pending     = false;
+
+    ParticleSet &A = st->set[ st->cur ], &B = st->set[ st->cur ^ 1 ];
+    launch_integrate( st, P );                                                         // K1 (+K3 histogram)
+    {
+        StageTimer T( st, ST_SCAN );                                                   // K4 cell-start table
+        exclusive_scan( st->cell_count, st->cell_start, (size_t)G.cells + 1, st->scratch, st->stream );
+    }
+    const uint32_t *slot_of = st->slot_of;
+    {
+        StageTimer T( st, ST_SORT );                                                   // K5
+        if ( st->opt_sort == 1 ) {
+            PPC_CK( cudaMemcpyAsync( st->sort_keys_a, A.key, n * sizeof( uint32_t ), cudaMemcpyDeviceToDevice, st->stream ) );
+            const int where = radix_sort_pairs( st->sort_keys_a, st->slot_of, st->sort_keys_b, st->sort_vals_b, true, n,
+                                                bits_for( G.cells ), st->scratch, st->stream );
+            slot_of         = where ? st->sort_vals_b : st->slot_of;
+        } else {
+            PPC_CK( cudaMemsetAsync( st->cell_count, 0, (size_t)G.cells * sizeof( uint32_t ), st->stream ) );
+            PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, st->cell_count, st->cell_start,
+                        st->slot_of, n );
+        }
+    }
+    {
+        StageTimer T( st, ST_GATHER );                                                 // K6
+        PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
+                    P.do_colour );
+    }
+    st->cur ^= 1;   // B is now the sorted, pre-resolve state
+    ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
+    st->grid       = G;
+    st->grid_valid = true;
+    if ( st->opt_resolve ) {
+        StageTimer T( st, ST_COLLIDE );                                                // K7
+        if ( st->opt_stash )
+            PPC_LAUNCH( k_collide_global<COLLIDE_STASH>, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, S, O.pv,
+                        st->cell_start, n, G, dt );
+        else
+            PPC_LAUNCH( k_collide_global<0>, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G,
+                        dt );
+        float4 *t = S.pv;   // post-resolve positions become current; the pre-resolve ones stay readable in the
+        S.pv      = O.pv;   // other set until the next substep (ppc_debug_pairs uses them)
+        O.pv      = t;
+    }
+    st->pre_valid = true;
+}
+
+static void download( Store *st, struct Particles_t *p, unsigned mask ) {
+    flush_pending_update( st );
+    const size_t n = st->n < p->length ? st->n : p->length;
+    if ( n && mask ) {
+        StageTimer T( st, ST_DOWNLOAD );
+        PPC_LAUNCH( k_unpack_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->api_f[ 0 ],
+                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_col, n, mask );
+        if ( mask & PPC_DL_POS ) {
+            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        }
+        if ( mask & PPC_DL_VEL ) {
+            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        }
+        if ( mask & PPC_DL_COLOR )
+            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
+    }
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+}
+
+static void *pinned_alloc( size_t bytes ) {
+    void *h = nullptr;
+    if ( cudaHostAlloc( &h, bytes ? bytes : 4, cudaHostAllocDefault ) != cudaSuccess || !h ) {
+        fprintf( stderr, "Failed to initialize particles" );   // reference src/particles_arrays.c:149
+        exit( EXIT_FAILURE );
+    }
+    memset( h, 0, bytes );
+    return h;
+}
+
+}   // namespace ppc
+
+using namespace ppc;
+
+// =================================================================================================================
+// Part 1: the reference's entry points
+// =================================================================================================================
+extern "C" struct Particles_t particlesCreate( size_t num_particles_init ) {
+    select_device();
+    struct Particles_t p;
+    p.mass   = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.radius = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.colors = (Color *)pinned_alloc( num_particles_init * sizeof( Color ) );
+    p.p_x    = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.p_y    = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.v_x    = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.v_y    = (float *)pinned_alloc( num_particles_init * sizeof( float ) );
+    p.length = 0;
+    p.size   = num_particles_init;
+    Store *st     = new_store( &p, true );
+    st->dirty_all = false;   // nothing to upload yet: length == 0
+    return p;
+}
+
+extern "C" void particlesFree( struct Particles_t *particles ) {
+    for ( size_t k = 0; k < g_stores.size(); k++ ) {
+        Store *st = g_stores[ k ];
+        if ( st->host_key != particles->mass )
+            continue;
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        free_particle_arrays( st );
+        cudaFree( st->cell_count );
+        cudaFree( st->cell_start );
+        cudaFree( st->d_word );
+        cudaEventDestroy( st->ev0 );
+        cudaEventDestroy( st->ev1 );
+        cudaStreamDestroy( st->stream );
+        if ( st->owns_host ) {
+            cudaFreeHost( particles->mass );
+            cudaFreeHost( particles->radius );
+            cudaFreeHost( particles->colors );
+            cudaFreeHost( particles->p_x );
+            cudaFreeHost( particles->p_y );
+            cudaFreeHost( particles->v_x );
+            cudaFreeHost( particles->v_y );
+        }
+        delete st;
+        g_stores.erase( g_stores.begin() + k );
+        return;
+    }
+    // not ours and never seen by the solver: behave like the reference (src/particles_arrays.c:134-143)
+    free( particles->mass );
+    free( particles->radius );
+    free( particles->colors );
+    free( particles->p_x );
+    free( particles->p_y );
+    free( particles->v_x );
+    free( particles->v_y );
+}
+
+// reference src/particles_arrays.c:196-255: double the seven arrays
+static void grow_arrays( Store *st, struct Particles_t *p ) {
+    size_t new_size = (size_t)( (int)p->size ) * 2;   // ARRAY_GROWTH_FACTOR, includes/constants.h:25
+    if ( new_size < 16 )
+        new_size = 16;
+    if ( !st->owns_host ) {
+        fprintf( stderr, "particlephysicsc_b200: cannot grow arrays that particlesCreate did not allocate\n" );
+        abort();
+    }
+    void  **slots[ 7 ] = { (void **)&p->mass, (void **)&p->radius, (void **)&p->colors, (void **)&p->p_x,
+                           (void **)&p->p_y,  (void **)&p->v_x,    (void **)&p->v_y };
+    for ( int a = 0; a < 7; a++ ) {
+        void *fresh = pinned_alloc( new_size * 4 );
+        memcpy( fresh, *slots[ a ], p->size * 4 );
+        cudaFreeHost( *slots[ a ] );
+        *slots[ a ] = fresh;
+    }
+    p->size      = new_size;
+    st->host_key = p->mass;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    resize_particle_arrays( st, new_size, st->n );
+}
+
+extern "C" void particlesAddParticle( struct Particles_t *particles, const Vector2 particle_i_position, const float particle_i_mass,
+                                      const float particle_i_radius, uint8_t num_particles ) {
+    Store *st = store_of( particles );
+    // reference :260-262 grows once; keep growing until the write below fits (the reference would overrun)
+    if ( particles->length + num_particles >= particles->size )
+        grow_arrays( st, particles );
+    while ( particles->length + num_particles >= particles->size )
+        grow_arrays( st, particles );
+    const Color blue = { 0, 121, 241, 255 };   // Raylib BLUE
+    while ( num_particles-- ) {                // reference :265-277
+        particles->length += 1;
+        const size_t index        = particles->length;
+        particles->mass[ index ]   = particle_i_mass;
+        particles->radius[ index ] = particle_i_radius;
+        particles->colors[ index ] = blue;
+        particles->p_y[ index ]    = (float)particle_i_position.y;
+        particles->v_x[ index ]    = 0.0f;
+        particles->v_y[ index ]    = 0.0f;
+        particles->p_x[ index ]    = (float)particle_i_position.x;
+    }
+    // the device picks the new slots up at the next solver call (absorb_host_changes)
+}
+
+extern "C" void particlesRemoveParticle( struct Particles_t *particles ) {
+    Store *st = store_of( particles );
+    // The particle leaving the processed range keeps its latest state in the host arrays (it re-enters on the
+    // next add, reference :266-269), so bring the host up to date first, then rebuild the mirror from it.
+    if ( !st->dirty_all )
+        download( st, particles, PPC_DL_ALL );
+    const Color  raywhite = { 245, 245, 245, 255 };
+    const size_t index    = particles->length;   // reference :281-290
+    particles->mass[ index ]   = 0.0f;
+    particles->radius[ index ] = 0.0f;
+    particles->colors[ index ] = raywhite;
+    particles->p_y[ index ]    = 0.0f;
+    particles->v_x[ index ]    = 0.0f;
+    particles->v_y[ index ]    = 0.0f;
+    particles->p_x[ index ]    = 0.0f;
+    particles->length -= 1;
+    st->dirty_all = true;
+}
+
+extern "C" void particlesUpdate( struct Particles_t *particles, const float time_step ) {
+    Store *st = store_of( particles );
+    absorb_host_changes( st, particles );
+    flush_pending_update( st );   // two updates in a row: the first one runs on its own
+    st->pending        = true;
+    st->pending_dt     = time_step;
+    st->pending_colour = st->sync_policy != PPC_SYNC_MANUAL || st->colour_wanted;
+    st->colour_wanted  = false;
+    if ( st->sync_policy == PPC_SYNC_EVERY_CALL )
+        download( st, particles, st->dl_mask );
+}
+
+extern "C" void particlesCollisionsCheck_Grid( struct Particles_t *particles, const uint16_t window_width, const uint16_t window_height,
+                                               float time_step ) {
+    Store *st = store_of( particles );
+    absorb_host_changes( st, particles );
+    collide_step( st, window_width, window_height, time_step );
+    if ( st->sync_policy != PPC_SYNC_MANUAL )
+        download( st, particles, st->dl_mask );
+}
+
+// =================================================================================================================
+// Part 2: harness extensions
+// =================================================================================================================
+extern "C" void ppc_set_device( int cuda_device ) { g_device = cuda_device; }
+extern "C" void ppc_set_sync_policy( struct Particles_t *p, int policy ) { store_of( p )->sync_policy = policy; }
+extern "C" void ppc_set_download_mask( struct Particles_t *p, unsigned mask ) { store_of( p )->dl_mask = mask; }
+extern "C" void ppc_request_colors( struct Particles_t *p ) { store_of( p )->colour_wanted = true; }
+extern "C" void ppc_host_modified( struct Particles_t *p ) { store_of( p )->dirty_all = true; }
+extern "C" void ppc_download( struct Particles_t *p, unsigned mask ) {
+    Store *st = store_of( p );
+    absorb_host_changes( st, p );
+    download( st, p, mask );
+}
+extern "C" void ppc_synchronize( struct Particles_t *p ) { PPC_CK( cudaStreamSynchronize( store_of( p )->stream ) ); }
+
+extern "C" void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t window_height, float time_step, int n,
+                                  int color_last ) {
+    Store *st = store_of( p );
+    absorb_host_changes( st, p );
+    for ( int s = 0; s < n; s++ ) {
+        if ( st->n == 0 )   // reference src/main.c:92
+            break;
+        flush_pending_update( st );
+        st->pending        = true;
+        st->pending_dt     = time_step;
+        st->pending_colour = color_last && s == n - 1;
+        collide_step( st, window_width, window_height, time_step );
+    }
+}
+
+extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long long value ) {
+    Store *st = store_of( p );
+    if ( !strcmp( name, "sort" ) )
+        st->opt_sort = (int)value;
+    else if ( !strcmp( name, "stash" ) )
+        st->opt_stash = (int)value;
+    else if ( !strcmp( name, "resolve" ) )
+        st->opt_resolve = (int)value;
+    else if ( !strcmp( name, "collide" ) )
+        st->opt_collide = (int)value;
+    else
+        return -1;
+    return 0;
+}
+
+extern "C" int ppc_debug_grid_info( struct Particles_t *p, ppc_grid_info *out ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid )
+        return -1;
+    out->max_radius = st->max_radius;
+    out->cell_size  = st->grid.cell_size;
+    out->cols       = st->grid.cols;
+    out->rows       = st->grid.rows;
+    out->cells      = st->grid.cells;
+    out->n          = st->n;
+    return 0;
+}
+
+extern "C" int ppc_debug_keys( struct Particles_t *p, uint32_t *keys_by_index ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid )
+        return -1;
+    PPC_LAUNCH( k_export_keys, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->slot_of, st->n );
+    PPC_CK( cudaMemcpyAsync( keys_by_index, st->slot_of, st->n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    return 0;
+}
+
+extern "C" int ppc_debug_sorted_order( struct Particles_t *p, uint32_t *order ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid )
+        return -1;
+    PPC_CK( cudaMemcpyAsync( order, st->set[ st->cur ].gid, st->n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    return 0;
+}
+
+extern "C" int ppc_debug_cell_start( struct Particles_t *p, uint32_t *cell_start ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid )
+        return -1;
+    PPC_CK( cudaMemcpyAsync( cell_start, st->cell_start, ( (size_t)st->grid.cells + 1 ) * sizeof( uint32_t ), cudaMemcpyDeviceToHost,
+                             st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    return 0;
+}
+
+extern "C" int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid || !st->pre_valid )
+        return -1;
+    const size_t n   = st->n;
+    ParticleSet  pre = st->set[ st->cur ];
+    if ( st->opt_resolve )
+        pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw (before the resolve moved anything)
+    uint32_t *count  = st->sort_keys_a;       // n + 1 words needed; sort_keys_a has cap >= n, use scratch when tight
+    uint32_t *offset = st->sort_keys_b;
+    uint32_t *tmp    = nullptr;
+    if ( n + 1 > st->cap ) {
+        tmp    = dev_alloc<uint32_t>( 2 * ( n + 1 ) );
+        count  = tmp;
+        offset = tmp + n + 1;
+    }
+    PPC_CK( cudaMemsetAsync( count, 0, ( n + 1 ) * sizeof( uint32_t ), st->stream ) );
+    PPC_LAUNCH( k_pairs_count, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, pre, st->cell_start, n, st->grid, count );
+    exclusive_scan( count, offset, n + 1, st->scratch, st->stream );
+    uint32_t total = 0;
+    PPC_CK( cudaMemcpyAsync( &total, offset + n, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    if ( pairs && max_pairs && total ) {
+        const size_t keep  = total < max_pairs ? total : max_pairs;
+        int32_t     *d_out = (int32_t *)dev_alloc<int32_t>( 2 * keep );
+        PPC_LAUNCH( k_pairs_emit, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, pre, st->cell_start, n, st->grid, offset,
+                    d_out, keep );
+        PPC_CK( cudaMemcpyAsync( pairs, d_out, 2 * keep * sizeof( int32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        cudaFree( d_out );
+    }
+    cudaFree( tmp );
+    return (int64_t)total;
+}
+
+extern "C" void              *ppc_stream( struct Particles_t *p ) { return (void *)store_of( p )->stream; }
+extern "C" unsigned long long ppc_kernel_launches( void ) { return g_launches; }
+extern "C" void               ppc_profile( struct Particles_t *p, int enable ) { store_of( p )->profiling = enable != 0; }
+extern "C" int                ppc_profile_stages( void ) { return ST_COUNT; }
+extern "C" const char        *ppc_profile_stage_name( int stage ) { return stage >= 0 && stage < ST_COUNT ? k_stage_names[ stage ] : ""; }
+extern "C" int ppc_profile_read( struct Particles_t *p, int stage, double *total_ms, unsigned long long *launches ) {
+    Store *st = store_of( p );
+    if ( stage < 0 || stage >= ST_COUNT )
+        return -1;
+    *total_ms = st->stage_ms[ stage ];
+    *launches = st->stage_launches[ stage ];
+    return 0;
+}
+extern "C" void ppc_profile_reset( struct Particles_t *p ) {
+    Store *st = store_of( p );
+    for ( int s = 0; s < ST_COUNT; s++ ) {
+        st->stage_ms[ s ]       = 0;
+        st->stage_launches[ s ] = 0;
+    }
+}
+extern "C" const char *ppc_version( void ) { return "particlephysicsc_b200 0.1 (sm_100a)"; }

@@ -135,12 +135,15 @@ def jittered_lattice(n: int, radius: float = 2.0, phi: float = 0.30, seed: int =
 
 
 def polydisperse_pile(n: int, rmin: float = 1.5, rmax: float = 6.0, W: int = 31500, H: int = 40000, seed: int = 0x5EED0003,
-                      classes: int = 16, vmax: float = 0.0, name: str = "pile") -> Scene:
-    """Config 3 starting field: radii uniform in [rmin, rmax] (ratio 1:4), packed bottom-up (y grows
-    downward, reference includes/constants.h:15) in bands of similar size on jittered hex lattices, densest
-    band lowest.  The GPU solver then settles it; the settled state is what gets benchmarked.
+                      classes: int = 64, compress: float = 0.99, vmax: float = 0.0, name: str = "pile") -> Scene:
+    """Config 3 field: radii uniform in [rmin, rmax] (ratio 1:4) packed bottom-up (y grows downward, reference
+    includes/constants.h:15) as a dense pile resting on the bottom wall.  Particles are grouped into narrow size
+    classes, largest lowest; each class fills jittered hex-lattice rows whose pitch is ``compress`` x the class's
+    mean diameter, so neighbours touch or overlap by about a percent -- the contact network of a pile under its own
+    weight (area fraction ~0.8).  The solver then relaxes it during the settle/warm-up substeps; the relaxed state
+    is what gets benchmarked.
 
-    For smaller n the default box is scaled down at constant aspect so the pile still fills ~88% of it.
+    For n other than 2**24 the default box is scaled at constant aspect so the pile fills the same share of it.
     """
     rng = Stream(seed)
     radius = (np.float32(rmin) + rng.unit(n) * np.float32(rmax - rmin)).astype(np.float32)
@@ -155,20 +158,20 @@ def polydisperse_pile(n: int, rmin: float = 1.5, rmax: float = 6.0, W: int = 315
         members = order[edges[c]:edges[c + 1]]
         if members.size == 0:
             continue
-        rc = float(radius[members].max())
-        pitch = 2.0 * rc * 1.02
+        rc, rmean = float(radius[members].max()), float(radius[members].mean())
+        pitch = 2.0 * rmean * compress
         per_row = max(1, int((W - 2 * rc) // pitch))
         rows = int(math.ceil(members.size / per_row))
         row_h = pitch * math.sqrt(3.0) / 2.0
         k = np.arange(members.size)
         row, col = k // per_row, k % per_row
-        jit = np.float32(0.2 * (pitch - 2.0 * rc))
-        x = rc + (col + 0.5 * (row % 2)) * pitch + 0.5 * pitch
+        jit = np.float32(0.05 * rmean)
+        x = rc + (col + 0.5 * (row % 2)) * pitch
         x = np.minimum(x, W - rc)
         y = y_floor - rc - row * row_h
         px[members] = x.astype(np.float32) + (rng.unit(members.size) - np.float32(0.5)) * jit
         py[members] = y.astype(np.float32) + (rng.unit(members.size) - np.float32(0.5)) * jit
-        y_floor -= rows * row_h + rc * 0.3
+        y_floor -= (rows - 1) * row_h + 2.0 * rc * compress
     if y_floor < 0:
         raise ValueError("pile does not fit the box")
     return _finish(name, W, H, px, py, radius, rng, vmax)
