@@ -156,6 +156,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     sc = make_scene(args.workload, n, seed_offset=0x100 * rank)
     p = api.Particles(n, device=local_rank)
     p.set_sync_policy(api.PPC_SYNC_MANUAL)
+    p.set_option("resolve", args.resolve)
     p.fill(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba)
     W, H = sc.W, sc.H
     torch.cuda.set_device(local_rank)
@@ -245,6 +246,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "data": "synthetic",
                 "config": {"workload": descr, "particles_per_gpu": n, "box": [W, H], "dt": DT, "grid": [g.cols, g.rows],
                            "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
+                           "resolve": {1: "sequential-equivalent wavefront (bit-exact)", 2: "jacobi"}.get(args.resolve, str(args.resolve)),
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n / 1e6),
                            "parallelism": "independent replicas" if world > 1 else "single GPU"},
                 "roofline": roofline,
@@ -270,6 +272,7 @@ def main():
     ap.add_argument("--workload", default="uniform16m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

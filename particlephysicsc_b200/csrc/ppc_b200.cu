@@ -26,9 +26,9 @@
 namespace ppc {
 unsigned long long g_launches = 0;
 
-enum Stage { ST_INTEGRATE = 0, ST_SCAN, ST_SORT, ST_GATHER, ST_COLLIDE, ST_UPLOAD, ST_DOWNLOAD, ST_MISC, ST_COUNT };
+enum Stage { ST_INTEGRATE = 0, ST_SCAN, ST_SORT, ST_GATHER, ST_COLLIDE, ST_WAVEFRONT, ST_UPLOAD, ST_DOWNLOAD, ST_MISC, ST_COUNT };
 static const char *k_stage_names[ ST_COUNT ] = { "integrate_walls_keys", "cell_scan", "cell_sort", "canonical_gather",
-                                                 "collide",              "upload",    "download",  "misc" };
+                                                 "collide",              "resolve_wavefront", "upload", "download", "misc" };
 
 struct Store {
     // identity / host side
@@ -43,7 +43,7 @@ struct Store {
     int      sync_policy   = PPC_SYNC_FRAME;
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
-    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0;
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -60,6 +60,9 @@ struct Store {
     uint32_t    *scratch = nullptr;
     size_t       scratch_words = 0;
     uint32_t    *d_word = nullptr;   // one word for small reductions
+    WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
+    size_t       wave_cap = 0;
+    int          wave_grid = 0;
     // last grid
     bool     grid_valid = false, pre_valid = false;
     GridDims grid = {};
@@ -116,7 +119,57 @@ struct StageTimer {
 };
 
 // ---- device storage -------------------------------------------------------------------------------------------
+static void free_wave_buffers( Store *st ) {
+    cudaFree( st->wave.deg );
+    cudaFree( st->wave.state );
+    cudaFree( st->wave.inc );
+    cudaFree( st->wave.list[ 0 ] );
+    cudaFree( st->wave.list[ 1 ] );
+    cudaFree( st->wave.counters );
+    st->wave     = WaveBuffers{};
+    st->wave_cap = 0;
+}
+
+static void ensure_wave_buffers( Store *st ) {
+    if ( st->wave_cap >= st->cap && st->wave.deg )
+        return;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    free_wave_buffers( st );
+    const size_t cap    = st->cap ? st->cap : 1;
+    st->wave.deg        = dev_alloc<uint16_t>( cap );
+    st->wave.state      = dev_alloc<uint32_t>( cap );
+    st->wave.inc        = dev_alloc<uint32_t>( cap * (size_t)INC_MAXDEG );
+    st->wave.stride     = cap;
+    st->wave.list[ 0 ]  = dev_alloc<uint32_t>( cap );
+    st->wave.list[ 1 ]  = dev_alloc<uint32_t>( cap );
+    st->wave.counters   = dev_alloc<uint32_t>( 4 );
+    st->wave_cap        = cap;
+    PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 4 * sizeof( uint32_t ), st->stream ) );
+    int per_sm = 0, sms = 0, dev = 0;
+    PPC_CK( cudaGetDevice( &dev ) );
+    PPC_CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
+    PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_wavefront, WAVE_THREADS, 0 ) );
+    if ( per_sm < 1 ) {
+        fprintf( stderr, "particlephysicsc_b200: wavefront kernel cannot be made resident\n" );
+        abort();
+    }
+    st->wave_grid = per_sm * sms;
+}
+
+static void check_device_flags( Store *st ) {   // after a stream synchronise
+    if ( !st->wave.counters )
+        return;
+    uint32_t flags = 0;
+    PPC_CK( cudaMemcpy( &flags, st->wave.counters + 3, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
+    if ( flags ) {
+        fprintf( stderr, "particlephysicsc_b200: resolve failed (%s%s)\n", ( flags & 1u ) ? "a particle has more than 4095 simultaneous contacts " : "",
+                 ( flags & 2u ) ? "pair dependency chain longer than 2^20 rounds" : "" );
+        abort();
+    }
+}
+
 static void free_particle_arrays( Store *st ) {
+    free_wave_buffers( st );
     for ( int s = 0; s < 2; s++ ) {
         cudaFree( st->set[ s ].pv );
         cudaFree( st->set[ s ].rm );
@@ -182,6 +235,7 @@ static void resize_particle_arrays( Store *st, size_t cap, size_t keep ) {
     st->sort_vals_b = dev_alloc<uint32_t>( cap );
     st->cap         = cap;
     st->pre_valid   = false;
+    free_wave_buffers( st );
 }
 
 static void ensure_scratch( Store *st, size_t words ) {
@@ -392,15 +446,38 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     st->grid       = G;
     st->grid_valid = true;
     if ( st->opt_resolve ) {
-        StageTimer T( st, ST_COLLIDE );                                                // K7
-        if ( st->opt_stash )
-            PPC_LAUNCH( k_collide_global<COLLIDE_STASH>, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, S, O.pv,
-                        st->cell_start, n, G, dt );
-        else
-            PPC_LAUNCH( k_collide_global<0>, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G,
-                        dt );
-        float4 *t = S.pv;   // post-resolve positions become current; the pre-resolve ones stay readable in the
-        S.pv      = O.pv;   // other set until the next substep (ppc_debug_pairs uses them)
+        const bool jacobi = st->opt_resolve == 2;
+        if ( !jacobi ) {
+            ensure_wave_buffers( st );
+            PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
+        }
+        const WaveBuffers WB = st->wave;
+        {
+            StageTimer T( st, ST_COLLIDE );                                            // K7: narrow phase + position pushes
+            const unsigned blocks = div_up( n, COLLIDE_THREADS );
+            if ( jacobi && st->opt_stash )
+                PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
+            else if ( jacobi )
+                PPC_LAUNCH( ( k_collide_global<0, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
+            else if ( st->opt_stash )
+                PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
+            else
+                PPC_LAUNCH( ( k_collide_global<0, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
+        }
+        if ( !jacobi ) {
+            StageTimer T( st, ST_WAVEFRONT );                                          // K7b: velocities, in the reference's pair order
+            float4        *pv_out = O.pv;
+            const uint32_t *cs    = st->cell_start;
+            int             grid  = st->wave_grid;
+            const int       want  = (int)div_up( n, WAVE_THREADS );
+            if ( grid > want )
+                grid = want;
+            void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&G, (void *)&dt, (void *)&WB };
+            PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_wavefront, dim3( grid ), dim3( WAVE_THREADS ), args, 0, st->stream ) );
+            ++g_launches;
+        }
+        float4 *t = S.pv;   // post-resolve state becomes current; the pre-resolve one stays readable in the other
+        S.pv      = O.pv;   // set until the next substep (ppc_debug_pairs uses it)
         O.pv      = t;
     }
     st->pre_valid = true;
@@ -425,6 +502,7 @@ static void download( Store *st, struct Particles_t *p, unsigned mask ) {
             PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
     }
     PPC_CK( cudaStreamSynchronize( st->stream ) );
+    check_device_flags( st );
 }
 
 static void *pinned_alloc( size_t bytes ) {
@@ -596,7 +674,11 @@ extern "C" void ppc_download( struct Particles_t *p, unsigned mask ) {
     absorb_host_changes( st, p );
     download( st, p, mask );
 }
-extern "C" void ppc_synchronize( struct Particles_t *p ) { PPC_CK( cudaStreamSynchronize( store_of( p )->stream ) ); }
+extern "C" void ppc_synchronize( struct Particles_t *p ) {
+    Store *st = store_of( p );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    check_device_flags( st );
+}
 
 extern "C" void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t window_height, float time_step, int n,
                                   int color_last ) {
@@ -682,9 +764,10 @@ extern "C" int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_
     uint32_t *offset = st->sort_keys_b;
     uint32_t *tmp    = nullptr;
     if ( n + 1 > st->cap ) {
-        tmp    = dev_alloc<uint32_t>( 2 * ( n + 1 ) );
+        const size_t padded = ( n + 1 + 63 ) & ~(size_t)63;   // the scan reads and writes 128-bit vectors: keep both bases aligned
+        tmp    = dev_alloc<uint32_t>( 2 * padded );
         count  = tmp;
-        offset = tmp + n + 1;
+        offset = tmp + padded;
     }
     PPC_CK( cudaMemsetAsync( count, 0, ( n + 1 ) * sizeof( uint32_t ), st->stream ) );
     PPC_LAUNCH( k_pairs_count, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, pre, st->cell_start, n, st->grid, count );

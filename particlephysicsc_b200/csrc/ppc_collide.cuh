@@ -2,7 +2,7 @@
 //
 // Input is the cell-sorted particle set of this substep (storage order = ascending (cell key, API index)) plus the
 // cell-start table.  Each thread owns ONE particle and gathers the contributions of all its contacts, so there are
-// no atomics and no write conflicts: the result is deterministic, run to run and across GPU counts.
+// no atomics on particle data and no write conflicts: the result is deterministic, run to run and across GPU counts.
 //
 // Relation to the reference (src/particles_solver.c):
 //  * The candidate set is the reference's: 3x3 neighbourhood of the particle's cell (:331-340), the AABB reject
@@ -13,17 +13,31 @@
 //    the order the reference's pair list would touch this particle -- first the pairs in which it is j (ascending
 //    i), then the pairs in which it is i (neighbour cells dy-major / dx-minor, members in descending index,
 //    :311-383) -- which makes positions bit-identical to the reference's sequential loop.
-//  * Velocity impulses (:158-190) are evaluated Jacobi-style: every pair reads the velocities the resolve started
-//    with, whereas the reference lets earlier pairs of the list feed later ones (Gauss-Seidel).  Summation order is
-//    the same list order.  oracle/ppc_oracle.c:ppc_oracle_resolve_jacobi is the CPU model of exactly this.
+//  * Velocity impulses (:158-190) are order dependent in the reference: every pair reads the velocities left by the
+//    pairs before it in the list (Gauss-Seidel).  Two resolve modes:
+//      - SEQUENTIAL-EQUIVALENT (default): k_collide_* records, per particle, its contacts in list order; then
+//        k_resolve_wavefront fires, round by round, every pair that is at the head of BOTH its particles' lists.
+//        Two pairs that share a particle never fire in the same round, and a pair fires only after all earlier pairs
+//        of both particles have: the schedule is a topological order of the reference's dependency graph, so every
+//        pair sees exactly the velocities it sees in the reference.  Velocities are bit-identical to the reference.
+//      - JACOBI: every pair reads the velocities the resolve started with; one pass, no rounds.  Matches the
+//        reference statistically while particles have at most a few simultaneous contacts, diverges in dense packings.
+//        oracle/ppc_oracle.c:ppc_oracle_resolve_jacobi is the CPU model of exactly this.
 #pragma once
 #include "ppc_common.cuh"
 #include "ppc_math.cuh"
 
+#include <cooperative_groups.h>
+
 namespace ppc {
 
-constexpr int COLLIDE_THREADS = 128;
-constexpr int COLLIDE_STASH   = 24;   // contacts kept per thread before falling back to the streaming path
+constexpr int      COLLIDE_THREADS = 128;
+constexpr int      COLLIDE_STASH   = 24;    // contacts kept per thread before falling back to the streaming path
+constexpr int      INC_MAXDEG      = 16;    // contacts per particle stored for the wavefront; above: recomputed on demand
+constexpr uint32_t INC_LO_FLAG     = 0x80000000u;   // this particle is the pair's i (lower API index)
+constexpr uint32_t PC_BITS         = 12;    // wavefront state word: (round << 12) | contacts already resolved
+constexpr uint32_t PC_MASK         = ( 1u << PC_BITS ) - 1u;
+constexpr int      WAVE_THREADS    = 256;
 
 struct Cand {
     float    x, y, r;
@@ -52,7 +66,8 @@ struct GlobalAccessor {
         vy             = s.w;
         m              = rm[ q ].y;
     }
-    __device__ __forceinline__ void cell_range( const uint32_t c, uint32_t &b, uint32_t &e ) const {
+    __device__ __forceinline__ float mass( const uint32_t q ) const { return rm[ q ].y; }
+    __device__ __forceinline__ void  cell_range( const uint32_t c, uint32_t &b, uint32_t &e ) const {
         b = cell_start[ c ];
         e = cell_start[ c + 1 ];
     }
@@ -91,42 +106,15 @@ __device__ __forceinline__ bool in_contact( const Self &me, const Cand &c ) {
     return overlaps( dx, dy, __fadd_rn( me.r, c.r ) );
 }
 
-template <class Acc>
-__device__ __forceinline__ void apply_contact( const Acc &acc, const Self &me, const uint32_t q, const float dt, float4 &out ) {
-    const Cand c = acc.geom( q );
-    float      qvx, qvy, qm;
-    acc.dyn( q, qvx, qvy, qm );
-    if ( me.gid < c.gid ) {   // this particle is the pair's i
-        const PairTerms T = pair_terms( me.x, me.y, me.r, me.m, me.vx, me.vy, c.x, c.y, c.r, qm, qvx, qvy, dt );
-        if ( T.push ) {
-            out.x = __fadd_rn( out.x, T.dpx_lo );
-            out.y = __fadd_rn( out.y, T.dpy_lo );
-        }
-        if ( T.impulse ) {
-            out.z = __fadd_rn( out.z, T.dvx_lo );
-            out.w = __fadd_rn( out.w, T.dvy_lo );
-        }
-    } else {   // this particle is the pair's j
-        const PairTerms T = pair_terms( c.x, c.y, c.r, qm, qvx, qvy, me.x, me.y, me.r, me.m, me.vx, me.vy, dt );
-        if ( T.push ) {
-            out.x = __fsub_rn( out.x, T.dpx_hi );
-            out.y = __fsub_rn( out.y, T.dpy_hi );
-        }
-        if ( T.impulse ) {
-            out.z = __fsub_rn( out.z, T.dvx_hi );
-            out.w = __fsub_rn( out.w, T.dvy_hi );
-        }
-    }
-}
-
-// Resolve every contact of one particle.  Returns its (p_x, p_y, v_x, v_y) after the resolve.
-template <class Acc, int STASH>
-__device__ float4 resolve_particle( const Acc &acc, const GridDims &G, const Self &me, const uint32_t key, const float dt ) {
+// Call sink(q) for every contact of `me`, in the order the reference's pair list touches this particle:
+// pairs (i, me) with i < me by ascending i, then pairs (me, j) in scan order.
+template <class Acc, int STASH, class Sink>
+__device__ __forceinline__ void for_each_contact_in_list_order( const Acc &acc, const GridDims &G, const Self &me, const uint32_t key,
+                                                                Sink &&sink ) {
     const int cy = (int)( key / (uint32_t)G.cols ), cx = (int)( key - (uint32_t)cy * (uint32_t)G.cols );
-    float4    out = make_float4( me.x, me.y, me.vx, me.vy );
 
-    // One sweep in reference order.  Contacts in which this particle is i go to the front of the stash in the
-    // order met (already the list order); contacts in which it is j go to the back and are sorted by index.
+    // One sweep in scan order.  Contacts in which this particle is i go to the front of the stash in the order met
+    // (already the list order); contacts in which it is j go to the back and are sorted by index afterwards.
     uint32_t stash_q[ STASH > 0 ? STASH : 1 ], stash_g[ STASH > 0 ? STASH : 1 ];
     int      n_i = 0, n_j = 0;
     bool     overflow = false;
@@ -150,24 +138,22 @@ __device__ float4 resolve_particle( const Acc &acc, const GridDims &G, const Sel
     } );
 
     if ( !overflow ) {
-        // pairs (i, me) with i < me come first in the reference list, by ascending i
-        for ( int a = 0; a < n_j; a++ ) {
-            int best = STASH - n_j + a;
-            for ( int b = best + 1; b < STASH; b++ )
+        for ( int a = 0; a < n_j; a++ ) {   // selection sort of the j-role contacts by ascending index
+            const int at   = STASH - n_j + a;
+            int       best = at;
+            for ( int b = at + 1; b < STASH; b++ )
                 if ( stash_g[ b ] < stash_g[ best ] )
                     best = b;
-            const int      at = STASH - n_j + a;
             const uint32_t tq = stash_q[ best ], tg = stash_g[ best ];
             stash_q[ best ] = stash_q[ at ];
             stash_g[ best ] = stash_g[ at ];
             stash_q[ at ]   = tq;
             stash_g[ at ]   = tg;
-            apply_contact( acc, me, tq, dt, out );
+            sink( tq );
         }
-        // then pairs (me, j) in scan order
         for ( int a = 0; a < n_i; a++ )
-            apply_contact( acc, me, stash_q[ a ], dt, out );
-        return out;
+            sink( stash_q[ a ] );
+        return;
     }
 
     // Streaming path for particles with more contacts than the stash holds (e.g. the coincident 10-particle
@@ -190,7 +176,7 @@ __device__ float4 resolve_particle( const Acc &acc, const GridDims &G, const Sel
         } );
         if ( !found )
             break;
-        apply_contact( acc, me, best_q, dt, out );
+        sink( best_q );
         have_last = true;
         last      = best_g;
     }
@@ -198,9 +184,96 @@ __device__ float4 resolve_particle( const Acc &acc, const GridDims &G, const Sel
         const Cand c = acc.geom( q );
         if ( c.gid <= me.gid || !in_contact( me, c ) )
             return;
-        apply_contact( acc, me, q, dt, out );
+        sink( q );
     } );
-    return out;
+}
+
+// The c-th entry (0-based) of a particle's contact list, recomputed from the neighbourhood.  Used by the wavefront
+// only for particles with more than INC_MAXDEG contacts, whose list is not stored.  Returns slot | INC_LO_FLAG if
+// the particle is the pair's i.  Cost O((c + 2) x candidates).
+template <class Acc>
+__device__ uint32_t nth_contact( const Acc &acc, const GridDims &G, const Self &me, const uint32_t key, const uint32_t c ) {
+    const int cy = (int)( key / (uint32_t)G.cols ), cx = (int)( key - (uint32_t)cy * (uint32_t)G.cols );
+    uint32_t  n_j = 0;
+    for_each_candidate( acc, G, cx, cy, [ & ]( const uint32_t q ) {
+        const Cand k = acc.geom( q );
+        if ( k.gid < me.gid && in_contact( me, k ) )
+            n_j++;
+    } );
+    if ( c < n_j ) {
+        bool     have_last = false;
+        uint32_t last = 0, best_q = 0;
+        for ( uint32_t t = 0; t <= c; t++ ) {
+            bool     found  = false;
+            uint32_t best_g = 0;
+            for_each_candidate( acc, G, cx, cy, [ & ]( const uint32_t q ) {
+                const Cand k = acc.geom( q );
+                if ( k.gid >= me.gid || ( have_last && k.gid <= last ) || ( found && k.gid >= best_g ) )
+                    return;
+                if ( !in_contact( me, k ) )
+                    return;
+                found  = true;
+                best_q = q;
+                best_g = k.gid;
+            } );
+            have_last = true;
+            last      = best_g;
+        }
+        return best_q;
+    }
+    uint32_t seen = 0, hit = 0;
+    for_each_candidate( acc, G, cx, cy, [ & ]( const uint32_t q ) {
+        const Cand k = acc.geom( q );
+        if ( k.gid <= me.gid || !in_contact( me, k ) )
+            return;
+        if ( seen == c - n_j )
+            hit = q;
+        seen++;
+    } );
+    return hit | INC_LO_FLAG;
+}
+
+// position push of one contact onto `me` (:145-156)
+template <class Acc>
+__device__ __forceinline__ void apply_push( const Acc &acc, const Self &me, const uint32_t q, const float dt, float4 &out ) {
+    const Cand  c  = acc.geom( q );
+    const float qm = acc.mass( q );
+    if ( me.gid < c.gid ) {   // this particle is the pair's i
+        const PushTerms T = push_terms( contact_geom( me.x, me.y, me.r, c.x, c.y, c.r, dt ), inv_mass_u8( me.m ), inv_mass_u8( qm ) );
+        if ( T.push ) {
+            out.x = __fadd_rn( out.x, T.dpx_lo );
+            out.y = __fadd_rn( out.y, T.dpy_lo );
+        }
+    } else {   // this particle is the pair's j
+        const PushTerms T = push_terms( contact_geom( c.x, c.y, c.r, me.x, me.y, me.r, dt ), inv_mass_u8( qm ), inv_mass_u8( me.m ) );
+        if ( T.push ) {
+            out.x = __fsub_rn( out.x, T.dpx_hi );
+            out.y = __fsub_rn( out.y, T.dpy_hi );
+        }
+    }
+}
+
+// Jacobi velocity impulse of one contact onto `me`, from the velocities the resolve started with
+template <class Acc>
+__device__ __forceinline__ void apply_impulse_frozen( const Acc &acc, const Self &me, const uint32_t q, const float dt, float4 &out ) {
+    const Cand c = acc.geom( q );
+    float      qvx, qvy, qm;
+    acc.dyn( q, qvx, qvy, qm );
+    if ( me.gid < c.gid ) {
+        const ImpulseTerms T = impulse_terms( contact_geom( me.x, me.y, me.r, c.x, c.y, c.r, dt ), inv_mass_u8( me.m ), inv_mass_u8( qm ),
+                                              me.vx, me.vy, qvx, qvy );
+        if ( T.impulse ) {
+            out.z = __fadd_rn( out.z, T.dvx_lo );
+            out.w = __fadd_rn( out.w, T.dvy_lo );
+        }
+    } else {
+        const ImpulseTerms T = impulse_terms( contact_geom( c.x, c.y, c.r, me.x, me.y, me.r, dt ), inv_mass_u8( qm ), inv_mass_u8( me.m ),
+                                              qvx, qvy, me.vx, me.vy );
+        if ( T.impulse ) {
+            out.z = __fsub_rn( out.z, T.dvx_hi );
+            out.w = __fsub_rn( out.w, T.dvy_hi );
+        }
+    }
 }
 
 __device__ __forceinline__ Self load_self( const ParticleSet &S, const size_t k ) {
@@ -217,17 +290,159 @@ __device__ __forceinline__ Self load_self( const ParticleSet &S, const size_t k 
     return me;
 }
 
+// Per-particle bookkeeping of the sequential-equivalent resolve.
+struct WaveBuffers {
+    uint16_t *deg;       // contacts of each particle (sorted slot)
+    uint32_t *state;     // (round of last advance << PC_BITS) | contacts already resolved
+    uint32_t *inc;       // inc[c * stride + k] = c-th contact of particle k: partner slot | INC_LO_FLAG
+    size_t    stride;    // particle capacity
+    uint32_t *list[ 2 ]; // active-particle lists (ping-pong between rounds)
+    uint32_t *counters;  // [0..2] rotating list lengths, [3] error flags
+};
+
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
-template <int STASH>
+// JACOBI = true : positions and velocities in one pass (velocities from frozen values).
+// JACOBI = false: positions only; the contact list goes to the wavefront buffers and particles with contacts are
+//                 appended to the first active list.
+template <int STASH, bool JACOBI>
 __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const ParticleSet S, float4 *__restrict__ pv_out,
                                                                        const uint32_t *__restrict__ cell_start, const size_t n,
-                                                                       const GridDims G, const float dt ) {
-    const size_t k = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
-    if ( k >= n )
-        return;
-    const Self           me = load_self( S, k );
+                                                                       const GridDims G, const float dt, const WaveBuffers WB ) {
+    const size_t   k     = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
+    const bool     valid = k < n;
+    const unsigned lane  = threadIdx.x & 31u;
+    uint32_t       cnt   = 0;
+    if ( valid ) {
+        const Self           me = load_self( S, k );
+        const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
+        float4               out = make_float4( me.x, me.y, me.vx, me.vy );
+        for_each_contact_in_list_order<GlobalAccessor, STASH>( acc, G, me, S.key[ k ], [ & ]( const uint32_t q ) {
+            apply_push( acc, me, q, dt, out );
+            if ( JACOBI ) {
+                apply_impulse_frozen( acc, me, q, dt, out );
+            } else {
+                if ( cnt < (uint32_t)INC_MAXDEG )
+                    WB.inc[ (size_t)cnt * WB.stride + k ] = q | ( me.gid < acc.gid[ q ] ? INC_LO_FLAG : 0u );
+                cnt++;
+            }
+        } );
+        pv_out[ k ] = out;
+        if ( !JACOBI ) {
+            if ( cnt > PC_MASK ) {   // more simultaneous contacts than the state word can count
+                atomicOr( &WB.counters[ 3 ], 1u );
+                cnt = PC_MASK;
+            }
+            WB.deg[ k ]   = (uint16_t)cnt;
+            WB.state[ k ] = 0u;
+        }
+    }
+    if ( !JACOBI ) {   // warp-aggregated append of the particles that have contacts
+        const unsigned active = __ballot_sync( 0xffffffffu, valid && cnt > 0 );
+        if ( active ) {
+            const unsigned leader = (unsigned)( __ffs( active ) - 1 );
+            uint32_t       base   = 0;
+            if ( lane == leader )
+                base = atomicAdd( &WB.counters[ 0 ], (uint32_t)__popc( active ) );
+            base = __shfl_sync( 0xffffffffu, base, leader );
+            if ( valid && cnt > 0 )
+                WB.list[ 0 ][ base + (uint32_t)__popc( active & ( ( 1u << lane ) - 1u ) ) ] = (uint32_t)k;
+        }
+    }
+}
+
+// ---- K7b: sequential-equivalent velocity resolve, as a wavefront over the pair dependency graph ----------------
+// Cooperative launch (all CTAs co-resident).  Round r: every still-active particle looks at the head of its contact
+// list; if it is the pair's i and the partner's head is this very pair -- and neither particle was advanced earlier
+// in this round -- it fires the pair: impulse of :158-190 from the CURRENT velocities, both particles advance.
+// Particles with contacts left go to the next round's list.  One grid barrier per round; the number of rounds is
+// the depth of the reference's pair dependency graph.
+__device__ __forceinline__ uint32_t head_contact( const ParticleSet &S, const GlobalAccessor &acc, const GridDims &G, const WaveBuffers &WB,
+                                                  const uint32_t k, const uint32_t pc, const uint32_t deg ) {
+    if ( deg <= (uint32_t)INC_MAXDEG )
+        return WB.inc[ (size_t)pc * WB.stride + k ];
+    return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
+}
+
+__global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const ParticleSet S, float4 *pv_out,
+                                                                       const uint32_t *__restrict__ cell_start, const GridDims G,
+                                                                       const float dt, const WaveBuffers WB ) {
+    namespace cg            = cooperative_groups;
+    cg::grid_group grid     = cg::this_grid();
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
-    pv_out[ k ] = resolve_particle<GlobalAccessor, STASH>( acc, G, me, S.key[ k ], dt );
+    const unsigned       lane        = threadIdx.x & 31u;
+    const size_t         warp_global = ( (size_t)blockIdx.x * WAVE_THREADS + threadIdx.x ) >> 5;
+    const size_t         warps_total = ( (size_t)gridDim.x * WAVE_THREADS ) >> 5;
+    volatile uint32_t   *counters    = WB.counters;
+
+    for ( uint32_t r = 1;; r++ ) {
+        const uint32_t n_active = counters[ ( r - 1 ) % 3 ];
+        if ( n_active == 0 )
+            break;
+        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {   // round stamp would overflow: flag and stop
+            if ( blockIdx.x == 0 && threadIdx.x == 0 )
+                atomicOr( &WB.counters[ 3 ], 2u );
+            break;
+        }
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            counters[ ( r + 1 ) % 3 ] = 0;
+        const uint32_t *src   = WB.list[ ( r - 1 ) & 1 ];
+        uint32_t       *dst   = WB.list[ r & 1 ];
+        uint32_t       *d_cnt = &WB.counters[ r % 3 ];
+
+        for ( size_t t0 = warp_global * 32; t0 < n_active; t0 += warps_total * 32 ) {
+            const size_t t    = t0 + lane;
+            bool         keep = false;
+            uint32_t     me   = 0;
+            if ( t < n_active ) {
+                me                 = src[ t ];
+                const uint32_t w   = __ldcg( &WB.state[ me ] );
+                const uint32_t pc  = w & PC_MASK;
+                const uint32_t deg = WB.deg[ me ];
+                if ( pc < deg ) {
+                    keep = true;
+                    if ( ( w >> PC_BITS ) != r ) {
+                        const uint32_t entry = head_contact( S, acc, G, WB, me, pc, deg );
+                        if ( entry & INC_LO_FLAG ) {   // this particle is the pair's i: it executes the pair
+                            const uint32_t q    = entry & ~INC_LO_FLAG;
+                            const uint32_t wq   = __ldcg( &WB.state[ q ] );
+                            const uint32_t pcq  = wq & PC_MASK;
+                            const uint32_t degq = WB.deg[ q ];
+                            if ( ( wq >> PC_BITS ) != r && pcq < degq && head_contact( S, acc, G, WB, q, pcq, degq ) == me ) {
+                                const Self a = load_self( S, me ), b = load_self( S, q );   // frozen geometry (pass 1)
+                                float2    *va = reinterpret_cast<float2 *>( pv_out + me ) + 1;
+                                float2    *vb = reinterpret_cast<float2 *>( pv_out + q ) + 1;
+                                float2     ua = __ldcg( va ), ub = __ldcg( vb );             // current velocities
+                                const ImpulseTerms T = impulse_terms( contact_geom( a.x, a.y, a.r, b.x, b.y, b.r, dt ), inv_mass_u8( a.m ),
+                                                                      inv_mass_u8( b.m ), ua.x, ua.y, ub.x, ub.y );
+                                if ( T.impulse ) {
+                                    ua.x = __fadd_rn( ua.x, T.dvx_lo );
+                                    ua.y = __fadd_rn( ua.y, T.dvy_lo );
+                                    ub.x = __fsub_rn( ub.x, T.dvx_hi );
+                                    ub.y = __fsub_rn( ub.y, T.dvy_hi );
+                                    *va  = ua;
+                                    *vb  = ub;
+                                }
+                                WB.state[ me ] = ( r << PC_BITS ) | ( pc + 1 );
+                                WB.state[ q ]  = ( r << PC_BITS ) | ( pcq + 1 );
+                                keep           = pc + 1 < deg;
+                            }
+                        }
+                    }
+                }
+            }
+            const unsigned active = __ballot_sync( 0xffffffffu, keep );
+            if ( active ) {
+                const unsigned leader = (unsigned)( __ffs( active ) - 1 );
+                uint32_t       base   = 0;
+                if ( lane == leader )
+                    base = atomicAdd( d_cnt, (uint32_t)__popc( active ) );
+                base = __shfl_sync( 0xffffffffu, base, leader );
+                if ( keep )
+                    dst[ base + (uint32_t)__popc( active & ( ( 1u << lane ) - 1u ) ) ] = me;
+            }
+        }
+        grid.sync();
+    }
 }
 
 // ---- candidate-pair list in the reference's order (parity exporter; not on the hot path) -----------------------

@@ -129,67 +129,87 @@ __device__ __forceinline__ bool overlaps( const float dx, const float dy, const 
 }
 
 // ---- contact response of ONE pair (lo = lower API index = the reference's i, hi = its j) ----------------------
-// Pass 1 (:84-127) from the frozen positions, pass 2 (:138-190) with the velocities handed in.  The result is
-// the four increments the reference applies: lo gets +dp_lo / +dv_lo, hi gets -dp_hi / -dv_hi.
-struct PairTerms {
-    float dpx_lo, dpy_lo, dpx_hi, dpy_hi;   // position pushes (:152-155); zero when not penetrating
-    float dvx_lo, dvy_lo, dvx_hi, dvy_hi;   // velocity impulses (:187-190)
-    bool  push;                             // raw depth > 0 (:145)
-    bool  impulse;                          // not skipped by :170
+// Pass 1 (:84-127): geometry frozen before anything moves.
+struct ContactGeom {
+    float nx, ny;      // unit normal from hi towards lo (:96-97)
+    float raw;         // penetration depth (:103)
+    float corrected;   // clamped share resolved positionally (:106-113)
+    float vbias;       // Baumgarte velocity term (:116-127)
 };
+
+__device__ __forceinline__ ContactGeom contact_geom( const float xlo, const float ylo, const float rlo, const float xhi, const float yhi,
+                                                     const float rhi, const float dt ) {
+    ContactGeom C;
+    const float dx = __fsub_rn( xlo, xhi ), dy = __fsub_rn( ylo, yhi );                      // :85-86
+    float       d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );                  // :87
+    d2             = fmaxf( d2, PPC_EPSILON );                                               // :88
+    const float d  = __fsqrt_rn( d2 );                                                       // :89
+    if ( d < PPC_EPSILON ) {                                                                 // :92 (unreachable: d >= 1e-4)
+        C.nx = 1.0f;
+        C.ny = 0.0f;
+    } else {
+        C.nx = __fdiv_rn( dx, d );                                                           // :96-97
+        C.ny = __fdiv_rn( dy, d );
+    }
+    C.raw       = __fsub_rn( __fadd_rn( rlo, rhi ), d );                                     // :103
+    C.corrected = 0.0f;
+    C.vbias     = 0.0f;
+    if ( C.raw > 0.0f ) {
+        const float cap = __fmul_rn( PPC_DEPTH_CAP, fminf( rlo, rhi ) );                     // :107
+        float       cor = __fmul_rn( C.raw, PPC_SOLVER_TUNER );                              // :108
+        cor             = fmaxf( -cap, fminf( cor, cap ) );                                  // :109
+        C.corrected     = cor;
+        const float residual = __fsub_rn( C.raw, cor );                                      // :117
+        const float slop     = __fmul_rn( PPC_SLOP_FACTOR, fmaxf( rlo, rhi ) );              // :118
+        if ( residual > slop )
+            C.vbias = __fdiv_rn( __fmul_rn( PPC_BAUMGARTE, __fsub_rn( residual, slop ) ), dt );   // :121
+    }
+    return C;
+}
 
 __device__ __forceinline__ float inv_mass_u8( const float m ) {   // :141-142,146-147 masses are read through uint8_t
     return __fdiv_rn( 1.0f, (float)( (unsigned)__float2int_rz( m ) & 0xffu ) );
 }
 
-__device__ __forceinline__ PairTerms pair_terms( const float xlo, const float ylo, const float rlo, const float mlo,
-                                                 const float vxlo, const float vylo, const float xhi, const float yhi,
-                                                 const float rhi, const float mhi, const float vxhi, const float vyhi,
-                                                 const float dt ) {
-    PairTerms   T;
-    const float dx = __fsub_rn( xlo, xhi ), dy = __fsub_rn( ylo, yhi );                      // :85-86
-    float       d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );                  // :87
-    d2             = fmaxf( d2, PPC_EPSILON );                                               // :88
-    const float d  = __fsqrt_rn( d2 );                                                       // :89
-    float       nx, ny;
-    if ( d < PPC_EPSILON ) {                                                                 // :92 (unreachable: d >= 1e-4)
-        nx = 1.0f;
-        ny = 0.0f;
-    } else {
-        nx = __fdiv_rn( dx, d );                                                             // :96-97
-        ny = __fdiv_rn( dy, d );
-    }
-    const float raw = __fsub_rn( __fadd_rn( rlo, rhi ), d );                                 // :103
-    float       corrected = 0.0f, vbias = 0.0f;
-    if ( raw > 0.0f ) {
-        const float cap = __fmul_rn( PPC_DEPTH_CAP, fminf( rlo, rhi ) );                     // :107
-        corrected       = __fmul_rn( raw, PPC_SOLVER_TUNER );                                // :108
-        corrected       = fmaxf( -cap, fminf( corrected, cap ) );                            // :109
-        const float residual = __fsub_rn( raw, corrected );                                  // :117
-        const float slop     = __fmul_rn( PPC_SLOP_FACTOR, fmaxf( rlo, rhi ) );              // :118
-        if ( residual > slop )
-            vbias = __fdiv_rn( __fmul_rn( PPC_BAUMGARTE, __fsub_rn( residual, slop ) ), dt );   // :121
-    }
-    const float wlo = inv_mass_u8( mlo ), whi = inv_mass_u8( mhi );
-    const float wsum = __fadd_rn( wlo, whi );                                                // :148,179
-    T.push = raw > 0.0f;
+// Pass 2, positional part (:145-156): lo gets +(dpx_lo, dpy_lo), hi gets -(dpx_hi, dpy_hi); only when push.
+struct PushTerms {
+    float dpx_lo, dpy_lo, dpx_hi, dpy_hi;
+    bool  push;
+};
+__device__ __forceinline__ PushTerms push_terms( const ContactGeom &C, const float wlo, const float whi ) {
+    PushTerms T;
+    T.push = C.raw > 0.0f;                                                                   // :145
     T.dpx_lo = T.dpy_lo = T.dpx_hi = T.dpy_hi = 0.0f;
-    if ( T.push ) {                                                                          // :145-156
-        const float flo = __fmul_rn( __fdiv_rn( wlo, wsum ), corrected );
-        const float fhi = __fmul_rn( __fdiv_rn( whi, wsum ), corrected );
-        T.dpx_lo = __fmul_rn( flo, nx );
-        T.dpy_lo = __fmul_rn( flo, ny );
-        T.dpx_hi = __fmul_rn( fhi, nx );
-        T.dpy_hi = __fmul_rn( fhi, ny );
+    if ( T.push ) {
+        const float wsum = __fadd_rn( wlo, whi );                                            // :148
+        const float flo  = __fmul_rn( __fdiv_rn( wlo, wsum ), C.corrected );                 // :149-150
+        const float fhi  = __fmul_rn( __fdiv_rn( whi, wsum ), C.corrected );
+        T.dpx_lo = __fmul_rn( flo, C.nx );                                                   // :152-155
+        T.dpy_lo = __fmul_rn( flo, C.ny );
+        T.dpx_hi = __fmul_rn( fhi, C.nx );
+        T.dpy_hi = __fmul_rn( fhi, C.ny );
     }
-    const float rx = __fsub_rn( vxlo, vxhi ), ry = __fsub_rn( vylo, vyhi );                  // :163-164
-    const float vn = __fadd_rn( __fmul_rn( rx, nx ), __fmul_rn( ry, ny ) );                  // :166
-    T.impulse = !( vn > 0.0f && vbias == 0.0f );                                             // :170
+    return T;
+}
+
+// Pass 2, velocity part (:158-190) from the velocities handed in: lo gets +(dvx_lo, dvy_lo), hi gets -(dvx_hi, dvy_hi);
+// only when impulse (the :170 early-out did not fire).
+struct ImpulseTerms {
+    float dvx_lo, dvy_lo, dvx_hi, dvy_hi;
+    bool  impulse;
+};
+__device__ __forceinline__ ImpulseTerms impulse_terms( const ContactGeom &C, const float wlo, const float whi, const float vxlo,
+                                                       const float vylo, const float vxhi, const float vyhi ) {
+    ImpulseTerms T;
+    const float  rx = __fsub_rn( vxlo, vxhi ), ry = __fsub_rn( vylo, vyhi );                 // :163-164
+    const float  vn = __fadd_rn( __fmul_rn( rx, C.nx ), __fmul_rn( ry, C.ny ) );             // :166
+    T.impulse = !( vn > 0.0f && C.vbias == 0.0f );                                           // :170
     T.dvx_lo = T.dvy_lo = T.dvx_hi = T.dvy_hi = 0.0f;
     if ( T.impulse ) {
-        const float want = __double2float_rn( __dadd_rn( __dmul_rn( -PPC_RESTITUTION, (double)vn ), (double)vbias ) );   // :175
+        const float want = __double2float_rn( __dadd_rn( __dmul_rn( -PPC_RESTITUTION, (double)vn ), (double)C.vbias ) );   // :175
+        const float wsum = __fadd_rn( wlo, whi );                                            // :179
         const float jmag = __fdiv_rn( __fsub_rn( want, vn ), wsum );                         // :180
-        const float ix = __fmul_rn( jmag, nx ), iy = __fmul_rn( jmag, ny );                  // :183-184
+        const float ix = __fmul_rn( jmag, C.nx ), iy = __fmul_rn( jmag, C.ny );              // :183-184
         T.dvx_lo = __fmul_rn( wlo, ix );                                                     // :187-190
         T.dvy_lo = __fmul_rn( wlo, iy );
         T.dvx_hi = __fmul_rn( whi, ix );

@@ -147,6 +147,7 @@ def polydisperse_pile(n: int, rmin: float = 1.5, rmax: float = 6.0, W: int = 315
     """
     rng = Stream(seed)
     radius = (np.float32(rmin) + rng.unit(n) * np.float32(rmax - rmin)).astype(np.float32)
+    classes = max(4, min(classes, n // 4096))   # small fields: fewer, wider classes so rows are not mostly empty
     scale = math.sqrt(n / float(1 << 24))
     W, H = max(64, int(round(W * scale))), max(64, int(round(H * scale)))
     order = np.argsort(radius, kind="stable")[::-1]  # big ones at the bottom

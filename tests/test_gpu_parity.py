@@ -4,8 +4,9 @@ Bars (BASELINE.json north_star):
   * integer work -- cell keys, canonical sorted order, cell-start table, candidate-pair list -- bit-exact;
   * positions after a substep with collisions disabled within 1e-4 x radius (asserted bit-exact, which is stricter:
     one float ulp exceeds that tolerance in the large boxes);
-  * positions after ONE substep with collisions on: bit-exact against the reference's sequential resolve;
-  * velocities / many substeps: bit-exact against the oracle's Jacobi model of the device
+  * collisions on, default resolve mode (sequential-equivalent wavefront): positions AND velocities bit-exact against
+    the reference's sequential resolve, for any number of substeps -- stricter than the 1% statistical bar;
+  * collisions on, "resolve"=2 (Jacobi): bit-exact against the oracle's Jacobi model of the device
     (oracle/ppc_oracle.c:ppc_oracle_resolve_jacobi), and within 1% of the reference's sequential solver on kinetic
     energy and momentum over 1000 substeps, with the reference's own pair-order noise floor printed beside it.
 """
@@ -86,7 +87,7 @@ def test_integer_pipeline_is_bit_exact(oracle, name, make, sort_mode):
     p.set_option("sort", sort_mode)
     for step in range(4):   # later steps start from cell-sorted storage: the coherent regime
         oracle.update(ref, DT, False)
-        res = oracle.collisions_check_grid(ref, sc.W, sc.H, DT, mode=1, want_grid=True)
+        res = oracle.collisions_check_grid(ref, sc.W, sc.H, DT, mode=0, want_grid=True)
         p.Update(DT)
         p.CollisionsCheck_Grid(sc.W, sc.H, DT)
         g = p.debug_grid()
@@ -99,47 +100,116 @@ def test_integer_pipeline_is_bit_exact(oracle, name, make, sort_mode):
     p.Free()
 
 
-# ---- one substep with collisions: positions equal the REFERENCE's sequential resolve ------------------------------
+# ---- collisions on, default mode: bit-identical to the REFERENCE's sequential resolve --------------------------------
 @pytest.mark.parametrize("name,make", SCENES)
-def test_one_substep_positions_match_sequential_reference(oracle, name, make):
+def test_one_substep_matches_sequential_reference(oracle, name, make):
     sc = make()
-    seq, jac = state_from_scene(sc), state_from_scene(sc)
+    seq = state_from_scene(sc)
     p = gpu_store(seq)
     oracle.substep(seq, sc.W, sc.H, DT, 0, True)
-    oracle.substep(jac, sc.W, sc.H, DT, 1, True)
     p.request_colors()
     p.Update(DT)
     p.CollisionsCheck_Grid(sc.W, sc.H, DT)
     got = gpu_state(p)
-    assert_state_bits(got, seq, f"{name} vs sequential reference", fields=("px", "py"))
-    assert_state_bits(got, jac, f"{name} vs Jacobi model")
+    assert_state_bits(got, seq, f"{name} vs sequential reference")
     assert_colours_close(got.rgba, seq.rgba, name)
     p.Free()
 
 
-# ---- many substeps: bit-exact against the CPU model of the device semantics -------------------------------------
 @pytest.mark.parametrize("name,make", SCENES)
-def test_thirty_substeps_match_jacobi_model(oracle, name, make):
+def test_thirty_substeps_match_sequential_reference(oracle, name, make):
     sc = make()
     ref = state_from_scene(sc)
     p = gpu_store(ref)
     for _ in range(30):
-        oracle.substep(ref, sc.W, sc.H, DT, 1, False)
+        oracle.substep(ref, sc.W, sc.H, DT, 0, False)
     p.run_substeps(sc.W, sc.H, DT, 30)
     assert_state_bits(gpu_state(p), ref, f"{name} after 30 substeps")
+    p.Free()
+
+
+def test_dense_pile_stays_bit_identical(oracle):
+    """Dense contact network (every particle in several simultaneous contacts, dependency chains tens of pairs long):
+    the regime where a Jacobi resolve diverges and only the reference's pair order gives the reference's answer."""
+    sc = scenes.polydisperse_pile(30000, seed=110)
+    ref = state_from_scene(sc)
+    p = gpu_store(ref)
+    for _ in range(40):
+        oracle.substep(ref, sc.W, sc.H, DT, 0, False)
+    p.run_substeps(sc.W, sc.H, DT, 40)
+    assert oracle.stats(ref, sc.W, sc.H)["contacts"] > 1000
+    assert_state_bits(gpu_state(p), ref, "dense pile after 40 substeps")
+    p.Free()
+
+
+def test_spatially_ordered_indices_long_dependency_chains(oracle):
+    """API indices in raster order make the pair dependency chains as long as a row of particles (hundreds of rounds)."""
+    sc = scenes.polydisperse_pile(20000, seed=111)
+    o = np.lexsort((sc.px, sc.py))
+    for f in ("px", "py", "vx", "vy", "mass", "radius"):
+        setattr(sc, f, np.ascontiguousarray(getattr(sc, f)[o]))
+    ref = state_from_scene(sc)
+    p = gpu_store(ref)
+    for _ in range(5):
+        oracle.substep(ref, sc.W, sc.H, DT, 0, False)
+    p.run_substeps(sc.W, sc.H, DT, 5)
+    assert_state_bits(gpu_state(p), ref, "raster-ordered pile after 5 substeps")
+    p.Free()
+
+
+def test_many_contacts_per_particle(oracle):
+    """More contacts per particle than the stored list (16) and than the stash (24): the recompute-on-demand paths."""
+    rng = scenes.Stream(112)
+    n = 300
+    s = State.empty(n)
+    s.px[:] = 40.0 + rng.unit(n) * 30.0
+    s.py[:] = 40.0 + rng.unit(n) * 30.0
+    s.vx[:] = (rng.unit(n) - 0.5) * 10
+    s.vy[:] = (rng.unit(n) - 0.5) * 10
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 2.0 + rng.unit(n) * 4.0
+    ref = s.copy()
+    p = gpu_store(s)
+    for _ in range(3):
+        oracle.substep(ref, 120, 120, DT, 0, False)
+    p.run_substeps(120, 120, DT, 3)
+    assert_state_bits(gpu_state(p), ref, "crowded cluster")
+    p.Free()
+
+
+# ---- "resolve"=2: bit-exact against the CPU model of the Jacobi device semantics ----------------------------------
+@pytest.mark.parametrize("name,make", SCENES)
+def test_jacobi_option_matches_jacobi_model(oracle, name, make):
+    sc = make()
+    seq, jac = state_from_scene(sc), state_from_scene(sc)
+    p = gpu_store(seq)
+    p.set_option("resolve", 2)
+    oracle.substep(seq, sc.W, sc.H, DT, 0, False)
+    oracle.substep(jac, sc.W, sc.H, DT, 1, False)
+    p.run_substeps(sc.W, sc.H, DT, 1)
+    got = gpu_state(p)
+    assert_state_bits(got, seq, f"{name} one substep vs sequential reference", fields=("px", "py"))   # pushes are pure sums
+    assert_state_bits(got, jac, f"{name} one substep vs Jacobi model")
+    for _ in range(19):
+        oracle.substep(jac, sc.W, sc.H, DT, 1, False)
+    p.run_substeps(sc.W, sc.H, DT, 19)
+    assert_state_bits(gpu_state(p), jac, f"{name} after 20 substeps vs Jacobi model")
     p.Free()
 
 
 def test_streaming_path_equals_stash_path(oracle):
     """The per-thread contact stash is an optimisation; without it (option stash=0) results are identical."""
     sc = scenes.uniform_random(20000, 2.0, 0.7, seed=106, vmax=60.0)
-    a, b = gpu_store(state_from_scene(sc)), gpu_store(state_from_scene(sc))
-    b.set_option("stash", 0)
-    a.run_substeps(sc.W, sc.H, DT, 5)
-    b.run_substeps(sc.W, sc.H, DT, 5)
-    assert_state_bits(gpu_state(a), gpu_state(b), "stash on vs off")
-    a.Free()
-    b.Free()
+    for mode in (1, 2):
+        a, b = gpu_store(state_from_scene(sc)), gpu_store(state_from_scene(sc))
+        a.set_option("resolve", mode)
+        b.set_option("resolve", mode)
+        b.set_option("stash", 0)
+        a.run_substeps(sc.W, sc.H, DT, 5)
+        b.run_substeps(sc.W, sc.H, DT, 5)
+        assert_state_bits(gpu_state(a), gpu_state(b), f"stash on vs off, resolve mode {mode}")
+        a.Free()
+        b.Free()
 
 
 # ---- golden vectors generated from the unmodified reference ------------------------------------------------------
@@ -158,50 +228,38 @@ def test_golden_vectors(name):
         assert_bits_equal(getattr(got, f), g[f"upd_{f}"], f"{name} particlesUpdate {f}")
     assert_colours_close(got.rgba, g["upd_rgba"], name)
     p.CollisionsCheck_Grid(W, H, dt)
-    assert_bits_equal(p.array("p_x"), g["col_px"], f"{name} particlesCollisionsCheck_Grid p_x")
-    assert_bits_equal(p.array("p_y"), g["col_py"], f"{name} particlesCollisionsCheck_Grid p_y")
+    for f, a in (("px", "p_x"), ("py", "p_y"), ("vx", "v_x"), ("vy", "v_y")):
+        assert_bits_equal(p.array(a), g[f"col_{f}"], f"{name} particlesCollisionsCheck_Grid {a}")
     if s0.n >= 2:
         assert np.array_equal(p.debug_pairs(), g["pairs"]), f"{name} candidate-pair list"
+    for _ in range(int(g["steps"]) - 1):
+        p.Update(dt)
+        p.CollisionsCheck_Grid(W, H, dt)
+    for f, a in (("px", "p_x"), ("py", "p_y"), ("vx", "v_x"), ("vy", "v_y")):
+        assert_bits_equal(p.array(a), g[f"end_{f}"], f"{name} after {int(g['steps'])} substeps {a}")
+    assert_colours_close(p.array("colors"), g["end_rgba"], name)
     p.Free()
 
 
 # ---- the store: add / remove bookkeeping (reference src/particles_arrays.c:257-291) ---------------------------------
-def test_store_add_remove_semantics(oracle):
+def test_store_add_remove_semantics():
+    """The reference's own particlesCreate / AddParticle / RemoveParticle / Update / CollisionsCheck_Grid sequence
+    (tests/golden/make_golden.py case 8, shaped like src/main.c:80-98): every host array, including the never-written
+    slot 0 and the dormant newest slot, equals the reference's after every frame."""
     g = np.load(os.path.join(GOLDEN, "store_frames_12.npz"))
     W, H, dt, remove_at = int(g["W"]), int(g["H"]), float(g["dt"]), int(g["remove_at"])
     p = api.Particles(64)   # PPC_SYNC_FRAME, as main.c would use it
-    shadow = State.empty(4096)   # CPU model of the same store, stepped with the Jacobi oracle
-    length = 0
     for f, (x, y, m, r, cnt) in enumerate(g["ops"]):
         p.AddParticle(float(x), float(y), float(m), float(r), int(cnt))
-        for _ in range(int(cnt)):
-            length += 1
-            shadow.px[length], shadow.py[length], shadow.mass[length], shadow.radius[length] = x, y, m, r
-            shadow.vx[length] = shadow.vy[length] = 0.0
         if f == remove_at:
             p.RemoveParticle()
-            for a in (shadow.px, shadow.py, shadow.vx, shadow.vy, shadow.mass, shadow.radius):
-                a[length] = 0.0
-            length -= 1
-        p.Update(dt)
-        p.CollisionsCheck_Grid(W, H, dt)
-        sub = State(*(a[:length].copy() for a in (shadow.px, shadow.py, shadow.vx, shadow.vy, shadow.mass, shadow.radius)),
-                    shadow.rgba[:length].copy())
-        oracle.substep(sub, W, H, dt, 1, False)
-        for dst, src in ((shadow.px, sub.px), (shadow.py, sub.py), (shadow.vx, sub.vx), (shadow.vy, sub.vy)):
-            dst[:length] = src
-        snap = g[f"snap_{f}"]
-        assert p.length == length == int(g["lengths"][f])
-        # constants and the dormant newest slot are exactly what the reference holds
-        assert_bits_equal(p.array("mass", full=True)[: length + 1], snap[4], f"frame {f} mass")
-        assert_bits_equal(p.array("radius", full=True)[: length + 1], snap[5], f"frame {f} radius")
-        assert_bits_equal(p.array("p_x", full=True)[length], snap[0][length], f"frame {f} dormant p_x")
-        # positions: bit-exact against the reference (sums of frozen terms); everything against the Jacobi model
-        assert_bits_equal(p.array("p_x"), snap[0][:length], f"frame {f} p_x vs reference") if f == 0 else None
-        assert_bits_equal(p.array("p_x"), shadow.px[:length], f"frame {f} p_x")
-        assert_bits_equal(p.array("p_y"), shadow.py[:length], f"frame {f} p_y")
-        assert_bits_equal(p.array("v_x"), shadow.vx[:length], f"frame {f} v_x")
-        assert_bits_equal(p.array("v_y"), shadow.vy[:length], f"frame {f} v_y")
+        if p.length > 0:
+            p.Update(dt)
+            p.CollisionsCheck_Grid(W, H, dt)
+        snap, length = g[f"snap_{f}"], int(g["lengths"][f])
+        assert p.length == length
+        for row, a in enumerate(("p_x", "p_y", "v_x", "v_y", "mass", "radius")):
+            assert_bits_equal(p.array(a, full=True)[: length + 1], snap[row], f"frame {f} {a}")
     assert p.size == int(g["size"])
     p.Free()
 
@@ -228,8 +286,8 @@ def test_update_and_collide_compose_like_the_reference(oracle):
     p = gpu_store(ref)
     oracle.update(ref, DT, False)
     oracle.update(ref, 2 * DT, False)
-    oracle.collisions_check_grid(ref, sc.W, sc.H, 3 * DT, mode=1)
-    oracle.collisions_check_grid(ref, sc.W, sc.H, DT, mode=1)
+    oracle.collisions_check_grid(ref, sc.W, sc.H, 3 * DT, mode=0)
+    oracle.collisions_check_grid(ref, sc.W, sc.H, DT, mode=0)
     p.Update(DT)
     p.Update(2 * DT)
     p.CollisionsCheck_Grid(sc.W, sc.H, 3 * DT)
@@ -250,7 +308,7 @@ def test_tiny_counts(oracle, n):
     ref = s.copy()
     p = gpu_store(s, extra=4)
     for _ in range(3):
-        oracle.substep(ref, 200, 100, DT, 1, False)
+        oracle.substep(ref, 200, 100, DT, 0, False)
         if n:
             p.Update(DT)
             p.CollisionsCheck_Grid(200, 100, DT)
@@ -258,36 +316,47 @@ def test_tiny_counts(oracle, n):
     p.Free()
 
 
-# ---- 1000 substeps: statistics against the reference's sequential solver ------------------------------------------
-def test_thousand_substeps_statistics_within_one_percent(oracle):
-    n, steps, dt = 20000, 1000, 1.0 / 1152.0
-    sc = scenes.jittered_lattice(n, 2.0, 0.30, seed=109, vmax=20.0)   # non-overlapping start
-    seq, rev = state_from_scene(sc), None
-    p = gpu_store(state_from_scene(sc))
-    p.run_substeps(sc.W, sc.H, dt, steps)
+# ---- 1000 substeps against the reference's sequential solver -----------------------------------------------------
+def _reference_run(oracle, sc, steps, dt, reverse=False):
+    """The compiled reference when it is here (oracle/_ref/libref.so), else the oracle restatement of it."""
+    s = state_from_scene(sc)
+    R = None
     try:
         from oracle import oracle as om
         R = om.Reference() if om.reference_available() else None
     except Exception:
         R = None
-    if R is not None:   # the real reference, plus its own pair-order noise floor
-        rev = state_from_scene(sc)
+    if R is None:
+        if reverse:
+            return None
         for _ in range(steps):
-            R.substep(seq, sc.W, sc.H, dt)
-        R.set_pair_order(1)
-        try:
-            for _ in range(steps):
-                R.substep(rev, sc.W, sc.H, dt)
-        finally:
-            R.set_pair_order(0)
-    else:
+            oracle.substep(s, sc.W, sc.H, dt, 0, False)
+        return s
+    R.set_pair_order(1 if reverse else 0)
+    try:
         for _ in range(steps):
-            oracle.substep(seq, sc.W, sc.H, dt, 0, False)
-    got = gpu_state(p)
-    sg, ss = oracle.stats(got, sc.W, sc.H), oracle.stats(seq, sc.W, sc.H)
+            R.substep(s, sc.W, sc.H, dt)
+    finally:
+        R.set_pair_order(0)
+    return s
+
+
+def test_thousand_substeps(oracle):
+    n, steps, dt = 20000, 1000, 1.0 / 1152.0
+    sc = scenes.jittered_lattice(n, 2.0, 0.30, seed=109, vmax=20.0)   # non-overlapping start (SURVEY.md section 8c)
+    exact, jac = gpu_store(state_from_scene(sc)), gpu_store(state_from_scene(sc))
+    jac.set_option("resolve", 2)
+    exact.run_substeps(sc.W, sc.H, dt, steps)
+    jac.run_substeps(sc.W, sc.H, dt, steps)
+    seq = _reference_run(oracle, sc, steps, dt)
+    rev = _reference_run(oracle, sc, steps, dt, reverse=True)
+    # default mode: the reference's own answer, bit for bit, after 1000 substeps
+    assert_state_bits(gpu_state(exact), seq, "1000 substeps, sequential-equivalent resolve")
+    # Jacobi option: the north-star's statistical bar
+    sg, ss = oracle.stats(gpu_state(jac), sc.W, sc.H), oracle.stats(seq, sc.W, sc.H)
     rel = lambda a, b: abs(a - b) / max(abs(b), 1e-30)
     report = {k: (sg[k], ss[k], rel(sg[k], ss[k])) for k in ("ke", "mom_x", "mom_y", "overlap", "contacts")}
-    print("\n1000-substep statistics  gpu / reference / relative difference")
+    print("\n1000-substep statistics  gpu(Jacobi) / reference / relative difference")
     for k, v in report.items():
         print(f"  {k:9s} {v[0]:.6g}  {v[1]:.6g}  {100 * v[2]:.4f}%")
     if rev is not None:
@@ -298,7 +367,8 @@ def test_thousand_substeps_statistics_within_one_percent(oracle):
     # residual overlap rests on ~50 contacts here; its spread under the reference's own reordering is ~10%
     # (SURVEY.md section 8c), so it is reported above and bounded loosely rather than at 1%
     assert report["overlap"][2] < 0.5
-    p.Free()
+    exact.Free()
+    jac.Free()
 
 
 # ---- BASELINE sizes: full integer parity at 1M, size-independent properties at 16M ----------------------------------
@@ -309,7 +379,7 @@ def test_one_million_particles_integer_parity(oracle):
     dt = DT
     for step in range(2):
         oracle.update(ref, dt, False)
-        res = oracle.collisions_check_grid(ref, sc.W, sc.H, dt, mode=1, want_grid=True)
+        res = oracle.collisions_check_grid(ref, sc.W, sc.H, dt, mode=0, want_grid=True)
         p.Update(dt)
         p.CollisionsCheck_Grid(sc.W, sc.H, dt)
         g = p.debug_grid()
