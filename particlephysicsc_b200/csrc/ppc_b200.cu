@@ -43,6 +43,7 @@ struct Store {
     int      sync_policy   = PPC_SYNC_FRAME;
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
+    bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
     int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
@@ -339,6 +340,7 @@ static void absorb_host_changes( Store *st, struct Particles_t *p ) {
         st->pending = false;
         st->n       = p->length;
         upload_range( st, p, 0, st->n );
+        st->col_valid        = true;   // the host's colours
         st->dirty_all        = false;
         st->grid_valid       = false;
         st->pre_valid        = false;
@@ -376,6 +378,7 @@ static void flush_pending_update( Store *st ) {
     P.do_integrate = 1;
     P.do_colour    = st->pending_colour ? 1 : 0;
     launch_integrate( st, P );
+    st->col_valid = st->pending_colour;
     st->pre_valid = false;
 }
 
@@ -414,6 +417,8 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     P.wall_w        = (float)(int)W;
     P.wall_h        = (float)(int)H;
     P.grid          = G;
+    if ( st->pending )
+        st->col_valid = st->pending_colour;
     st->pending     = false;
 
     ParticleSet &A = st->set[ st->cur ], &B = st->set[ st->cur ^ 1 ];
@@ -439,7 +444,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
         PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
-                    P.do_colour );
+                    st->col_valid ? 1 : 0 );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
     ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
@@ -472,7 +477,8 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
             const int       want  = (int)div_up( n, WAVE_THREADS );
             if ( grid > want )
                 grid = want;
-            void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&G, (void *)&dt, (void *)&WB };
+            size_t n_arg = n;
+            void  *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB };
             PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_wavefront, dim3( grid ), dim3( WAVE_THREADS ), args, 0, st->stream ) );
             ++g_launches;
         }

@@ -296,23 +296,20 @@ struct WaveBuffers {
     uint32_t *state;     // (round of last advance << PC_BITS) | contacts already resolved
     uint32_t *inc;       // inc[c * stride + k] = c-th contact of particle k: partner slot | INC_LO_FLAG
     size_t    stride;    // particle capacity
-    uint32_t *list[ 2 ]; // active-particle lists (ping-pong between rounds)
-    uint32_t *counters;  // [0..2] rotating list lengths, [3] error flags
+    uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
+    uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
 // JACOBI = true : positions and velocities in one pass (velocities from frozen values).
-// JACOBI = false: positions only; the contact list goes to the wavefront buffers and particles with contacts are
-//                 appended to the first active list.
+// JACOBI = false: positions only; the contact list and the contact count go to the wavefront buffers.
 template <int STASH, bool JACOBI>
 __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const ParticleSet S, float4 *__restrict__ pv_out,
                                                                        const uint32_t *__restrict__ cell_start, const size_t n,
                                                                        const GridDims G, const float dt, const WaveBuffers WB ) {
-    const size_t   k     = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
-    const bool     valid = k < n;
-    const unsigned lane  = threadIdx.x & 31u;
-    uint32_t       cnt   = 0;
-    if ( valid ) {
+    const size_t k   = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
+    uint32_t     cnt = 0;
+    if ( k < n ) {
         const Self           me = load_self( S, k );
         const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
         float4               out = make_float4( me.x, me.y, me.vx, me.vy );
@@ -336,18 +333,6 @@ __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const Par
             WB.state[ k ] = 0u;
         }
     }
-    if ( !JACOBI ) {   // warp-aggregated append of the particles that have contacts
-        const unsigned active = __ballot_sync( 0xffffffffu, valid && cnt > 0 );
-        if ( active ) {
-            const unsigned leader = (unsigned)( __ffs( active ) - 1 );
-            uint32_t       base   = 0;
-            if ( lane == leader )
-                base = atomicAdd( &WB.counters[ 0 ], (uint32_t)__popc( active ) );
-            base = __shfl_sync( 0xffffffffu, base, leader );
-            if ( valid && cnt > 0 )
-                WB.list[ 0 ][ base + (uint32_t)__popc( active & ( ( 1u << lane ) - 1u ) ) ] = (uint32_t)k;
-        }
-    }
 }
 
 // ---- K7b: sequential-equivalent velocity resolve, as a wavefront over the pair dependency graph ----------------
@@ -363,83 +348,105 @@ __device__ __forceinline__ uint32_t head_contact( const ParticleSet &S, const Gl
     return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
 }
 
+// One wavefront step for particle `me` in round r.  Returns true while the particle still has unresolved contacts.
+__device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const GlobalAccessor &acc, float4 *pv_out, const GridDims &G,
+                                                 const float dt, const WaveBuffers &WB, const uint32_t me, const uint32_t r ) {
+    const uint32_t deg = WB.deg[ me ];
+    if ( deg == 0 )
+        return false;
+    const uint32_t w  = __ldcg( &WB.state[ me ] );
+    const uint32_t pc = w & PC_MASK;
+    if ( pc >= deg )
+        return false;
+    if ( ( w >> PC_BITS ) == r )   // advanced earlier in this round by the partner's thread: look again next round
+        return true;
+    const uint32_t entry = head_contact( S, acc, G, WB, me, pc, deg );
+    if ( !( entry & INC_LO_FLAG ) )   // the pair's j waits for the pair's i to execute it
+        return true;
+    const uint32_t q    = entry & ~INC_LO_FLAG;
+    const uint32_t wq   = __ldcg( &WB.state[ q ] );
+    const uint32_t pcq  = wq & PC_MASK;
+    const uint32_t degq = WB.deg[ q ];
+    if ( ( wq >> PC_BITS ) == r || pcq >= degq || head_contact( S, acc, G, WB, q, pcq, degq ) != me )
+        return true;   // the partner still has earlier pairs to resolve
+    const Self a = load_self( S, me ), b = load_self( S, q );   // frozen geometry (pass 1, :84-127)
+    float2    *va = reinterpret_cast<float2 *>( pv_out + me ) + 1;
+    float2    *vb = reinterpret_cast<float2 *>( pv_out + q ) + 1;
+    float2     ua = __ldcg( va ), ub = __ldcg( vb );             // current velocities (:159-162)
+    const ImpulseTerms T = impulse_terms( contact_geom( a.x, a.y, a.r, b.x, b.y, b.r, dt ), inv_mass_u8( a.m ), inv_mass_u8( b.m ), ua.x,
+                                          ua.y, ub.x, ub.y );
+    if ( T.impulse ) {
+        ua.x = __fadd_rn( ua.x, T.dvx_lo );
+        ua.y = __fadd_rn( ua.y, T.dvy_lo );
+        ub.x = __fsub_rn( ub.x, T.dvx_hi );
+        ub.y = __fsub_rn( ub.y, T.dvy_hi );
+        *va  = ua;
+        *vb  = ub;
+    }
+    WB.state[ me ] = ( r << PC_BITS ) | ( pc + 1 );
+    WB.state[ q ]  = ( r << PC_BITS ) | ( pcq + 1 );
+    return pc + 1 < deg;
+}
+
+// Each CTA owns a contiguous chunk of sorted particles and a private queue of those that still have contacts to
+// resolve (queues never grow: particles only leave), so rounds need no global atomics except one add per CTA for
+// the termination count.  Round 1 scans the chunk itself; later rounds walk the queue.
 __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const ParticleSet S, float4 *pv_out,
-                                                                       const uint32_t *__restrict__ cell_start, const GridDims G,
-                                                                       const float dt, const WaveBuffers WB ) {
-    namespace cg            = cooperative_groups;
-    cg::grid_group grid     = cg::this_grid();
+                                                                       const uint32_t *__restrict__ cell_start, const size_t n,
+                                                                       const GridDims G, const float dt, const WaveBuffers WB ) {
+    namespace cg        = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
-    const unsigned       lane        = threadIdx.x & 31u;
-    const size_t         warp_global = ( (size_t)blockIdx.x * WAVE_THREADS + threadIdx.x ) >> 5;
-    const size_t         warps_total = ( (size_t)gridDim.x * WAVE_THREADS ) >> 5;
-    volatile uint32_t   *counters    = WB.counters;
+    const unsigned       lane = threadIdx.x & 31u;
+    __shared__ uint32_t  q_len[ 2 ];   // length of this CTA's queue being read / being written
+    volatile uint32_t   *counters = WB.counters;
+
+    const size_t chunk = ( n + gridDim.x - 1 ) / gridDim.x;
+    const size_t first = (size_t)blockIdx.x * chunk;
+    const size_t last  = first + chunk < n ? first + chunk : n;   // may be <= first for trailing CTAs
+    if ( threadIdx.x == 0 )
+        q_len[ 0 ] = q_len[ 1 ] = 0;
+    __syncthreads();
 
     for ( uint32_t r = 1;; r++ ) {
-        const uint32_t n_active = counters[ ( r - 1 ) % 3 ];
-        if ( n_active == 0 )
+        if ( r > 1 && counters[ ( r - 1 ) % 3 ] == 0 )   // nobody has contacts left
             break;
-        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {   // round stamp would overflow: flag and stop
+        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {     // round stamp would overflow: flag and stop
             if ( blockIdx.x == 0 && threadIdx.x == 0 )
                 atomicOr( &WB.counters[ 3 ], 2u );
             break;
         }
         if ( blockIdx.x == 0 && threadIdx.x == 0 )
             counters[ ( r + 1 ) % 3 ] = 0;
-        const uint32_t *src   = WB.list[ ( r - 1 ) & 1 ];
-        uint32_t       *dst   = WB.list[ r & 1 ];
-        uint32_t       *d_cnt = &WB.counters[ r % 3 ];
+        const uint32_t *src     = WB.list[ ( r - 1 ) & 1 ] + first;
+        uint32_t       *dst     = WB.list[ r & 1 ] + first;
+        uint32_t       *dst_len = &q_len[ r & 1 ];
+        const size_t    count   = r == 1 ? ( last > first ? last - first : 0 ) : (size_t)q_len[ ( r - 1 ) & 1 ];
 
-        for ( size_t t0 = warp_global * 32; t0 < n_active; t0 += warps_total * 32 ) {
+        for ( size_t t0 = ( threadIdx.x & ~31u ); t0 < count; t0 += WAVE_THREADS ) {
             const size_t t    = t0 + lane;
             bool         keep = false;
             uint32_t     me   = 0;
-            if ( t < n_active ) {
-                me                 = src[ t ];
-                const uint32_t w   = __ldcg( &WB.state[ me ] );
-                const uint32_t pc  = w & PC_MASK;
-                const uint32_t deg = WB.deg[ me ];
-                if ( pc < deg ) {
-                    keep = true;
-                    if ( ( w >> PC_BITS ) != r ) {
-                        const uint32_t entry = head_contact( S, acc, G, WB, me, pc, deg );
-                        if ( entry & INC_LO_FLAG ) {   // this particle is the pair's i: it executes the pair
-                            const uint32_t q    = entry & ~INC_LO_FLAG;
-                            const uint32_t wq   = __ldcg( &WB.state[ q ] );
-                            const uint32_t pcq  = wq & PC_MASK;
-                            const uint32_t degq = WB.deg[ q ];
-                            if ( ( wq >> PC_BITS ) != r && pcq < degq && head_contact( S, acc, G, WB, q, pcq, degq ) == me ) {
-                                const Self a = load_self( S, me ), b = load_self( S, q );   // frozen geometry (pass 1)
-                                float2    *va = reinterpret_cast<float2 *>( pv_out + me ) + 1;
-                                float2    *vb = reinterpret_cast<float2 *>( pv_out + q ) + 1;
-                                float2     ua = __ldcg( va ), ub = __ldcg( vb );             // current velocities
-                                const ImpulseTerms T = impulse_terms( contact_geom( a.x, a.y, a.r, b.x, b.y, b.r, dt ), inv_mass_u8( a.m ),
-                                                                      inv_mass_u8( b.m ), ua.x, ua.y, ub.x, ub.y );
-                                if ( T.impulse ) {
-                                    ua.x = __fadd_rn( ua.x, T.dvx_lo );
-                                    ua.y = __fadd_rn( ua.y, T.dvy_lo );
-                                    ub.x = __fsub_rn( ub.x, T.dvx_hi );
-                                    ub.y = __fsub_rn( ub.y, T.dvy_hi );
-                                    *va  = ua;
-                                    *vb  = ub;
-                                }
-                                WB.state[ me ] = ( r << PC_BITS ) | ( pc + 1 );
-                                WB.state[ q ]  = ( r << PC_BITS ) | ( pcq + 1 );
-                                keep           = pc + 1 < deg;
-                            }
-                        }
-                    }
-                }
+            if ( t < count ) {
+                me   = r == 1 ? (uint32_t)( first + t ) : src[ t ];
+                keep = wavefront_visit( S, acc, pv_out, G, dt, WB, me, r );
             }
             const unsigned active = __ballot_sync( 0xffffffffu, keep );
             if ( active ) {
                 const unsigned leader = (unsigned)( __ffs( active ) - 1 );
                 uint32_t       base   = 0;
                 if ( lane == leader )
-                    base = atomicAdd( d_cnt, (uint32_t)__popc( active ) );
+                    base = atomicAdd( dst_len, (uint32_t)__popc( active ) );   // shared-memory counter
                 base = __shfl_sync( 0xffffffffu, base, leader );
                 if ( keep )
                     dst[ base + (uint32_t)__popc( active & ( ( 1u << lane ) - 1u ) ) ] = me;
             }
+        }
+        __syncthreads();
+        if ( threadIdx.x == 0 ) {
+            if ( *dst_len )
+                atomicAdd( &WB.counters[ r % 3 ], *dst_len );
+            q_len[ ( r - 1 ) & 1 ] = 0;   // becomes the write queue of the next round
         }
         grid.sync();
     }

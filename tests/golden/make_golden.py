@@ -105,6 +105,12 @@ def main():
     #    interleaved with substeps like src/main.c:80-98 (slot 0 never written, newest particle dormant)
     lib = R.lib
     p = lib.particlesCreate(64)
+    # The reference never initialises its arrays (aligned_alloc, src/particles_arrays.c:147-183) yet slot 0 is
+    # processed without ever being written (src/particles_arrays.c:266-269).  A fresh 200 KB allocation is zero pages
+    # in practice; the B200 store DEFINES it as zero.  Zero the reference's arrays here so the
+    # fixture does not depend on heap history.
+    for a in ("p_x", "p_y", "v_x", "v_y", "mass", "radius", "colors"):
+        C.memset(getattr(p, a), 0, 4 * p.size)
     ops, snaps = [], []
     frames = list(scenes.debug_scene_frames(frames=12, per_frame=10, W=240, H=135, seed=0x5EED1009))
     for f, (x, y, m, r, cnt) in enumerate(frames):
