@@ -241,6 +241,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         if world == 1 and not args.no_cpu_baseline:
             _, _, cpu = time_reference_cpu(args.workload, 3, 1)
         g = p.grid_info()
+        wave = p.wave_stats()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
@@ -255,6 +256,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step,
                         "note": "particlesUpdate + particlesCollisionsCheck_Grid x8, then p_x, p_y, colors copied to the host arrays"},
+                "resolve_wavefront": None if wave is None else {"rounds_last_substep": wave[0], "particle_visits_last_substep": wave[1]},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     p.Free()

@@ -109,8 +109,9 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
 /* Named integer options; returns 0 on success, -1 for an unknown name.
  *   "sort"     0 = counting sort on the cell key (default), 1 = LSD radix sort
  *   "stash"    per-thread contact stash: 1 = on (default), 0 = off (streaming path only; test hook)
- *   "resolve"  1 = resolve contacts (default), 0 = walls + grid only
- *   "collide"  0 = auto, 1 = global-memory kernel, 2 = shared-memory tile kernel */
+ *   "resolve"  1 = sequential-equivalent wavefront: replays the reference's pair order, bit-exact (default),
+ *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
+ *   "collide"  0 = auto (shared-memory tile kernel), 1 = global-memory thread-per-particle kernel */
 int ppc_set_option( struct Particles_t *p, const char *name, long long value );
 
 /* ---- parity exporters: state of the LAST grid build (all return 0 on success, -1 if no grid was built) ---- */
@@ -125,6 +126,8 @@ int     ppc_debug_sorted_order( struct Particles_t *p, uint32_t *order /* n */ )
 int     ppc_debug_cell_start( struct Particles_t *p, uint32_t *cell_start /* cells+1 */ );
 /* candidate pairs (i, j) in the reference's list order (:311-383); returns the count, writes min(count, max_pairs) */
 int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
+/* last sequential-equivalent resolve: rounds = depth of the reference's pair dependency graph, visits = particle visits */
+int     ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *rounds, unsigned long long *visits );
 
 /* ---- timing ---- */
 void              *ppc_stream( struct Particles_t *p );                /* the cudaStream_t all work is queued on */

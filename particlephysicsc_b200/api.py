@@ -53,7 +53,7 @@ REFERENCE_SYMBOLS = ["particlesCreate", "particlesFree", "particlesAddParticle",
                      "particlesCollisionsCheck_Grid"]
 EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_mask", "ppc_request_colors", "ppc_host_modified",
                      "ppc_download", "ppc_synchronize", "ppc_run_substeps", "ppc_set_option", "ppc_debug_grid_info", "ppc_debug_keys",
-                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_stream", "ppc_kernel_launches",
+                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
 
@@ -94,6 +94,8 @@ def load_library() -> C.CDLL:
     L.ppc_debug_sorted_order.argtypes, L.ppc_debug_sorted_order.restype = [PP, u32p], C.c_int
     L.ppc_debug_cell_start.argtypes, L.ppc_debug_cell_start.restype = [PP, u32p], C.c_int
     L.ppc_debug_pairs.argtypes, L.ppc_debug_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
+    L.ppc_debug_wave_stats.argtypes = [PP, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.ppc_debug_wave_stats.restype = C.c_int
     L.ppc_stream.argtypes, L.ppc_stream.restype = [PP], C.c_void_p
     L.ppc_kernel_launches.argtypes, L.ppc_kernel_launches.restype = [], C.c_ulonglong
     L.ppc_profile.argtypes, L.ppc_profile.restype = [PP, C.c_int], None
@@ -226,6 +228,13 @@ class Particles:
         if n:
             self.lib.ppc_debug_pairs(C.byref(self.s), out.ctypes.data_as(i32p), n)
         return out
+
+    def wave_stats(self):
+        """(rounds, particle visits) of the last sequential-equivalent resolve."""
+        r, v = C.c_ulonglong(), C.c_ulonglong()
+        if self.lib.ppc_debug_wave_stats(C.byref(self.s), C.byref(r), C.byref(v)) != 0:
+            return None
+        return int(r.value), int(v.value)
 
     def stream(self) -> int:
         return int(self.lib.ppc_stream(C.byref(self.s)) or 0)

@@ -143,9 +143,9 @@ static void ensure_wave_buffers( Store *st ) {
     st->wave.stride     = cap;
     st->wave.list[ 0 ]  = dev_alloc<uint32_t>( cap );
     st->wave.list[ 1 ]  = dev_alloc<uint32_t>( cap );
-    st->wave.counters   = dev_alloc<uint32_t>( 4 );
+    st->wave.counters   = dev_alloc<uint32_t>( 8 );
     st->wave_cap        = cap;
-    PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 4 * sizeof( uint32_t ), st->stream ) );
+    PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 8 * sizeof( uint32_t ), st->stream ) );
     int per_sm = 0, sms = 0, dev = 0;
     PPC_CK( cudaGetDevice( &dev ) );
     PPC_CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
@@ -455,6 +455,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 4 * sizeof( uint32_t ), st->stream ) );
         }
         const WaveBuffers WB = st->wave;
         {
@@ -464,7 +465,19 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                 PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else if ( jacobi )
                 PPC_LAUNCH( ( k_collide_global<0, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
-            else if ( st->opt_stash )
+            else if ( st->opt_collide != 1 && st->opt_stash ) {   // shared-memory tile kernel (default)
+                static bool configured = false;
+                if ( !configured ) {
+                    PPC_CK( cudaFuncSetAttribute( k_collide_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( TileSmem ) ) );
+                    configured = true;
+                }
+                const double per_cell = (double)n / (double)G.cells;
+                int          wc       = (int)( 0.55 * TILE_CCAP / ( TILE_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
+                wc                    = wc < 4 ? 4 : ( wc > TILE_MAX_WC ? TILE_MAX_WC : wc );
+                const int tiles_x = ( G.cols + wc - 1 ) / wc, tiles_y = ( G.rows + TILE_R - 1 ) / TILE_R;
+                PPC_LAUNCH( k_collide_tile, (unsigned)( tiles_x * tiles_y ), TILE_THREADS, sizeof( TileSmem ), st->stream, S, O.pv,
+                            st->cell_start, G, dt, WB, wc, tiles_x );
+            } else if ( st->opt_stash )
                 PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else
                 PPC_LAUNCH( ( k_collide_global<0, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
@@ -792,6 +805,18 @@ extern "C" int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_
     }
     cudaFree( tmp );
     return (int64_t)total;
+}
+
+extern "C" int ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *rounds, unsigned long long *visits ) {
+    Store *st = store_of( p );
+    if ( !st->wave.counters )
+        return -1;
+    uint32_t w[ 8 ];
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    PPC_CK( cudaMemcpy( w, st->wave.counters, sizeof( w ), cudaMemcpyDeviceToHost ) );
+    *rounds = w[ 4 ];
+    *visits = ( (unsigned long long)w[ 7 ] << 32 ) | w[ 6 ];
+    return 0;
 }
 
 extern "C" void              *ppc_stream( struct Particles_t *p ) { return (void *)store_of( p )->stream; }

@@ -297,40 +297,321 @@ struct WaveBuffers {
     uint32_t *inc;       // inc[c * stride + k] = c-th contact of particle k: partner slot | INC_LO_FLAG
     size_t    stride;    // particle capacity
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
-    uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags
+    uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
+                         // [6..7] particle visits of the last resolve (64-bit)
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
 // JACOBI = true : positions and velocities in one pass (velocities from frozen values).
 // JACOBI = false: positions only; the contact list and the contact count go to the wavefront buffers.
+// One particle, generic path: candidates straight from global memory, one thread does everything.
+template <int STASH, bool JACOBI>
+__device__ __noinline__ void collide_one_generic( const ParticleSet &S, float4 *__restrict__ pv_out, const uint32_t *__restrict__ cell_start,
+                                                     const GridDims &G, const float dt, const WaveBuffers &WB, const size_t k ) {
+    uint32_t             cnt = 0;
+    const Self           me  = load_self( S, k );
+    const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
+    float4               out = make_float4( me.x, me.y, me.vx, me.vy );
+    for_each_contact_in_list_order<GlobalAccessor, STASH>( acc, G, me, S.key[ k ], [ & ]( const uint32_t q ) {
+        apply_push( acc, me, q, dt, out );
+        if ( JACOBI ) {
+            apply_impulse_frozen( acc, me, q, dt, out );
+        } else {
+            if ( cnt < (uint32_t)INC_MAXDEG )
+                WB.inc[ (size_t)cnt * WB.stride + k ] = q | ( me.gid < acc.gid[ q ] ? INC_LO_FLAG : 0u );
+            cnt++;
+        }
+    } );
+    pv_out[ k ] = out;
+    if ( !JACOBI ) {
+        if ( cnt > PC_MASK ) {   // more simultaneous contacts than the state word can count
+            atomicOr( &WB.counters[ 3 ], 1u );
+            cnt = PC_MASK;
+        }
+        WB.deg[ k ]   = (uint16_t)cnt;
+        WB.state[ k ] = 0u;
+    }
+}
+
 template <int STASH, bool JACOBI>
 __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const ParticleSet S, float4 *__restrict__ pv_out,
                                                                        const uint32_t *__restrict__ cell_start, const size_t n,
                                                                        const GridDims G, const float dt, const WaveBuffers WB ) {
-    const size_t k   = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
-    uint32_t     cnt = 0;
-    if ( k < n ) {
-        const Self           me = load_self( S, k );
-        const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
-        float4               out = make_float4( me.x, me.y, me.vx, me.vy );
-        for_each_contact_in_list_order<GlobalAccessor, STASH>( acc, G, me, S.key[ k ], [ & ]( const uint32_t q ) {
-            apply_push( acc, me, q, dt, out );
-            if ( JACOBI ) {
-                apply_impulse_frozen( acc, me, q, dt, out );
-            } else {
-                if ( cnt < (uint32_t)INC_MAXDEG )
-                    WB.inc[ (size_t)cnt * WB.stride + k ] = q | ( me.gid < acc.gid[ q ] ? INC_LO_FLAG : 0u );
-                cnt++;
+    const size_t k = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
+    if ( k < n )
+        collide_one_generic<STASH, JACOBI>( S, pv_out, cell_start, G, dt, WB, k );
+}
+
+// ---- K7, shared-memory tile form (sequential-equivalent mode) --------------------------------------------------
+// One CTA per tile of TILE_R cell rows x wc cell columns.  Because storage is sorted row-major by cell, the tile and
+// its one-cell halo are TILE_R + 2 contiguous slot runs: they are staged into shared memory with coalesced loads
+// (x, y, radius, mass, API index, slot), each particle being read by ~1.5 CTAs instead of by the 9 cells around it.
+// Work is then distributed CELL-wise: a warp takes one centre cell, its lanes take one candidate each (the 3x3
+// neighbourhood is three contiguous shared-memory ranges) and the warp loops over the cell's own particles.  That
+// keeps all 32 lanes busy on candidate tests, where a thread-per-particle loop idles on the longest lane.
+// Hits (few) are ranked into the reference's list order, their push terms are computed one per lane and added
+// sequentially in that order, so positions equal the reference's bit for bit; the ordered contact list goes to the
+// wavefront buffers.  Tiles or particles that do not fit the fixed shared-memory budget take the generic path.
+constexpr int TILE_THREADS = 512;
+constexpr int TILE_WARPS   = TILE_THREADS / 32;
+constexpr int TILE_R       = 8;      // centre rows per tile
+constexpr int TILE_MAX_WC  = 64;     // centre columns per tile (run-time value <= this)
+constexpr int TILE_CAP     = 2560;   // staged particles (centre + halo)
+constexpr int TILE_CCAP    = 2048;   // centre particles
+constexpr int TILE_HB      = 64;     // hits per particle handled in shared memory
+constexpr int TILE_BW      = TILE_MAX_WC + 4;   // boundary-table row stride
+
+struct TileSmem {
+    float    sx[ TILE_CAP ], sy[ TILE_CAP ], sr[ TILE_CAP ], sm[ TILE_CAP ];
+    uint32_t sg[ TILE_CAP ], sslot[ TILE_CAP ];
+    float    ox[ TILE_CCAP ], oy[ TILE_CCAP ];
+    uint16_t odeg[ TILE_CCAP ];
+    uint32_t bound[ ( TILE_R + 2 ) * TILE_BW ];   // bound[j][i] = first staged index of cell c0 + i in staged row j
+    uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_s0[ TILE_R + 1 ];
+    uint32_t fallback;
+    uint16_t hq[ TILE_WARPS ][ TILE_HB ];
+    uint8_t  hord[ TILE_WARPS ][ TILE_HB ], tfl[ TILE_WARPS ][ TILE_HB ];
+    float    tdx[ TILE_WARPS ][ TILE_HB ], tdy[ TILE_WARPS ][ TILE_HB ];
+};
+
+__global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const ParticleSet S, float4 *__restrict__ pv_out,
+                                                                  const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
+                                                                  const WaveBuffers WB, const int wc, const int tiles_x ) {
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    TileSmem      &T    = *reinterpret_cast<TileSmem *>( smem_raw );
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const int      tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int      cx0 = tx * wc, cy0 = ty * TILE_R;                         // first centre cell
+    const int      cx1 = min( cx0 + wc, G.cols );                            // one past the last centre column
+    const int      c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
+    const int      nb = c1 - c0 + 1;                                         // boundaries per staged row
+
+    // ---- run table: staged row j = 0 .. TILE_R+1 is grid row cy0 - 1 + j ----
+    if ( threadIdx.x < TILE_R + 2 ) {
+        const int j = threadIdx.x, gy = cy0 - 1 + j;
+        uint32_t  g0 = 0, g1 = 0;
+        if ( gy >= 0 && gy < G.rows ) {
+            g0 = cell_start[ (size_t)gy * G.cols + c0 ];
+            g1 = cell_start[ (size_t)gy * G.cols + c1 ];
+        }
+        T.run_g0[ j ] = g0;
+        T.run_s0[ j ] = g1 - g0;   // length for now
+    }
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+        uint32_t run = 0;
+        for ( int j = 0; j < TILE_R + 2; j++ ) {
+            const uint32_t len = T.run_s0[ j ];
+            T.run_s0[ j ]      = run;
+            run += len;
+        }
+        T.run_s0[ TILE_R + 2 ] = run;
+        T.fallback             = run > (uint32_t)TILE_CAP ? 1u : 0u;
+    }
+    __syncthreads();
+    const uint32_t staged = T.run_s0[ TILE_R + 2 ];
+    if ( staged == 0 )
+        return;
+    // ---- boundary table (also needed to know the centre runs) ----
+    for ( int e = threadIdx.x; e < ( TILE_R + 2 ) * nb; e += TILE_THREADS ) {
+        const int j = e / nb, i = e - j * nb, gy = cy0 - 1 + j;
+        uint32_t  v = T.run_s0[ j ];
+        if ( gy >= 0 && gy < G.rows )
+            v += cell_start[ (size_t)gy * G.cols + c0 + i ] - T.run_g0[ j ];
+        T.bound[ j * TILE_BW + i ] = v;
+    }
+    __syncthreads();
+    const int cb = cx0 - c0, ce = cx1 - c0;   // centre columns within the boundary table: [cb, ce)
+    if ( threadIdx.x == 0 ) {
+        uint32_t run = 0;
+        for ( int j = 1; j <= TILE_R; j++ ) {
+            T.cen_s0[ j - 1 ] = run;
+            run += T.bound[ j * TILE_BW + ce ] - T.bound[ j * TILE_BW + cb ];
+        }
+        T.cen_s0[ TILE_R ] = run;
+        if ( run > (uint32_t)TILE_CCAP )
+            T.fallback = 1u;
+    }
+    __syncthreads();
+    const uint32_t centre = T.cen_s0[ TILE_R ];
+    if ( centre == 0 )
+        return;
+
+    if ( T.fallback ) {   // tile does not fit shared memory: thread-per-particle from global memory
+        for ( int j = 1; j <= TILE_R; j++ ) {
+            const uint32_t s_b = T.bound[ j * TILE_BW + cb ], s_e = T.bound[ j * TILE_BW + ce ];
+            const uint32_t g_b = T.run_g0[ j ] + ( s_b - T.run_s0[ j ] );
+            for ( uint32_t t = threadIdx.x; t < s_e - s_b; t += TILE_THREADS )
+                collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)g_b + t );
+        }
+        return;
+    }
+
+    // ---- stage the TILE_R + 2 runs ----
+    for ( int j = 0; j < TILE_R + 2; j++ ) {
+        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
+        for ( uint32_t t = threadIdx.x; t < len; t += TILE_THREADS ) {
+            const float4 p = S.pv[ g0 + t ];
+            const float2 a = S.rm[ g0 + t ];
+            T.sx[ s0 + t ]    = p.x;
+            T.sy[ s0 + t ]    = p.y;
+            T.sr[ s0 + t ]    = a.x;
+            T.sm[ s0 + t ]    = a.y;
+            T.sg[ s0 + t ]    = S.gid[ g0 + t ];
+            T.sslot[ s0 + t ] = g0 + t;
+        }
+    }
+    __syncthreads();
+
+    // ---- warp per centre cell ----
+    const int ncols = cx1 - cx0;
+    for ( int ci = warp; ci < TILE_R * ncols; ci += TILE_WARPS ) {
+        const int jr = ci / ncols, ic = ci - jr * ncols;
+        const int gx = cx0 + ic, gy = cy0 + jr;
+        if ( gy >= G.rows )
+            break;
+        const int      j  = jr + 1;
+        const uint32_t mb = T.bound[ j * TILE_BW + ( gx - c0 ) ], me_end = T.bound[ j * TILE_BW + ( gx - c0 ) + 1 ];
+        if ( mb == me_end )
+            continue;
+        // candidate ranges: rows gy-1, gy, gy+1, cells max(gx-1,0) .. min(gx+1,cols-1); b1/b2 = starts of the 2nd and 3rd cell
+        uint32_t rb[ 3 ], re[ 3 ], b1[ 3 ], b2[ 3 ];
+        uint32_t total = 0;
+        const int lo = max( gx - 1, 0 ), hi = min( gx + 1, G.cols - 1 );
+#pragma unroll
+        for ( int d = 0; d < 3; d++ ) {
+            const int ry = gy - 1 + d, jj = j - 1 + d;
+            if ( ry < 0 || ry >= G.rows ) {
+                rb[ d ] = re[ d ] = b1[ d ] = b2[ d ] = 0;
+                continue;
             }
-        } );
-        pv_out[ k ] = out;
-        if ( !JACOBI ) {
-            if ( cnt > PC_MASK ) {   // more simultaneous contacts than the state word can count
-                atomicOr( &WB.counters[ 3 ], 1u );
-                cnt = PC_MASK;
+            const uint32_t *B = &T.bound[ jj * TILE_BW ];
+            rb[ d ]           = B[ lo - c0 ];
+            re[ d ]           = B[ hi + 1 - c0 ];
+            b1[ d ]           = B[ min( lo + 1, hi + 1 ) - c0 ];
+            b2[ d ]           = B[ min( lo + 2, hi + 1 ) - c0 ];
+            total += re[ d ] - rb[ d ];
+        }
+        const uint32_t l0 = re[ 0 ] - rb[ 0 ], l1 = re[ 1 ] - rb[ 1 ];
+
+        for ( uint32_t m = mb; m < me_end; m++ ) {
+            Self me;
+            me.x = T.sx[ m ], me.y = T.sy[ m ], me.r = T.sr[ m ], me.m = T.sm[ m ], me.gid = T.sg[ m ];
+            me.vx = me.vy = 0.0f;
+            const uint32_t cidx = T.cen_s0[ jr ] + ( m - T.bound[ j * TILE_BW + cb ] );   // centre ordinal of this particle
+            uint32_t       nh   = 0;
+            for ( uint32_t base = 0; base < total; base += 32 ) {
+                const uint32_t f   = base + lane;
+                bool           hit = false;
+                uint32_t       s = 0, ord = 0;
+                if ( f < total ) {
+                    uint32_t d, e1, e2;   // row of the candidate and the starts of that row's 2nd and 3rd cell
+                    if ( f < l0 ) {
+                        d = 0, s = rb[ 0 ] + f, e1 = b1[ 0 ], e2 = b2[ 0 ];
+                    } else if ( f < l0 + l1 ) {
+                        d = 1, s = rb[ 1 ] + ( f - l0 ), e1 = b1[ 1 ], e2 = b2[ 1 ];
+                    } else {
+                        d = 2, s = rb[ 2 ] + ( f - l0 - l1 ), e1 = b1[ 2 ], e2 = b2[ 2 ];
+                    }
+                    ord = d * 4u + ( s >= e1 ? 1u : 0u ) + ( s >= e2 ? 1u : 0u );
+                    Cand c;
+                    c.x = T.sx[ s ], c.y = T.sy[ s ], c.r = T.sr[ s ], c.gid = T.sg[ s ];
+                    hit = c.gid != me.gid && in_contact( me, c );
+                }
+                const unsigned mask = __ballot_sync( 0xffffffffu, hit );
+                if ( hit ) {
+                    const uint32_t pos = nh + (uint32_t)__popc( mask & ( ( 1u << lane ) - 1u ) );
+                    if ( pos < (uint32_t)TILE_HB ) {
+                        T.hq[ warp ][ pos ]   = (uint16_t)s;
+                        T.hord[ warp ][ pos ] = (uint8_t)ord;
+                    }
+                }
+                nh += (uint32_t)__popc( mask );
             }
-            WB.deg[ k ]   = (uint16_t)cnt;
-            WB.state[ k ] = 0u;
+            if ( nh == 0 ) {
+                if ( lane == 0 ) {
+                    T.ox[ cidx ]   = me.x;
+                    T.oy[ cidx ]   = me.y;
+                    T.odeg[ cidx ] = 0;
+                }
+                continue;
+            }
+            if ( nh > (uint32_t)TILE_HB ) {   // crowded particle: generic path, which writes its own outputs
+                if ( lane == 0 ) {
+                    T.odeg[ cidx ] = 0xffffu;
+                    collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)T.sslot[ m ] );
+                }
+                __syncwarp();
+                continue;
+            }
+            __syncwarp();
+            // rank the hits into the reference's list order and compute one push term per lane
+            for ( uint32_t h = lane; h < nh; h += 32 ) {
+                const uint32_t s     = T.hq[ warp ][ h ];
+                const uint32_t g     = T.sg[ s ];
+                const uint32_t o     = T.hord[ warp ][ h ];
+                const bool     me_lo = me.gid < g;
+                uint32_t       rank  = 0;
+                for ( uint32_t u = 0; u < nh; u++ ) {
+                    const uint32_t gu = T.sg[ T.hq[ warp ][ u ] ];
+                    const uint32_t ou = T.hord[ warp ][ u ];
+                    if ( gu < me.gid ) {          // pairs (u, me): all of them precede the pairs (me, *)
+                        if ( me_lo || gu < g )
+                            rank++;
+                    } else if ( me_lo && ( ou < o || ( ou == o && gu > g ) ) ) {
+                        rank++;                   // pairs (me, u): scan order, descending index inside a cell
+                    }
+                }
+                float dx = 0.0f, dy = 0.0f;
+                bool  push;
+                if ( me_lo ) {
+                    const PushTerms P = push_terms( contact_geom( me.x, me.y, me.r, T.sx[ s ], T.sy[ s ], T.sr[ s ], dt ), inv_mass_u8( me.m ),
+                                                    inv_mass_u8( T.sm[ s ] ) );
+                    push = P.push;
+                    dx   = P.dpx_lo;
+                    dy   = P.dpy_lo;
+                } else {
+                    const PushTerms P = push_terms( contact_geom( T.sx[ s ], T.sy[ s ], T.sr[ s ], me.x, me.y, me.r, dt ),
+                                                    inv_mass_u8( T.sm[ s ] ), inv_mass_u8( me.m ) );
+                    push = P.push;
+                    dx   = -P.dpx_hi;   // x - t == x + (-t) exactly
+                    dy   = -P.dpy_hi;
+                }
+                T.tdx[ warp ][ rank ] = dx;
+                T.tdy[ warp ][ rank ] = dy;
+                T.tfl[ warp ][ rank ] = push ? 1 : 0;
+                if ( rank < (uint32_t)INC_MAXDEG )
+                    WB.inc[ (size_t)rank * WB.stride + T.sslot[ m ] ] = T.sslot[ s ] | ( me_lo ? INC_LO_FLAG : 0u );
+            }
+            __syncwarp();
+            if ( lane == 0 ) {
+                float X = me.x, Y = me.y;
+                for ( uint32_t u = 0; u < nh; u++ )
+                    if ( T.tfl[ warp ][ u ] ) {
+                        X = __fadd_rn( X, T.tdx[ warp ][ u ] );
+                        Y = __fadd_rn( Y, T.tdy[ warp ][ u ] );
+                    }
+                T.ox[ cidx ]   = X;
+                T.oy[ cidx ]   = Y;
+                T.odeg[ cidx ] = (uint16_t)nh;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- write the centre particles back, coalesced per run ----
+    for ( int j = 1; j <= TILE_R; j++ ) {
+        const uint32_t s_b = T.bound[ j * TILE_BW + cb ], s_e = T.bound[ j * TILE_BW + ce ];
+        const uint32_t g_b = T.run_g0[ j ] + ( s_b - T.run_s0[ j ] ), c_b = T.cen_s0[ j - 1 ];
+        for ( uint32_t t = threadIdx.x; t < s_e - s_b; t += TILE_THREADS ) {
+            const uint16_t d = T.odeg[ c_b + t ];
+            if ( d == 0xffffu )
+                continue;
+            const float4 old  = S.pv[ g_b + t ];
+            pv_out[ g_b + t ] = make_float4( T.ox[ c_b + t ], T.oy[ c_b + t ], old.z, old.w );
+            WB.deg[ g_b + t ]   = d;
+            WB.state[ g_b + t ] = 0u;
         }
     }
 }
@@ -447,6 +728,10 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
             if ( *dst_len )
                 atomicAdd( &WB.counters[ r % 3 ], *dst_len );
             q_len[ ( r - 1 ) & 1 ] = 0;   // becomes the write queue of the next round
+            if ( count )
+                atomicAdd( reinterpret_cast<unsigned long long *>( WB.counters + 6 ), (unsigned long long)count );
+            if ( blockIdx.x == 0 )
+                WB.counters[ 4 ] = r;
         }
         grid.sync();
     }

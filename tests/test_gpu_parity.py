@@ -177,6 +177,40 @@ def test_many_contacts_per_particle(oracle):
     p.Free()
 
 
+def test_tile_kernel_equals_global_kernel(oracle):
+    """The shared-memory tile narrow phase (default) and the thread-per-particle global-memory one ("collide"=1)."""
+    for make in (lambda: scenes.uniform_random(30000, 2.0, 0.7, seed=113, vmax=60.0), lambda: scenes.polydisperse_pile(30000, seed=114)):
+        sc = make()
+        a, b = gpu_store(state_from_scene(sc)), gpu_store(state_from_scene(sc))
+        b.set_option("collide", 1)
+        a.run_substeps(sc.W, sc.H, DT, 6)
+        b.run_substeps(sc.W, sc.H, DT, 6)
+        assert_state_bits(gpu_state(a), gpu_state(b), "tile vs global narrow phase")
+        assert np.array_equal(a.debug_pairs(), b.debug_pairs())
+        a.Free()
+        b.Free()
+
+
+def test_overfull_tile_takes_the_generic_path(oracle):
+    """More particles around one tile than its shared-memory budget (2560 staged): the whole tile falls back."""
+    rng = scenes.Stream(115)
+    n = 5000
+    s = State.empty(n)
+    s.px[:] = 100.0 + rng.unit(n) * 70.0
+    s.py[:] = 100.0 + rng.unit(n) * 70.0
+    s.vx[:] = (rng.unit(n) - 0.5) * 4
+    s.vy[:] = (rng.unit(n) - 0.5) * 4
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 1.0
+    ref = s.copy()
+    p = gpu_store(s)
+    for _ in range(2):
+        oracle.substep(ref, 400, 400, DT, 0, False)
+    p.run_substeps(400, 400, DT, 2)
+    assert_state_bits(gpu_state(p), ref, "overfull tile")
+    p.Free()
+
+
 # ---- "resolve"=2: bit-exact against the CPU model of the Jacobi device semantics ----------------------------------
 @pytest.mark.parametrize("name,make", SCENES)
 def test_jacobi_option_matches_jacobi_model(oracle, name, make):
