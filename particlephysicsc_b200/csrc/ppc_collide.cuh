@@ -344,47 +344,40 @@ __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const Par
 
 // ---- K7, shared-memory tile form (sequential-equivalent mode) --------------------------------------------------
 // One CTA per tile of TILE_R cell rows x wc cell columns.  Because storage is sorted row-major by cell, the tile and
-// its one-cell halo are TILE_R + 2 contiguous slot runs: they are staged into shared memory with coalesced loads
-// (x, y, radius, mass, API index, slot), each particle being read by ~1.5 CTAs instead of by the 9 cells around it.
-// Work is then distributed CELL-wise: a warp takes one centre cell, its lanes take one candidate each (the 3x3
-// neighbourhood is three contiguous shared-memory ranges) and the warp loops over the cell's own particles.  That
-// keeps all 32 lanes busy on candidate tests, where a thread-per-particle loop idles on the longest lane.
-// Hits (few) are ranked into the reference's list order, their push terms are computed one per lane and added
-// sequentially in that order, so positions equal the reference's bit for bit; the ordered contact list goes to the
-// wavefront buffers.  Tiles or particles that do not fit the fixed shared-memory budget take the generic path.
+// its one-cell halo are TILE_R + 2 contiguous slot runs: they are staged into shared memory with coalesced loads as
+// one 16-byte record per particle (x, y, radius, API index) plus the mass, each particle being read by ~1.5 CTAs
+// instead of by the 9 cells around it.  Each thread then owns one centre particle and scans the three contiguous
+// shared-memory ranges of its 3x3 neighbourhood with a lean loop: one LDS.128, the reference's AABB reject on x (:353),
+// on y (:356), then the circle test (:360-362).  The test is symmetric, so it is evaluated as (me - candidate) without
+// looking at indices.  The few hits are then put into the reference's list order (pairs in which the particle is j
+// by ascending i, then pairs in which it is i by scan order) and their push terms added in that order, so positions
+// equal the reference's bit for bit; the ordered contact list goes to the wavefront buffers.
+// Tiles or particles that do not fit the fixed budget take the generic path.
 constexpr int TILE_THREADS = 512;
-constexpr int TILE_WARPS   = TILE_THREADS / 32;
 constexpr int TILE_R       = 8;      // centre rows per tile
 constexpr int TILE_MAX_WC  = 64;     // centre columns per tile (run-time value <= this)
-constexpr int TILE_CAP     = 2560;   // staged particles (centre + halo)
-constexpr int TILE_CCAP    = 2048;   // centre particles
-constexpr int TILE_HB      = 64;     // hits per particle handled in shared memory
+constexpr int TILE_CAP     = 3072;   // staged particles (centre + halo)
+constexpr int TILE_STASH   = 16;     // hits per particle kept by the lean path
 constexpr int TILE_BW      = TILE_MAX_WC + 4;   // boundary-table row stride
 
 struct TileSmem {
-    float    sx[ TILE_CAP ], sy[ TILE_CAP ], sr[ TILE_CAP ], sm[ TILE_CAP ];
-    uint32_t sg[ TILE_CAP ], sslot[ TILE_CAP ];
-    float    ox[ TILE_CCAP ], oy[ TILE_CCAP ];
-    uint16_t odeg[ TILE_CCAP ];
+    float4   cand[ TILE_CAP ];                    // x, y, radius, API index (bits)
+    float    mass[ TILE_CAP ];
     uint32_t bound[ ( TILE_R + 2 ) * TILE_BW ];   // bound[j][i] = first staged index of cell c0 + i in staged row j
     uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_s0[ TILE_R + 1 ];
     uint32_t fallback;
-    uint16_t hq[ TILE_WARPS ][ TILE_HB ];
-    uint8_t  hord[ TILE_WARPS ][ TILE_HB ], tfl[ TILE_WARPS ][ TILE_HB ];
-    float    tdx[ TILE_WARPS ][ TILE_HB ], tdy[ TILE_WARPS ][ TILE_HB ];
 };
 
 __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const ParticleSet S, float4 *__restrict__ pv_out,
                                                                   const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
                                                                   const WaveBuffers WB, const int wc, const int tiles_x ) {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
-    TileSmem      &T    = *reinterpret_cast<TileSmem *>( smem_raw );
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const int      tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
-    const int      cx0 = tx * wc, cy0 = ty * TILE_R;                         // first centre cell
-    const int      cx1 = min( cx0 + wc, G.cols );                            // one past the last centre column
-    const int      c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
-    const int      nb = c1 - c0 + 1;                                         // boundaries per staged row
+    TileSmem &T = *reinterpret_cast<TileSmem *>( smem_raw );
+    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int cx0 = tx * wc, cy0 = ty * TILE_R;                         // first centre cell
+    const int cx1 = min( cx0 + wc, G.cols );                            // one past the last centre column
+    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
+    const int nb = c1 - c0 + 1;                                         // boundaries per staged row
 
     // ---- run table: staged row j = 0 .. TILE_R+1 is grid row cy0 - 1 + j ----
     if ( threadIdx.x < TILE_R + 2 ) {
@@ -409,10 +402,9 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
         T.fallback             = run > (uint32_t)TILE_CAP ? 1u : 0u;
     }
     __syncthreads();
-    const uint32_t staged = T.run_s0[ TILE_R + 2 ];
-    if ( staged == 0 )
+    if ( T.run_s0[ TILE_R + 2 ] == 0 )
         return;
-    // ---- boundary table (also needed to know the centre runs) ----
+    // ---- boundary table ----
     for ( int e = threadIdx.x; e < ( TILE_R + 2 ) * nb; e += TILE_THREADS ) {
         const int j = e / nb, i = e - j * nb, gy = cy0 - 1 + j;
         uint32_t  v = T.run_s0[ j ];
@@ -429,8 +421,6 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
             run += T.bound[ j * TILE_BW + ce ] - T.bound[ j * TILE_BW + cb ];
         }
         T.cen_s0[ TILE_R ] = run;
-        if ( run > (uint32_t)TILE_CCAP )
-            T.fallback = 1u;
     }
     __syncthreads();
     const uint32_t centre = T.cen_s0[ TILE_R ];
@@ -453,166 +443,114 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
         for ( uint32_t t = threadIdx.x; t < len; t += TILE_THREADS ) {
             const float4 p = S.pv[ g0 + t ];
             const float2 a = S.rm[ g0 + t ];
-            T.sx[ s0 + t ]    = p.x;
-            T.sy[ s0 + t ]    = p.y;
-            T.sr[ s0 + t ]    = a.x;
-            T.sm[ s0 + t ]    = a.y;
-            T.sg[ s0 + t ]    = S.gid[ g0 + t ];
-            T.sslot[ s0 + t ] = g0 + t;
+            T.cand[ s0 + t ] = make_float4( p.x, p.y, a.x, __uint_as_float( S.gid[ g0 + t ] ) );
+            T.mass[ s0 + t ] = a.y;
         }
     }
     __syncthreads();
 
-    // ---- warp per centre cell ----
-    const int ncols = cx1 - cx0;
-    for ( int ci = warp; ci < TILE_R * ncols; ci += TILE_WARPS ) {
-        const int jr = ci / ncols, ic = ci - jr * ncols;
-        const int gx = cx0 + ic, gy = cy0 + jr;
-        if ( gy >= G.rows )
-            break;
-        const int      j  = jr + 1;
-        const uint32_t mb = T.bound[ j * TILE_BW + ( gx - c0 ) ], me_end = T.bound[ j * TILE_BW + ( gx - c0 ) + 1 ];
-        if ( mb == me_end )
-            continue;
-        // candidate ranges: rows gy-1, gy, gy+1, cells max(gx-1,0) .. min(gx+1,cols-1); b1/b2 = starts of the 2nd and 3rd cell
-        uint32_t rb[ 3 ], re[ 3 ], b1[ 3 ], b2[ 3 ];
-        uint32_t total = 0;
-        const int lo = max( gx - 1, 0 ), hi = min( gx + 1, G.cols - 1 );
-#pragma unroll
+    // ---- one thread per centre particle ----
+    for ( uint32_t t = threadIdx.x; t < centre; t += TILE_THREADS ) {
+        int j = 1;
+        while ( j < TILE_R && t >= T.cen_s0[ j ] )
+            j++;
+        const uint32_t self = T.bound[ j * TILE_BW + cb ] + ( t - T.cen_s0[ j - 1 ] );   // staged index
+        const uint32_t gk   = T.run_g0[ j ] + ( self - T.run_s0[ j ] );                   // storage slot
+        const float4   me4  = T.cand[ self ];
+        const float    x = me4.x, y = me4.y, r = me4.z;
+        const uint32_t gid = __float_as_uint( me4.w );
+        const uint32_t key = S.key[ gk ];
+        const int      gy = (int)( key / (uint32_t)G.cols ), gx = (int)( key - (uint32_t)gy * (uint32_t)G.cols );
+        const int      lo = max( gx - 1, 0 ), hi = min( gx + 1, G.cols - 1 );
+
+        uint32_t stash[ TILE_STASH ];   // staged index | scan-cell ordinal << 16
+        uint32_t nh = 0;
+#pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
-            const int ry = gy - 1 + d, jj = j - 1 + d;
-            if ( ry < 0 || ry >= G.rows ) {
-                rb[ d ] = re[ d ] = b1[ d ] = b2[ d ] = 0;
+            const int ry = gy - 1 + d;
+            if ( ry < 0 || ry >= G.rows )
                 continue;
+            const uint32_t *B  = &T.bound[ ( j - 1 + d ) * TILE_BW ];
+            const uint32_t  rb = B[ lo - c0 ], re = B[ hi + 1 - c0 ];
+#pragma unroll 2
+            for ( uint32_t s = rb; s < re; s++ ) {
+                const float4 c  = T.cand[ s ];
+                const float  rs = __fadd_rn( r, c.z );
+                const float  dx = __fsub_rn( x, c.x );
+                if ( fabsf( dx ) > rs )   // :353
+                    continue;
+                const float dy = __fsub_rn( y, c.y );
+                if ( fabsf( dy ) > rs )   // :356
+                    continue;
+                const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
+                if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
+                    if ( nh < (uint32_t)TILE_STASH ) {
+                        const uint32_t ord = (uint32_t)d * 4u + ( s >= B[ min( lo + 1, hi + 1 ) - c0 ] ? 1u : 0u ) +
+                                             ( s >= B[ min( lo + 2, hi + 1 ) - c0 ] ? 1u : 0u );
+                        stash[ nh ] = s | ( ord << 16 );
+                    }
+                    nh++;
+                }
             }
-            const uint32_t *B = &T.bound[ jj * TILE_BW ];
-            rb[ d ]           = B[ lo - c0 ];
-            re[ d ]           = B[ hi + 1 - c0 ];
-            b1[ d ]           = B[ min( lo + 1, hi + 1 ) - c0 ];
-            b2[ d ]           = B[ min( lo + 2, hi + 1 ) - c0 ];
-            total += re[ d ] - rb[ d ];
         }
-        const uint32_t l0 = re[ 0 ] - rb[ 0 ], l1 = re[ 1 ] - rb[ 1 ];
-
-        for ( uint32_t m = mb; m < me_end; m++ ) {
-            Self me;
-            me.x = T.sx[ m ], me.y = T.sy[ m ], me.r = T.sr[ m ], me.m = T.sm[ m ], me.gid = T.sg[ m ];
-            me.vx = me.vy = 0.0f;
-            const uint32_t cidx = T.cen_s0[ jr ] + ( m - T.bound[ j * TILE_BW + cb ] );   // centre ordinal of this particle
-            uint32_t       nh   = 0;
-            for ( uint32_t base = 0; base < total; base += 32 ) {
-                const uint32_t f   = base + lane;
-                bool           hit = false;
-                uint32_t       s = 0, ord = 0;
-                if ( f < total ) {
-                    uint32_t d, e1, e2;   // row of the candidate and the starts of that row's 2nd and 3rd cell
-                    if ( f < l0 ) {
-                        d = 0, s = rb[ 0 ] + f, e1 = b1[ 0 ], e2 = b2[ 0 ];
-                    } else if ( f < l0 + l1 ) {
-                        d = 1, s = rb[ 1 ] + ( f - l0 ), e1 = b1[ 1 ], e2 = b2[ 1 ];
-                    } else {
-                        d = 2, s = rb[ 2 ] + ( f - l0 - l1 ), e1 = b1[ 2 ], e2 = b2[ 2 ];
-                    }
-                    ord = d * 4u + ( s >= e1 ? 1u : 0u ) + ( s >= e2 ? 1u : 0u );
-                    Cand c;
-                    c.x = T.sx[ s ], c.y = T.sy[ s ], c.r = T.sr[ s ], c.gid = T.sg[ s ];
-                    hit = c.gid != me.gid && in_contact( me, c );
-                }
-                const unsigned mask = __ballot_sync( 0xffffffffu, hit );
-                if ( hit ) {
-                    const uint32_t pos = nh + (uint32_t)__popc( mask & ( ( 1u << lane ) - 1u ) );
-                    if ( pos < (uint32_t)TILE_HB ) {
-                        T.hq[ warp ][ pos ]   = (uint16_t)s;
-                        T.hord[ warp ][ pos ] = (uint8_t)ord;
-                    }
-                }
-                nh += (uint32_t)__popc( mask );
-            }
-            if ( nh == 0 ) {
-                if ( lane == 0 ) {
-                    T.ox[ cidx ]   = me.x;
-                    T.oy[ cidx ]   = me.y;
-                    T.odeg[ cidx ] = 0;
-                }
-                continue;
-            }
-            if ( nh > (uint32_t)TILE_HB ) {   // crowded particle: generic path, which writes its own outputs
-                if ( lane == 0 ) {
-                    T.odeg[ cidx ] = 0xffffu;
-                    collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)T.sslot[ m ] );
-                }
-                __syncwarp();
-                continue;
-            }
-            __syncwarp();
-            // rank the hits into the reference's list order and compute one push term per lane
-            for ( uint32_t h = lane; h < nh; h += 32 ) {
-                const uint32_t s     = T.hq[ warp ][ h ];
-                const uint32_t g     = T.sg[ s ];
-                const uint32_t o     = T.hord[ warp ][ h ];
-                const bool     me_lo = me.gid < g;
-                uint32_t       rank  = 0;
-                for ( uint32_t u = 0; u < nh; u++ ) {
-                    const uint32_t gu = T.sg[ T.hq[ warp ][ u ] ];
-                    const uint32_t ou = T.hord[ warp ][ u ];
-                    if ( gu < me.gid ) {          // pairs (u, me): all of them precede the pairs (me, *)
-                        if ( me_lo || gu < g )
-                            rank++;
-                    } else if ( me_lo && ( ou < o || ( ou == o && gu > g ) ) ) {
-                        rank++;                   // pairs (me, u): scan order, descending index inside a cell
-                    }
-                }
-                float dx = 0.0f, dy = 0.0f;
-                bool  push;
-                if ( me_lo ) {
-                    const PushTerms P = push_terms( contact_geom( me.x, me.y, me.r, T.sx[ s ], T.sy[ s ], T.sr[ s ], dt ), inv_mass_u8( me.m ),
-                                                    inv_mass_u8( T.sm[ s ] ) );
-                    push = P.push;
-                    dx   = P.dpx_lo;
-                    dy   = P.dpy_lo;
-                } else {
-                    const PushTerms P = push_terms( contact_geom( T.sx[ s ], T.sy[ s ], T.sr[ s ], me.x, me.y, me.r, dt ),
-                                                    inv_mass_u8( T.sm[ s ] ), inv_mass_u8( me.m ) );
-                    push = P.push;
-                    dx   = -P.dpx_hi;   // x - t == x + (-t) exactly
-                    dy   = -P.dpy_hi;
-                }
-                T.tdx[ warp ][ rank ] = dx;
-                T.tdy[ warp ][ rank ] = dy;
-                T.tfl[ warp ][ rank ] = push ? 1 : 0;
-                if ( rank < (uint32_t)INC_MAXDEG )
-                    WB.inc[ (size_t)rank * WB.stride + T.sslot[ m ] ] = T.sslot[ s ] | ( me_lo ? INC_LO_FLAG : 0u );
-            }
-            __syncwarp();
-            if ( lane == 0 ) {
-                float X = me.x, Y = me.y;
-                for ( uint32_t u = 0; u < nh; u++ )
-                    if ( T.tfl[ warp ][ u ] ) {
-                        X = __fadd_rn( X, T.tdx[ warp ][ u ] );
-                        Y = __fadd_rn( Y, T.tdy[ warp ][ u ] );
-                    }
-                T.ox[ cidx ]   = X;
-                T.oy[ cidx ]   = Y;
-                T.odeg[ cidx ] = (uint16_t)nh;
-            }
-            __syncwarp();
+        if ( nh == 0 ) {
+            const float4 old = S.pv[ gk ];
+            pv_out[ gk ]     = make_float4( x, y, old.z, old.w );
+            WB.deg[ gk ]     = 0;
+            WB.state[ gk ]   = 0u;
+            continue;
         }
-    }
-    __syncthreads();
-
-    // ---- write the centre particles back, coalesced per run ----
-    for ( int j = 1; j <= TILE_R; j++ ) {
-        const uint32_t s_b = T.bound[ j * TILE_BW + cb ], s_e = T.bound[ j * TILE_BW + ce ];
-        const uint32_t g_b = T.run_g0[ j ] + ( s_b - T.run_s0[ j ] ), c_b = T.cen_s0[ j - 1 ];
-        for ( uint32_t t = threadIdx.x; t < s_e - s_b; t += TILE_THREADS ) {
-            const uint16_t d = T.odeg[ c_b + t ];
-            if ( d == 0xffffu )
-                continue;
-            const float4 old  = S.pv[ g_b + t ];
-            pv_out[ g_b + t ] = make_float4( T.ox[ c_b + t ], T.oy[ c_b + t ], old.z, old.w );
-            WB.deg[ g_b + t ]   = d;
-            WB.state[ g_b + t ] = 0u;
+        if ( nh > (uint32_t)TILE_STASH ) {   // crowded particle: generic path
+            collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
+            continue;
         }
+        // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell
+        float       X = x, Y = y;
+        const float wme = inv_mass_u8( T.mass[ self ] );
+#pragma unroll 1
+        for ( uint32_t a = 0; a < nh; a++ ) {
+            uint32_t           best = a;
+            unsigned long long bkey = ~0ull;
+#pragma unroll 1
+            for ( uint32_t b = a; b < nh; b++ ) {
+                const uint32_t           e  = stash[ b ];
+                const uint32_t           g  = __float_as_uint( T.cand[ e & 0xffffu ].w );
+                const unsigned long long k2 = g < gid ? (unsigned long long)g
+                                                      : ( 1ull << 40 ) | ( (unsigned long long)( e >> 16 ) << 32 ) | ( 0xffffffffu - g );
+                if ( k2 < bkey ) {
+                    bkey = k2;
+                    best = b;
+                }
+            }
+            const uint32_t e = stash[ best ];
+            stash[ best ]    = stash[ a ];
+            stash[ a ]       = e;
+            const uint32_t s     = e & 0xffffu;
+            const float4   c     = T.cand[ s ];
+            const bool     me_lo = gid < __float_as_uint( c.w );
+            const float    wq    = inv_mass_u8( T.mass[ s ] );
+            if ( me_lo ) {
+                const PushTerms P = push_terms( contact_geom( x, y, r, c.x, c.y, c.z, dt ), wme, wq );
+                if ( P.push ) {
+                    X = __fadd_rn( X, P.dpx_lo );
+                    Y = __fadd_rn( Y, P.dpy_lo );
+                }
+            } else {
+                const PushTerms P = push_terms( contact_geom( c.x, c.y, c.z, x, y, r, dt ), wq, wme );
+                if ( P.push ) {
+                    X = __fsub_rn( X, P.dpx_hi );
+                    Y = __fsub_rn( Y, P.dpy_hi );
+                }
+            }
+            int jj = 0;   // staged row of the partner -> its storage slot
+            while ( jj < TILE_R + 1 && s >= T.run_s0[ jj + 1 ] )
+                jj++;
+            WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
+        }
+        const float4 old = S.pv[ gk ];
+        pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
+        WB.deg[ gk ]     = (uint16_t)nh;
+        WB.state[ gk ]   = 0u;
     }
 }
 
