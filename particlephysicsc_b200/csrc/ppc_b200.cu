@@ -44,7 +44,7 @@ struct Store {
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
-    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 4;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -484,14 +484,33 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         }
         if ( !jacobi ) {
             StageTimer T( st, ST_WAVEFRONT );                                          // K7b: velocities, in the reference's pair order
-            float4        *pv_out = O.pv;
-            const uint32_t *cs    = st->cell_start;
-            int             grid  = st->wave_grid;
-            const int       want  = (int)div_up( n, WAVE_THREADS );
+            float4         *pv_out = O.pv;
+            const uint32_t *cs     = st->cell_start;
+            const int       passes = st->opt_wave_passes;
+            if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
+                static bool configured = false;
+                if ( !configured ) {
+                    PPC_CK( cudaFuncSetAttribute( k_wave_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( WaveTileSmem ) ) );
+                    configured = true;
+                }
+                const double per_cell = (double)n / (double)G.cells;
+                int          tw       = (int)sqrt( 1000.0 / ( per_cell > 0.05 ? per_cell : 0.05 ) );
+                tw                    = tw < 4 ? 4 : ( tw > WTILE_MAXR ? WTILE_MAXR : tw );
+                tw &= ~1;
+                for ( int pass = 0; pass < passes; pass++ ) {
+                    const int off_x = ( pass & 1 ) ? tw / 2 : 0, off_y = ( ( pass >> 1 ) & 1 ) ? tw / 2 : 0;
+                    const int tiles_x = ( G.cols + off_x + tw - 1 ) / tw, tiles_y = ( G.rows + off_y + tw - 1 ) / tw;
+                    PPC_LAUNCH( k_wave_tile, (unsigned)( tiles_x * tiles_y ), WTILE_THREADS, sizeof( WaveTileSmem ), st->stream, S, pv_out, cs,
+                                G, dt, WB, tw, off_x, off_y, tiles_x, pass == passes - 1 ? 1 : 0 );
+                }
+            }
+            int       grid = st->wave_grid;
+            const int want = (int)div_up( n, WAVE_THREADS );
             if ( grid > want )
                 grid = want;
-            size_t n_arg = n;
-            void  *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB };
+            size_t n_arg   = n;
+            int    after   = passes > 0 ? 1 : 0;
+            void  *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&after };
             PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_wavefront, dim3( grid ), dim3( WAVE_THREADS ), args, 0, st->stream ) );
             ++g_launches;
         }
@@ -724,6 +743,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_resolve = (int)value;
     else if ( !strcmp( name, "collide" ) )
         st->opt_collide = (int)value;
+    else if ( !strcmp( name, "wave_passes" ) )
+        st->opt_wave_passes = (int)value;
     else
         return -1;
     return 0;

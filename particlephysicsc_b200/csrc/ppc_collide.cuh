@@ -298,7 +298,7 @@ struct WaveBuffers {
     size_t    stride;    // particle capacity
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
-                         // [6..7] particle visits of the last resolve (64-bit)
+                         // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit)
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
@@ -612,9 +612,12 @@ __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const Glo
 // the termination count.  Round 1 scans the chunk itself; later rounds walk the queue.
 __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const ParticleSet S, float4 *pv_out,
                                                                        const uint32_t *__restrict__ cell_start, const size_t n,
-                                                                       const GridDims G, const float dt, const WaveBuffers WB ) {
+                                                                       const GridDims G, const float dt, const WaveBuffers WB,
+                                                                       const int after_tile_passes ) {
     namespace cg        = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    if ( after_tile_passes && __ldcg( &WB.counters[ 5 ] ) == 0 )   // the tile passes resolved everything
+        return;
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
     const unsigned       lane = threadIdx.x & 31u;
     __shared__ uint32_t  q_len[ 2 ];   // length of this CTA's queue being read / being written
@@ -672,6 +675,166 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
                 WB.counters[ 4 ] = r;
         }
         grid.sync();
+    }
+}
+
+// ---- K7b, tile passes: the same wavefront, run inside shared memory on one tile of cells at a time ------------------
+// In a dense packing the dependency DAG is ~60 pairs deep and nearly every particle is active, so global rounds
+// stream the whole state ~60 times with scattered access.  A tile pass instead loads the particles of a square tile of
+// cells (contact lists, velocities, list positions, frozen geometry) into shared memory once, runs rounds there until
+// nothing more can fire -- only pairs with BOTH particles inside the tile are eligible, everything else simply waits --
+// and writes velocities and list positions back.  The firing rule is unchanged (head of both lists, not yet advanced
+// this round), so any interleaving of tile passes and global rounds is still a topological order of the reference's
+// dependency graph.  Passes alternate between four tilings shifted by half a tile; measured on the dense pile one pass
+// resolves ~80% of the pairs and four passes >99.9%; k_resolve_wavefront then finishes the remainder.
+constexpr int      WTILE_THREADS = 512;
+constexpr int      WTILE_CAP     = 1536;   // particles per tile
+constexpr int      WTILE_MAXR    = 48;     // rows per tile (run table)
+constexpr uint16_t WTILE_NONLOCAL = 0x7fffu;
+constexpr uint16_t WTILE_LO       = 0x8000u;
+
+struct WaveTileSmem {
+    float    x[ WTILE_CAP ], y[ WTILE_CAP ], r[ WTILE_CAP ], w[ WTILE_CAP ];   // frozen geometry, inverse mass
+    float2   v[ WTILE_CAP ];                                                    // current velocity
+    uint32_t st[ WTILE_CAP ];                                                   // (local round << PC_BITS) | list position
+    uint16_t deg[ WTILE_CAP ];
+    uint16_t list[ INC_MAXDEG ][ WTILE_CAP ];   // partner as tile-local index | WTILE_LO, or WTILE_NONLOCAL
+    uint32_t run_g0[ WTILE_MAXR ], run_s0[ WTILE_MAXR + 1 ];
+    uint32_t fired, left;
+};
+
+__global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                                const GridDims G, const float dt, const WaveBuffers WB, const int tw,
+                                                                const int off_x, const int off_y, const int tiles_x, const int last_pass ) {
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    WaveTileSmem &T = *reinterpret_cast<WaveTileSmem *>( smem_raw );
+    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int cxa = max( tx * tw - off_x, 0 ), cxb = min( tx * tw - off_x + tw, G.cols );
+    const int cya = max( ty * tw - off_y, 0 ), cyb = min( ty * tw - off_y + tw, G.rows );
+    if ( cxa >= cxb || cya >= cyb )
+        return;
+    const int nrows = cyb - cya;
+    if ( (int)threadIdx.x < nrows ) {
+        const size_t row = (size_t)( cya + threadIdx.x ) * G.cols;
+        const uint32_t g0 = cell_start[ row + cxa ], g1 = cell_start[ row + cxb ];
+        T.run_g0[ threadIdx.x ] = g0;
+        T.run_s0[ threadIdx.x ] = g1 - g0;   // length for now
+    }
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+        uint32_t run = 0;
+        for ( int j = 0; j < nrows; j++ ) {
+            const uint32_t len = T.run_s0[ j ];
+            T.run_s0[ j ]      = run;
+            run += len;
+        }
+        T.run_s0[ nrows ] = run;
+        T.fired           = 0;
+        T.left            = 0;
+    }
+    __syncthreads();
+    const uint32_t count = T.run_s0[ nrows ];
+    if ( count == 0 )
+        return;
+    if ( count > (uint32_t)WTILE_CAP ) {   // too crowded for shared memory: left to the global rounds
+        if ( last_pass && threadIdx.x == 0 )
+            atomicAdd( &WB.counters[ 5 ], 1u );
+        return;
+    }
+
+    // ---- stage ----
+    uint32_t left = 0;
+    for ( int j = 0; j < nrows; j++ ) {
+        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
+        for ( uint32_t t = threadIdx.x; t < len; t += WTILE_THREADS ) {
+            const uint32_t g = g0 + t, s = s0 + t;
+            const uint32_t d = WB.deg[ g ];
+            T.deg[ s ]       = (uint16_t)d;
+            uint32_t pc      = d ? ( __ldcg( &WB.state[ g ] ) & PC_MASK ) : 0u;
+            if ( d > (uint32_t)INC_MAXDEG ) {   // list not stored: this particle waits for the global rounds
+                left += pc < d ? 1u : 0u;
+                pc = d, T.deg[ s ] = 0;
+            }
+            T.st[ s ] = pc < d ? pc : d;
+            if ( pc < d ) {
+                const float4 p = S.pv[ g ];
+                const float2 a = S.rm[ g ];
+                T.x[ s ] = p.x, T.y[ s ] = p.y, T.r[ s ] = a.x, T.w[ s ] = inv_mass_u8( a.y );
+                T.v[ s ] = __ldcg( reinterpret_cast<const float2 *>( pv_out + g ) + 1 );
+                for ( uint32_t c = pc; c < d; c++ ) {
+                    const uint32_t e = WB.inc[ (size_t)c * WB.stride + g ], q = e & ~INC_LO_FLAG;
+                    uint16_t       local = WTILE_NONLOCAL;
+#pragma unroll
+                    for ( int dj = -1; dj <= 1; dj++ ) {   // a contact lies in the same or an adjacent cell row
+                        const int jj = j + dj;
+                        if ( jj >= 0 && jj < nrows && q >= T.run_g0[ jj ] && q < T.run_g0[ jj ] + ( T.run_s0[ jj + 1 ] - T.run_s0[ jj ] ) )
+                            local = (uint16_t)( T.run_s0[ jj ] + ( q - T.run_g0[ jj ] ) );
+                    }
+                    T.list[ c ][ s ] = local == WTILE_NONLOCAL ? WTILE_NONLOCAL : (uint16_t)( local | ( ( e & INC_LO_FLAG ) ? WTILE_LO : 0 ) );
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- rounds ----
+    for ( uint32_t round = 1;; round++ ) {
+        bool fired = false;
+        for ( uint32_t t = threadIdx.x; t < count; t += WTILE_THREADS ) {
+            const uint32_t w = T.st[ t ], pc = w & PC_MASK, d = T.deg[ t ];
+            if ( pc >= d || ( w >> PC_BITS ) == round )
+                continue;
+            const uint16_t e = T.list[ pc ][ t ];
+            if ( !( e & WTILE_LO ) || ( e & 0x7fffu ) == WTILE_NONLOCAL )
+                continue;
+            const uint32_t q   = e & 0x7fffu;
+            const uint32_t wq  = T.st[ q ], pcq = wq & PC_MASK;
+            if ( ( wq >> PC_BITS ) == round || pcq >= T.deg[ q ] || T.list[ pcq ][ q ] != (uint16_t)t )
+                continue;
+            const ContactGeom  C = contact_geom( T.x[ t ], T.y[ t ], T.r[ t ], T.x[ q ], T.y[ q ], T.r[ q ], dt );
+            float2             ua = T.v[ t ], ub = T.v[ q ];
+            const ImpulseTerms I = impulse_terms( C, T.w[ t ], T.w[ q ], ua.x, ua.y, ub.x, ub.y );
+            if ( I.impulse ) {
+                ua.x = __fadd_rn( ua.x, I.dvx_lo );
+                ua.y = __fadd_rn( ua.y, I.dvy_lo );
+                ub.x = __fsub_rn( ub.x, I.dvx_hi );
+                ub.y = __fsub_rn( ub.y, I.dvy_hi );
+                T.v[ t ] = ua;
+                T.v[ q ] = ub;
+            }
+            T.st[ t ] = ( round << PC_BITS ) | ( pc + 1 );
+            T.st[ q ] = ( round << PC_BITS ) | ( pcq + 1 );
+            fired     = true;
+        }
+        if ( fired )
+            T.fired = round;
+        __syncthreads();
+        const bool any = T.fired == round;
+        __syncthreads();
+        if ( !any )
+            break;
+    }
+
+    // ---- write back what moved ----
+    for ( int j = 0; j < nrows; j++ ) {
+        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
+        for ( uint32_t t = threadIdx.x; t < len; t += WTILE_THREADS ) {
+            const uint32_t s = s0 + t, w = T.st[ s ];
+            if ( w >> PC_BITS ) {   // advanced at least once in this pass
+                WB.state[ g0 + t ] = w & PC_MASK;
+                *( reinterpret_cast<float2 *>( pv_out + g0 + t ) + 1 ) = T.v[ s ];
+            }
+            if ( ( w & PC_MASK ) < T.deg[ s ] )
+                left++;
+        }
+    }
+    if ( last_pass ) {   // how much is left for the global rounds
+        const unsigned any = __ballot_sync( 0xffffffffu, left != 0 );
+        if ( any && ( threadIdx.x & 31u ) == 0 )
+            atomicAdd( &T.left, 1u );
+        __syncthreads();
+        if ( threadIdx.x == 0 && T.left )
+            atomicAdd( &WB.counters[ 5 ], T.left );
     }
 }
 

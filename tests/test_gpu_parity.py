@@ -191,6 +191,20 @@ def test_tile_kernel_equals_global_kernel(oracle):
         b.Free()
 
 
+def test_wavefront_tile_passes_equal_global_rounds(oracle):
+    """Shared-memory tile passes (default 4) vs global rounds only ("wave_passes"=0) vs a single pass: same bits."""
+    sc = scenes.polydisperse_pile(40000, seed=116)
+    ref = state_from_scene(sc)
+    for _ in range(8):
+        oracle.substep(ref, sc.W, sc.H, DT, 0, False)
+    for passes in (0, 1, 4, 7):
+        p = gpu_store(state_from_scene(sc))
+        p.set_option("wave_passes", passes)
+        p.run_substeps(sc.W, sc.H, DT, 8)
+        assert_state_bits(gpu_state(p), ref, f"wave_passes={passes}")
+        p.Free()
+
+
 def test_overfull_tile_takes_the_generic_path(oracle):
     """More particles around one tile than its shared-memory budget (2560 staged): the whole tile falls back."""
     rng = scenes.Stream(115)
