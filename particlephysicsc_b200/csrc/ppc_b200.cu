@@ -64,6 +64,7 @@ struct Store {
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     size_t       wave_cap = 0;
     int          wave_grid = 0;
+    uint32_t    *h_active = nullptr;   // pinned: particles with contacts, as of a recent substep (heuristic only)
     // last grid
     bool     grid_valid = false, pre_valid = false;
     GridDims grid = {};
@@ -143,9 +144,9 @@ static void ensure_wave_buffers( Store *st ) {
     st->wave.stride     = cap;
     st->wave.list[ 0 ]  = dev_alloc<uint32_t>( cap );
     st->wave.list[ 1 ]  = dev_alloc<uint32_t>( cap );
-    st->wave.counters   = dev_alloc<uint32_t>( 8 );
+    st->wave.counters   = dev_alloc<uint32_t>( 16 );
     st->wave_cap        = cap;
-    PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 8 * sizeof( uint32_t ), st->stream ) );
+    PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 16 * sizeof( uint32_t ), st->stream ) );
     int per_sm = 0, sms = 0, dev = 0;
     PPC_CK( cudaGetDevice( &dev ) );
     PPC_CK( cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev ) );
@@ -268,6 +269,8 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     PPC_CK( cudaEventCreate( &st->ev0 ) );
     PPC_CK( cudaEventCreate( &st->ev1 ) );
     st->d_word = dev_alloc<uint32_t>( 4 );
+    PPC_CK( cudaHostAlloc( (void **)&st->h_active, sizeof( uint32_t ), cudaHostAllocDefault ) );
+    *st->h_active = 0xffffffffu;   // unknown yet: assume dense
     resize_particle_arrays( st, p->size, 0 );
     g_stores.push_back( st );
     return st;
@@ -455,7 +458,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
-            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 4 * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 5 * sizeof( uint32_t ), st->stream ) );
         }
         const WaveBuffers WB = st->wave;
         {
@@ -486,7 +489,11 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
             StageTimer T( st, ST_WAVEFRONT );                                          // K7b: velocities, in the reference's pair order
             float4         *pv_out = O.pv;
             const uint32_t *cs     = st->cell_start;
-            const int       passes = st->opt_wave_passes;
+            // tile passes pay off when most particles are in contact (deep dependency chains); sparse contact sets
+            // are cheaper on the compact queues of the global rounds.  The count is a few substeps old.
+            const bool      dense  = *st->h_active == 0xffffffffu || (double)*st->h_active > 0.25 * (double)n;
+            const int       passes = ( st->opt_wave_passes < 0 ) ? -st->opt_wave_passes : ( dense ? st->opt_wave_passes : 0 );
+            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
                 static bool configured = false;
                 if ( !configured ) {
@@ -587,6 +594,7 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFree( st->cell_count );
         cudaFree( st->cell_start );
         cudaFree( st->d_word );
+        cudaFreeHost( st->h_active );
         cudaEventDestroy( st->ev0 );
         cudaEventDestroy( st->ev1 );
         cudaStreamDestroy( st->stream );

@@ -298,7 +298,8 @@ struct WaveBuffers {
     size_t    stride;    // particle capacity
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
-                         // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit)
+                         // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
+                         // [8] particles with at least one contact in this substep (from k_collide_tile)
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
@@ -362,7 +363,7 @@ constexpr int TILE_BW      = TILE_MAX_WC + 4;   // boundary-table row stride
 
 struct TileSmem {
     float4   cand[ TILE_CAP ];                    // x, y, radius, API index (bits)
-    float    mass[ TILE_CAP ];
+    float    mass[ TILE_CAP ];   // INVERSE mass 1 / (float)(uint8_t)m
     uint32_t bound[ ( TILE_R + 2 ) * TILE_BW ];   // bound[j][i] = first staged index of cell c0 + i in staged row j
     uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_s0[ TILE_R + 1 ];
     uint32_t fallback;
@@ -437,19 +438,21 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
         return;
     }
 
-    // ---- stage the TILE_R + 2 runs ----
-    for ( int j = 0; j < TILE_R + 2; j++ ) {
-        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
-        for ( uint32_t t = threadIdx.x; t < len; t += TILE_THREADS ) {
-            const float4 p = S.pv[ g0 + t ];
-            const float2 a = S.rm[ g0 + t ];
-            T.cand[ s0 + t ] = make_float4( p.x, p.y, a.x, __uint_as_float( S.gid[ g0 + t ] ) );
-            T.mass[ s0 + t ] = a.y;
-        }
+    // ---- stage the TILE_R + 2 runs (flat index: every thread busy, one exposed memory latency) ----
+    for ( uint32_t t = threadIdx.x; t < T.run_s0[ TILE_R + 2 ]; t += TILE_THREADS ) {
+        int j = 0;
+        while ( j < TILE_R + 1 && t >= T.run_s0[ j + 1 ] )
+            j++;
+        const uint32_t g = T.run_g0[ j ] + ( t - T.run_s0[ j ] );
+        const float4   p = S.pv[ g ];
+        const float2   a = S.rm[ g ];
+        T.cand[ t ]      = make_float4( p.x, p.y, a.x, __uint_as_float( S.gid[ g ] ) );
+        T.mass[ t ]      = inv_mass_u8( a.y );   // inverse mass, as the resolve reads it (:141-147)
     }
     __syncthreads();
 
     // ---- one thread per centre particle ----
+    uint32_t n_active = 0;
     for ( uint32_t t = threadIdx.x; t < centre; t += TILE_THREADS ) {
         int j = 1;
         while ( j < TILE_R && t >= T.cen_s0[ j ] )
@@ -500,13 +503,14 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
             WB.state[ gk ]   = 0u;
             continue;
         }
+        n_active++;
         if ( nh > (uint32_t)TILE_STASH ) {   // crowded particle: generic path
             collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
             continue;
         }
         // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell
         float       X = x, Y = y;
-        const float wme = inv_mass_u8( T.mass[ self ] );
+        const float wme = T.mass[ self ];
 #pragma unroll 1
         for ( uint32_t a = 0; a < nh; a++ ) {
             uint32_t           best = a;
@@ -528,7 +532,7 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
             const uint32_t s     = e & 0xffffu;
             const float4   c     = T.cand[ s ];
             const bool     me_lo = gid < __float_as_uint( c.w );
-            const float    wq    = inv_mass_u8( T.mass[ s ] );
+            const float    wq    = T.mass[ s ];
             if ( me_lo ) {
                 const PushTerms P = push_terms( contact_geom( x, y, r, c.x, c.y, c.z, dt ), wme, wq );
                 if ( P.push ) {
@@ -552,6 +556,12 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
         WB.deg[ gk ]     = (uint16_t)nh;
         WB.state[ gk ]   = 0u;
     }
+    // how many particles have contacts: the host uses it (a substep late) to decide whether tile passes pay off
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        n_active += __shfl_xor_sync( 0xffffffffu, n_active, d );
+    if ( ( threadIdx.x & 31u ) == 0 && n_active )
+        atomicAdd( &WB.counters[ 8 ], n_active );
 }
 
 // ---- K7b: sequential-equivalent velocity resolve, as a wavefront over the pair dependency graph ----------------
@@ -742,36 +752,42 @@ __global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSe
         return;
     }
 
-    // ---- stage ----
+    // ---- stage (flat index over the tile's particles) ----
     uint32_t left = 0;
-    for ( int j = 0; j < nrows; j++ ) {
-        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
-        for ( uint32_t t = threadIdx.x; t < len; t += WTILE_THREADS ) {
-            const uint32_t g = g0 + t, s = s0 + t;
-            const uint32_t d = WB.deg[ g ];
-            T.deg[ s ]       = (uint16_t)d;
-            uint32_t pc      = d ? ( __ldcg( &WB.state[ g ] ) & PC_MASK ) : 0u;
-            if ( d > (uint32_t)INC_MAXDEG ) {   // list not stored: this particle waits for the global rounds
-                left += pc < d ? 1u : 0u;
-                pc = d, T.deg[ s ] = 0;
-            }
-            T.st[ s ] = pc < d ? pc : d;
-            if ( pc < d ) {
-                const float4 p = S.pv[ g ];
-                const float2 a = S.rm[ g ];
-                T.x[ s ] = p.x, T.y[ s ] = p.y, T.r[ s ] = a.x, T.w[ s ] = inv_mass_u8( a.y );
-                T.v[ s ] = __ldcg( reinterpret_cast<const float2 *>( pv_out + g ) + 1 );
-                for ( uint32_t c = pc; c < d; c++ ) {
-                    const uint32_t e = WB.inc[ (size_t)c * WB.stride + g ], q = e & ~INC_LO_FLAG;
-                    uint16_t       local = WTILE_NONLOCAL;
+    for ( uint32_t s = threadIdx.x; s < count; s += WTILE_THREADS ) {
+        int lo = 0, hi = nrows;   // row j with run_s0[j] <= s < run_s0[j+1]
+        while ( hi - lo > 1 ) {
+            const int mid = ( lo + hi ) >> 1;
+            if ( s >= T.run_s0[ mid ] )
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int      j = lo;
+        const uint32_t g = T.run_g0[ j ] + ( s - T.run_s0[ j ] );
+        const uint32_t d = WB.deg[ g ];
+        T.deg[ s ]       = (uint16_t)d;
+        uint32_t pc      = d ? ( __ldcg( &WB.state[ g ] ) & PC_MASK ) : 0u;
+        if ( d > (uint32_t)INC_MAXDEG ) {   // list not stored: this particle waits for the global rounds
+            left += pc < d ? 1u : 0u;
+            pc = d, T.deg[ s ] = 0;
+        }
+        T.st[ s ] = pc < d ? pc : d;
+        if ( pc < d ) {
+            const float4 p = S.pv[ g ];
+            const float2 a = S.rm[ g ];
+            T.x[ s ] = p.x, T.y[ s ] = p.y, T.r[ s ] = a.x, T.w[ s ] = inv_mass_u8( a.y );
+            T.v[ s ] = __ldcg( reinterpret_cast<const float2 *>( pv_out + g ) + 1 );
+            for ( uint32_t c = pc; c < d; c++ ) {
+                const uint32_t e = WB.inc[ (size_t)c * WB.stride + g ], q = e & ~INC_LO_FLAG;
+                uint16_t       local = WTILE_NONLOCAL;
 #pragma unroll
-                    for ( int dj = -1; dj <= 1; dj++ ) {   // a contact lies in the same or an adjacent cell row
-                        const int jj = j + dj;
-                        if ( jj >= 0 && jj < nrows && q >= T.run_g0[ jj ] && q < T.run_g0[ jj ] + ( T.run_s0[ jj + 1 ] - T.run_s0[ jj ] ) )
-                            local = (uint16_t)( T.run_s0[ jj ] + ( q - T.run_g0[ jj ] ) );
-                    }
-                    T.list[ c ][ s ] = local == WTILE_NONLOCAL ? WTILE_NONLOCAL : (uint16_t)( local | ( ( e & INC_LO_FLAG ) ? WTILE_LO : 0 ) );
+                for ( int dj = -1; dj <= 1; dj++ ) {   // a contact lies in the same or an adjacent cell row
+                    const int jj = j + dj;
+                    if ( jj >= 0 && jj < nrows && q >= T.run_g0[ jj ] && q < T.run_g0[ jj ] + ( T.run_s0[ jj + 1 ] - T.run_s0[ jj ] ) )
+                        local = (uint16_t)( T.run_s0[ jj ] + ( q - T.run_g0[ jj ] ) );
                 }
+                T.list[ c ][ s ] = local == WTILE_NONLOCAL ? WTILE_NONLOCAL : (uint16_t)( local | ( ( e & INC_LO_FLAG ) ? WTILE_LO : 0 ) );
             }
         }
     }
@@ -816,17 +832,23 @@ __global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSe
     }
 
     // ---- write back what moved ----
-    for ( int j = 0; j < nrows; j++ ) {
-        const uint32_t s0 = T.run_s0[ j ], len = T.run_s0[ j + 1 ] - s0, g0 = T.run_g0[ j ];
-        for ( uint32_t t = threadIdx.x; t < len; t += WTILE_THREADS ) {
-            const uint32_t s = s0 + t, w = T.st[ s ];
-            if ( w >> PC_BITS ) {   // advanced at least once in this pass
-                WB.state[ g0 + t ] = w & PC_MASK;
-                *( reinterpret_cast<float2 *>( pv_out + g0 + t ) + 1 ) = T.v[ s ];
+    for ( uint32_t s = threadIdx.x; s < count; s += WTILE_THREADS ) {
+        const uint32_t w = T.st[ s ];
+        if ( w >> PC_BITS ) {   // advanced at least once in this pass
+            int lo = 0, hi = nrows;
+            while ( hi - lo > 1 ) {
+                const int mid = ( lo + hi ) >> 1;
+                if ( s >= T.run_s0[ mid ] )
+                    lo = mid;
+                else
+                    hi = mid;
             }
-            if ( ( w & PC_MASK ) < T.deg[ s ] )
-                left++;
+            const uint32_t g = T.run_g0[ lo ] + ( s - T.run_s0[ lo ] );
+            WB.state[ g ]    = w & PC_MASK;
+            *( reinterpret_cast<float2 *>( pv_out + g ) + 1 ) = T.v[ s ];
         }
+        if ( ( w & PC_MASK ) < T.deg[ s ] )
+            left++;
     }
     if ( last_pass ) {   // how much is left for the global rounds
         const unsigned any = __ballot_sync( 0xffffffffu, left != 0 );
