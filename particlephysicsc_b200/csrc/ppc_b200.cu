@@ -140,7 +140,10 @@ static void ensure_wave_buffers( Store *st ) {
     const size_t cap    = st->cap ? st->cap : 1;
     st->wave.deg        = dev_alloc<uint16_t>( cap );
     st->wave.state      = dev_alloc<uint32_t>( cap );
-    st->wave.inc        = dev_alloc<uint32_t>( cap * (size_t)INC_MAXDEG );
+    // Contact lists: 16 positions per particle always; 64 while that stays under 1 GB, so that heavily overlapping
+    // scenes (the reference's debug scene stacks 10 coincident copies per add, src/main.c:80-85) keep stored lists.
+    st->wave.maxdeg     = cap <= ( (size_t)1 << 22 ) ? 64u : (uint32_t)INC_MAXDEG;
+    st->wave.inc        = dev_alloc<uint32_t>( cap * (size_t)st->wave.maxdeg );
     st->wave.stride     = cap;
     st->wave.list[ 0 ]  = dev_alloc<uint32_t>( cap );
     st->wave.list[ 1 ]  = dev_alloc<uint32_t>( cap );

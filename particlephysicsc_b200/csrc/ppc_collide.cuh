@@ -33,7 +33,7 @@ namespace ppc {
 
 constexpr int      COLLIDE_THREADS = 128;
 constexpr int      COLLIDE_STASH   = 24;    // contacts kept per thread before falling back to the streaming path
-constexpr int      INC_MAXDEG      = 16;    // contacts per particle stored for the wavefront; above: recomputed on demand
+constexpr int      INC_MAXDEG      = 16;    // contacts per particle the TILE kernels handle; the stored lists hold WaveBuffers::maxdeg >= 16
 constexpr uint32_t INC_LO_FLAG     = 0x80000000u;   // this particle is the pair's i (lower API index)
 constexpr uint32_t PC_BITS         = 12;    // wavefront state word: (round << 12) | contacts already resolved
 constexpr uint32_t PC_MASK         = ( 1u << PC_BITS ) - 1u;
@@ -296,6 +296,7 @@ struct WaveBuffers {
     uint32_t *state;     // (round of last advance << PC_BITS) | contacts already resolved
     uint32_t *inc;       // inc[c * stride + k] = c-th contact of particle k: partner slot | INC_LO_FLAG
     size_t    stride;    // particle capacity
+    uint32_t  maxdeg;    // list positions stored per particle (>= INC_MAXDEG); longer lists are recomputed on demand
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
                          // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
@@ -318,7 +319,7 @@ __device__ __noinline__ void collide_one_generic( const ParticleSet &S, float4 *
         if ( JACOBI ) {
             apply_impulse_frozen( acc, me, q, dt, out );
         } else {
-            if ( cnt < (uint32_t)INC_MAXDEG )
+            if ( cnt < WB.maxdeg )
                 WB.inc[ (size_t)cnt * WB.stride + k ] = q | ( me.gid < acc.gid[ q ] ? INC_LO_FLAG : 0u );
             cnt++;
         }
@@ -369,16 +370,35 @@ struct TileSmem {
     uint32_t fallback;
 };
 
-__global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const ParticleSet S, float4 *__restrict__ pv_out,
-                                                                  const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
-                                                                  const WaveBuffers WB, const int wc, const int tiles_x ) {
-    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
-    TileSmem &T = *reinterpret_cast<TileSmem *>( smem_raw );
-    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
-    const int cx0 = tx * wc, cy0 = ty * TILE_R;                         // first centre cell
-    const int cx1 = min( cx0 + wc, G.cols );                            // one past the last centre column
+// Staged particle count of the tile with centre columns [cx0, cx1) and centre rows [cy0, cy0 + TILE_R): the sum of
+// its TILE_R + 2 slot runs.  Called by all threads; the result is uniform.
+__device__ __forceinline__ uint32_t tile_staged_count( TileSmem &T, const uint32_t *__restrict__ cell_start, const GridDims &G, const int cx0,
+                                                       const int cx1, const int cy0 ) {
+    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );
+    __syncthreads();
+    if ( threadIdx.x < TILE_R + 2 ) {
+        const int gy = cy0 - 1 + (int)threadIdx.x;
+        uint32_t  len = 0;
+        if ( gy >= 0 && gy < G.rows )
+            len = cell_start[ (size_t)gy * G.cols + c1 ] - cell_start[ (size_t)gy * G.cols + c0 ];
+        T.run_s0[ threadIdx.x ] = len;
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for ( int j = 0; j < TILE_R + 2; j++ )
+        total += T.run_s0[ j ];
+    __syncthreads();
+    return total;
+}
+
+// One (sub-)tile: centre columns [cx0, cx1), centre rows [cy0, cy0 + TILE_R).
+__device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSet &S, float4 *__restrict__ pv_out,
+                                                   const uint32_t *__restrict__ cell_start, const GridDims &G, const float dt,
+                                                   const WaveBuffers &WB, const int cx0, const int cx1, const int cy0, uint32_t &n_active ) {
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
     const int nb = c1 - c0 + 1;                                         // boundaries per staged row
+    __syncthreads();                                                    // shared memory may still be in use by the previous sub-tile
 
     // ---- run table: staged row j = 0 .. TILE_R+1 is grid row cy0 - 1 + j ----
     if ( threadIdx.x < TILE_R + 2 ) {
@@ -452,7 +472,6 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
     __syncthreads();
 
     // ---- one thread per centre particle ----
-    uint32_t n_active = 0;
     for ( uint32_t t = threadIdx.x; t < centre; t += TILE_THREADS ) {
         int j = 1;
         while ( j < TILE_R && t >= T.cen_s0[ j ] )
@@ -556,6 +575,26 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
         WB.deg[ gk ]     = (uint16_t)nh;
         WB.state[ gk ]   = 0u;
     }
+}
+
+__global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const ParticleSet S, float4 *__restrict__ pv_out,
+                                                                  const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
+                                                                  const WaveBuffers WB, const int wc, const int tiles_x ) {
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    TileSmem &T = *reinterpret_cast<TileSmem *>( smem_raw );
+    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int cx0 = tx * wc, cy0 = ty * TILE_R;
+    const int cx1 = min( cx0 + wc, G.cols );
+    // Particle density varies across the box (a polydisperse pile holds ten times more small particles per cell than
+    // large ones): a tile that would overflow shared memory is cut into column strips that fit.
+    const uint32_t total = tile_staged_count( T, cell_start, G, cx0, cx1, cy0 );
+    if ( total == 0 )
+        return;
+    const int strips = (int)( ( total + ( TILE_CAP * 6 / 10 ) - 1 ) / ( TILE_CAP * 6 / 10 ) );
+    const int sw     = max( ( cx1 - cx0 + strips - 1 ) / strips, 1 );
+    uint32_t  n_active = 0;
+    for ( int sx = cx0; sx < cx1; sx += sw )
+        collide_tile_body( T, S, pv_out, cell_start, G, dt, WB, sx, min( sx + sw, cx1 ), cy0, n_active );
     // how many particles have contacts: the host uses it (a substep late) to decide whether tile passes pay off
 #pragma unroll
     for ( int d = 16; d > 0; d >>= 1 )
@@ -572,7 +611,7 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
 // the depth of the reference's pair dependency graph.
 __device__ __forceinline__ uint32_t head_contact( const ParticleSet &S, const GlobalAccessor &acc, const GridDims &G, const WaveBuffers &WB,
                                                   const uint32_t k, const uint32_t pc, const uint32_t deg ) {
-    if ( deg <= (uint32_t)INC_MAXDEG )
+    if ( deg <= WB.maxdeg )
         return WB.inc[ (size_t)pc * WB.stride + k ];
     return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
 }
@@ -713,14 +752,12 @@ struct WaveTileSmem {
     uint32_t fired, left;
 };
 
-__global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
-                                                                const GridDims G, const float dt, const WaveBuffers WB, const int tw,
-                                                                const int off_x, const int off_y, const int tiles_x, const int last_pass ) {
-    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
-    WaveTileSmem &T = *reinterpret_cast<WaveTileSmem *>( smem_raw );
-    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
-    const int cxa = max( tx * tw - off_x, 0 ), cxb = min( tx * tw - off_x + tw, G.cols );
-    const int cya = max( ty * tw - off_y, 0 ), cyb = min( ty * tw - off_y + tw, G.rows );
+// One (sub-)tile of a wavefront pass: cells [cxa, cxb) x [cya, cyb).  Returns, through left_tiles, whether any of its
+// particles still has unresolved contacts (only counted on the last pass).
+__device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleSet &S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                const GridDims &G, const float dt, const WaveBuffers &WB, const int cxa, const int cxb,
+                                                const int cya, const int cyb, const int last_pass ) {
+    __syncthreads();   // shared memory may still be in use by the previous sub-tile
     if ( cxa >= cxb || cya >= cyb )
         return;
     const int nrows = cyb - cya;
@@ -858,6 +895,38 @@ __global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSe
         if ( threadIdx.x == 0 && T.left )
             atomicAdd( &WB.counters[ 5 ], T.left );
     }
+}
+
+__global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                                const GridDims G, const float dt, const WaveBuffers WB, const int tw,
+                                                                const int off_x, const int off_y, const int tiles_x, const int last_pass ) {
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    WaveTileSmem &T = *reinterpret_cast<WaveTileSmem *>( smem_raw );
+    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int cxa = max( tx * tw - off_x, 0 ), cxb = min( tx * tw - off_x + tw, G.cols );
+    const int cya = max( ty * tw - off_y, 0 ), cyb = min( ty * tw - off_y + tw, G.rows );
+    if ( cxa >= cxb || cya >= cyb )
+        return;
+    // particle count of the whole tile; where the field is denser than average the tile is cut into f x f sub-tiles
+    __shared__ uint32_t tile_total;
+    if ( threadIdx.x == 0 )
+        tile_total = 0;
+    __syncthreads();
+    if ( (int)threadIdx.x < cyb - cya ) {
+        const size_t row = (size_t)( cya + threadIdx.x ) * G.cols;
+        atomicAdd( &tile_total, cell_start[ row + cxb ] - cell_start[ row + cxa ] );
+    }
+    __syncthreads();
+    const uint32_t total = tile_total;
+    if ( total == 0 )
+        return;
+    int f = 1;
+    while ( (uint32_t)( f * f ) * (uint32_t)( WTILE_CAP * 6 / 10 ) < total && f < tw )
+        f++;
+    const int sw = ( cxb - cxa + f - 1 ) / f, sh = ( cyb - cya + f - 1 ) / f;
+    for ( int y = cya; y < cyb; y += sh )
+        for ( int x = cxa; x < cxb; x += sw )
+            wave_tile_body( T, S, pv_out, cell_start, G, dt, WB, x, min( x + sw, cxb ), y, min( y + sh, cyb ), last_pass );
 }
 
 // ---- candidate-pair list in the reference's order (parity exporter; not on the hot path) -----------------------

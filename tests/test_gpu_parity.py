@@ -312,6 +312,39 @@ def test_store_add_remove_semantics():
     p.Free()
 
 
+def test_debug_scene_like_main_c(reference):
+    """BASELINE configs[0], shortened: the reference's debug scene (src/main.c:36-38,80-98) -- every frame one random
+    position / mass / radius is added 10 times through particlesAddParticle, then one update + collisions check --
+    driven through the reference's own store and solver (libref.so) and through the B200 library, entry point for entry
+    point.  Exercises growth, the dirty-tail upload, slot 0, the dormant newest slot and coincident clusters."""
+    import ctypes as C
+    from oracle.oracle import Vector2
+    W, H, dt = 1200, 675, 1.0 / 144.0
+    ref = reference.lib
+    rp = ref.particlesCreate(1000)
+    for a in ("p_x", "p_y", "v_x", "v_y", "mass", "radius", "colors"):
+        C.memset(getattr(rp, a), 0, 4 * rp.size)   # the reference leaves its arrays uninitialised; slot 0 is defined as zero
+    p = api.Particles(1000)
+    frames = list(scenes.debug_scene_frames(frames=260, W=W, H=H, seed=0x5EED0001))
+    for f, (x, y, m, r, cnt) in enumerate(frames):
+        ref.particlesAddParticle(C.byref(rp), Vector2(x, y), m, r, cnt)
+        p.AddParticle(x, y, m, r, cnt)
+        ref.particlesUpdate(C.byref(rp), dt)
+        ref.particlesCollisionsCheck_Grid(C.byref(rp), W, H, dt)
+        p.Update(dt)
+        p.CollisionsCheck_Grid(W, H, dt)
+        if f % 20 == 19 or f == len(frames) - 1:
+            assert p.length == rp.length and p.size == rp.size
+            for a in ("p_x", "p_y", "v_x", "v_y", "mass", "radius"):
+                want = np.ctypeslib.as_array(getattr(rp, a), shape=(rp.size,))[: rp.length + 1]
+                assert_bits_equal(p.array(a, full=True)[: p.length + 1], want, f"frame {f} {a}")
+            want = np.ctypeslib.as_array(rp.colors, shape=(rp.size, 4))[: rp.length]
+            assert_colours_close(p.array("colors"), want, f"frame {f}")
+    assert p.length == 2600 and p.size == 4000
+    ref.particlesFree(C.byref(rp))
+    p.Free()
+
+
 # ---- sync policies and entry-point composition ---------------------------------------------------------------------
 def test_sync_policies_agree(oracle):
     sc = scenes.uniform_random(5000, 2.0, 0.6, seed=107, vmax=40.0)
