@@ -12,6 +12,8 @@
  *  2. Defines the five Raylib draw/image calls that src/particles_arrays.c:297-307,337 references, as
  *     aborting stubs, so libref.so loads without Raylib.
  */
+#define _GNU_SOURCE
+#include <dlfcn.h>
 #include <raylib.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -92,6 +94,8 @@ void particlesResolveVelocity( struct Particles_t *particles, struct Pair *colli
             collisions[ b ]     = t;
         }
     }
+    if ( !g_real ) /* linked (not ctypes-loaded) use: the next definition in load order is the reference's own */
+        g_real = (resolve_fn)dlsym( RTLD_NEXT, "particlesResolveVelocity" );
     if ( !g_real ) {
         fprintf( stderr, "ref_shim: real particlesResolveVelocity not bound (call ppc_capture_set_real)\n" );
         abort();

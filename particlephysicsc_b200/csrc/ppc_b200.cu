@@ -64,7 +64,7 @@ struct Store {
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     size_t       wave_cap = 0;
     int          wave_grid = 0;
-    uint32_t    *h_active = nullptr;   // pinned: particles with contacts, as of a recent substep (heuristic only)
+    uint32_t    *h_active = nullptr;   // pinned [2]: particles with contacts, densest tile (per 1024 cells), as of a recent substep
     // last grid
     bool     grid_valid = false, pre_valid = false;
     GridDims grid = {};
@@ -272,8 +272,9 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     PPC_CK( cudaEventCreate( &st->ev0 ) );
     PPC_CK( cudaEventCreate( &st->ev1 ) );
     st->d_word = dev_alloc<uint32_t>( 4 );
-    PPC_CK( cudaHostAlloc( (void **)&st->h_active, sizeof( uint32_t ), cudaHostAllocDefault ) );
-    *st->h_active = 0xffffffffu;   // unknown yet: assume dense
+    PPC_CK( cudaHostAlloc( (void **)&st->h_active, 2 * sizeof( uint32_t ), cudaHostAllocDefault ) );
+    st->h_active[ 0 ] = 0xffffffffu;   // unknown yet: assume dense
+    st->h_active[ 1 ] = 0;
     resize_particle_arrays( st, p->size, 0 );
     g_stores.push_back( st );
     return st;
@@ -461,7 +462,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
-            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 5 * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 6 * sizeof( uint32_t ), st->stream ) );
         }
         const WaveBuffers WB = st->wave;
         {
@@ -496,17 +497,14 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
             // are cheaper on the compact queues of the global rounds.  The count is a few substeps old.
             const bool      dense  = *st->h_active == 0xffffffffu || (double)*st->h_active > 0.25 * (double)n;
             const int       passes = ( st->opt_wave_passes < 0 ) ? -st->opt_wave_passes : ( dense ? st->opt_wave_passes : 0 );
-            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 2 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
                 static bool configured = false;
                 if ( !configured ) {
                     PPC_CK( cudaFuncSetAttribute( k_wave_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( WaveTileSmem ) ) );
                     configured = true;
                 }
-                const double per_cell = (double)n / (double)G.cells;
-                int          tw       = (int)sqrt( 1000.0 / ( per_cell > 0.05 ? per_cell : 0.05 ) );
-                tw                    = tw < 4 ? 4 : ( tw > WTILE_MAXR ? WTILE_MAXR : tw );
-                tw &= ~1;
+                const int tw = WTILE_TW;   // fixed; dense tiles subdivide themselves (see k_wave_tile)
                 for ( int pass = 0; pass < passes; pass++ ) {
                     const int off_x = ( pass & 1 ) ? tw / 2 : 0, off_y = ( ( pass >> 1 ) & 1 ) ? tw / 2 : 0;
                     const int tiles_x = ( G.cols + off_x + tw - 1 ) / tw, tiles_y = ( G.rows + off_y + tw - 1 ) / tw;

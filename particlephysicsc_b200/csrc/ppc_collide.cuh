@@ -300,7 +300,7 @@ struct WaveBuffers {
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
                          // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
-                         // [8] particles with at least one contact in this substep (from k_collide_tile)
+                         // [8] particles with at least one contact in this substep, [9] densest tile in particles per 1024 cells (from k_collide_tile)
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
@@ -590,6 +590,8 @@ __global__ void __launch_bounds__( TILE_THREADS ) k_collide_tile( const Particle
     const uint32_t total = tile_staged_count( T, cell_start, G, cx0, cx1, cy0 );
     if ( total == 0 )
         return;
+    if ( threadIdx.x == 0 )   // densest tile, in particles per 1024 cells: sizes the wavefront tiles (a substep late)
+        atomicMax( &WB.counters[ 9 ], (uint32_t)( ( (unsigned long long)total << 10 ) / (unsigned)( ( TILE_R + 2 ) * ( cx1 - cx0 + 2 ) ) ) );
     const int strips = (int)( ( total + ( TILE_CAP * 6 / 10 ) - 1 ) / ( TILE_CAP * 6 / 10 ) );
     const int sw     = max( ( cx1 - cx0 + strips - 1 ) / strips, 1 );
     uint32_t  n_active = 0;
@@ -736,9 +738,10 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
 // this round), so any interleaving of tile passes and global rounds is still a topological order of the reference's
 // dependency graph.  Passes alternate between four tilings shifted by half a tile; measured on the dense pile one pass
 // resolves ~80% of the pairs and four passes >99.9%; k_resolve_wavefront then finishes the remainder.
-constexpr int      WTILE_THREADS = 512;
-constexpr int      WTILE_CAP     = 1536;   // particles per tile
-constexpr int      WTILE_MAXR    = 48;     // rows per tile (run table)
+constexpr int      WTILE_THREADS = 256;
+constexpr int      WTILE_CAP     = 1024;   // particles per (sub-)tile: 64 KB of shared memory, three CTAs per SM overlap their round latencies
+constexpr int      WTILE_TW      = 30;     // tile edge in cells: divisible by 2 (half shift), 3 and 5 (odd subdivisions)
+constexpr int      WTILE_MAXR    = WTILE_TW;   // rows per tile (run table)
 constexpr uint16_t WTILE_NONLOCAL = 0x7fffu;
 constexpr uint16_t WTILE_LO       = 0x8000u;
 
@@ -907,7 +910,11 @@ __global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSe
     const int cya = max( ty * tw - off_y, 0 ), cyb = min( ty * tw - off_y + tw, G.rows );
     if ( cxa >= cxb || cya >= cyb )
         return;
-    // particle count of the whole tile; where the field is denser than average the tile is cut into f x f sub-tiles
+    // Density varies across the box (a polydisperse pile holds ten times more small particles per cell than large ones),
+    // so a tile that would overflow shared memory is cut into f x f sub-tiles, f in {3, 5}.  f is ODD on purpose: the
+    // shifted passes move the tiling by tw/2 = (f/2) sub-tile widths, a half-integer, so every sub-tile boundary of one
+    // pass falls in the middle of a sub-tile of the shifted pass (and two odd subdivisions never share a boundary with
+    // a half-shifted one either).  A sub-tile that still overflows is left to the global rounds.
     __shared__ uint32_t tile_total;
     if ( threadIdx.x == 0 )
         tile_total = 0;
@@ -920,13 +927,13 @@ __global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSe
     const uint32_t total = tile_total;
     if ( total == 0 )
         return;
-    int f = 1;
-    while ( (uint32_t)( f * f ) * (uint32_t)( WTILE_CAP * 6 / 10 ) < total && f < tw )
-        f++;
-    const int sw = ( cxb - cxa + f - 1 ) / f, sh = ( cyb - cya + f - 1 ) / f;
-    for ( int y = cya; y < cyb; y += sh )
-        for ( int x = cxa; x < cxb; x += sw )
-            wave_tile_body( T, S, pv_out, cell_start, G, dt, WB, x, min( x + sw, cxb ), y, min( y + sh, cyb ), last_pass );
+    const int f  = total <= (uint32_t)( WTILE_CAP * 85 / 100 ) ? 1 : ( total <= 9u * ( WTILE_CAP / 2 ) ? 3 : 5 );
+    const int sw = tw / f;                                    // tw is a multiple of 30
+    const int ox = tx * tw - off_x, oy = ty * tw - off_y;     // unclipped origin: sub-tile boundaries do not depend on clipping
+    for ( int ky = 0; ky < f; ky++ )
+        for ( int kx = 0; kx < f; kx++ )
+            wave_tile_body( T, S, pv_out, cell_start, G, dt, WB, max( ox + kx * sw, 0 ), min( ox + ( kx + 1 ) * sw, G.cols ),
+                            max( oy + ky * sw, 0 ), min( oy + ( ky + 1 ) * sw, G.rows ), last_pass );
 }
 
 // ---- candidate-pair list in the reference's order (parity exporter; not on the hot path) -----------------------
