@@ -738,8 +738,8 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
 // this round), so any interleaving of tile passes and global rounds is still a topological order of the reference's
 // dependency graph.  Passes alternate between four tilings shifted by half a tile; measured on the dense pile one pass
 // resolves ~80% of the pairs and four passes >99.9%; k_resolve_wavefront then finishes the remainder.
-constexpr int      WTILE_THREADS = 256;
-constexpr int      WTILE_CAP     = 1024;   // particles per (sub-)tile: 64 KB of shared memory, three CTAs per SM overlap their round latencies
+constexpr int      WTILE_THREADS = 512;    // two particles per thread; three CTAs per SM overlap their barriers
+constexpr int      WTILE_CAP     = 1024;   // particles per (sub-)tile: 64 KB of shared memory
 constexpr int      WTILE_TW      = 30;     // tile edge in cells: divisible by 2 (half shift), 3 and 5 (odd subdivisions)
 constexpr int      WTILE_MAXR    = WTILE_TW;   // rows per tile (run table)
 constexpr uint16_t WTILE_NONLOCAL = 0x7fffu;
@@ -752,7 +752,7 @@ struct WaveTileSmem {
     uint16_t deg[ WTILE_CAP ];
     uint16_t list[ INC_MAXDEG ][ WTILE_CAP ];   // partner as tile-local index | WTILE_LO, or WTILE_NONLOCAL
     uint32_t run_g0[ WTILE_MAXR ], run_s0[ WTILE_MAXR + 1 ];
-    uint32_t fired, left;
+    uint32_t fired[ 2 ], left;
 };
 
 // One (sub-)tile of a wavefront pass: cells [cxa, cxb) x [cya, cyb).  Returns, through left_tiles, whether any of its
@@ -779,8 +779,8 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
             run += len;
         }
         T.run_s0[ nrows ] = run;
-        T.fired           = 0;
-        T.left            = 0;
+        T.fired[ 0 ] = T.fired[ 1 ] = 0;
+        T.left                      = 0;
     }
     __syncthreads();
     const uint32_t count = T.run_s0[ nrows ];
@@ -863,11 +863,9 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
             fired     = true;
         }
         if ( fired )
-            T.fired = round;
+            T.fired[ round & 1 ] = round;   // two alternating flags: one barrier per round is enough
         __syncthreads();
-        const bool any = T.fired == round;
-        __syncthreads();
-        if ( !any )
+        if ( T.fired[ round & 1 ] != round )
             break;
     }
 
@@ -900,7 +898,7 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
     }
 }
 
-__global__ void __launch_bounds__( WTILE_THREADS ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+__global__ void __launch_bounds__( WTILE_THREADS, 3 ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
                                                                 const GridDims G, const float dt, const WaveBuffers WB, const int tw,
                                                                 const int off_x, const int off_y, const int tiles_x, const int last_pass ) {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
