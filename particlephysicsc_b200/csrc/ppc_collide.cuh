@@ -744,15 +744,19 @@ constexpr int      WTILE_TW      = 30;     // tile edge in cells: divisible by 2
 constexpr int      WTILE_MAXR    = WTILE_TW;   // rows per tile (run table)
 constexpr uint16_t WTILE_NONLOCAL = 0x7fffu;
 constexpr uint16_t WTILE_LO       = 0x8000u;
+constexpr uint32_t WTILE_MOVED    = 0x80000000u;
 
 struct WaveTileSmem {
     float    x[ WTILE_CAP ], y[ WTILE_CAP ], r[ WTILE_CAP ], w[ WTILE_CAP ];   // frozen geometry, inverse mass
     float2   v[ WTILE_CAP ];                                                    // current velocity
-    uint32_t st[ WTILE_CAP ];                                                   // (local round << PC_BITS) | list position
+    uint32_t st[ WTILE_CAP ];                                                   // list position | WTILE_MOVED once advanced in this pass
+    uint32_t qmark[ WTILE_CAP ];                                                // round in which the particle's head pair was queued
+    uint16_t queue[ 2 ][ WTILE_CAP ];                                           // executors (the pair's i) of the pairs ready to fire
+    uint16_t fired_hi[ WTILE_CAP ];                                             // partner of each pair fired in the current round
     uint16_t deg[ WTILE_CAP ];
     uint16_t list[ INC_MAXDEG ][ WTILE_CAP ];   // partner as tile-local index | WTILE_LO, or WTILE_NONLOCAL
     uint32_t run_g0[ WTILE_MAXR ], run_s0[ WTILE_MAXR + 1 ];
-    uint32_t fired[ 2 ], left;
+    uint32_t qlen[ 2 ], left;
 };
 
 // One (sub-)tile of a wavefront pass: cells [cxa, cxb) x [cya, cyb).  Returns, through left_tiles, whether any of its
@@ -779,8 +783,8 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
             run += len;
         }
         T.run_s0[ nrows ] = run;
-        T.fired[ 0 ] = T.fired[ 1 ] = 0;
-        T.left                      = 0;
+        T.qlen[ 0 ] = T.qlen[ 1 ] = 0;
+        T.left                    = 0;
     }
     __syncthreads();
     const uint32_t count = T.run_s0[ nrows ];
@@ -812,7 +816,8 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
             left += pc < d ? 1u : 0u;
             pc = d, T.deg[ s ] = 0;
         }
-        T.st[ s ] = pc < d ? pc : d;
+        T.st[ s ]    = pc < d ? pc : d;
+        T.qmark[ s ] = 0;
         if ( pc < d ) {
             const float4 p = S.pv[ g ];
             const float2 a = S.rm[ g ];
@@ -833,20 +838,35 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
     }
     __syncthreads();
 
-    // ---- rounds ----
+    // ---- rounds, event driven: a queue of the pairs that are ready, instead of polling every particle every round ----
+    // ready(lo, hi): the pair is at the head of both lists.  A particle's head is unique, so the ready pairs of one round
+    // never share a particle; pairs that BECOME ready when a round's pairs advance are found right after that round
+    // (all advances visible) and queued, once, for the next round.
+    auto head_ready = [ & ]( const uint32_t lo, const uint32_t hi ) -> bool {
+        const uint32_t pl = T.st[ lo ] & PC_MASK, ph = T.st[ hi ] & PC_MASK;
+        return pl < T.deg[ lo ] && ph < T.deg[ hi ] && T.list[ pl ][ lo ] == (uint16_t)( hi | WTILE_LO ) && T.list[ ph ][ hi ] == (uint16_t)lo;
+    };
+    for ( uint32_t t = threadIdx.x; t < count; t += WTILE_THREADS ) {   // initial scan
+        const uint32_t pc = T.st[ t ] & PC_MASK;
+        if ( pc >= T.deg[ t ] )
+            continue;
+        const uint16_t e = T.list[ pc ][ t ];
+        if ( ( e & WTILE_LO ) && ( e & 0x7fffu ) != WTILE_NONLOCAL && head_ready( t, e & 0x7fffu ) )
+            T.queue[ 0 ][ atomicAdd( &T.qlen[ 0 ], 1u ) ] = (uint16_t)t;
+    }
+    __syncthreads();
     for ( uint32_t round = 1;; round++ ) {
-        bool fired = false;
-        for ( uint32_t t = threadIdx.x; t < count; t += WTILE_THREADS ) {
-            const uint32_t w = T.st[ t ], pc = w & PC_MASK, d = T.deg[ t ];
-            if ( pc >= d || ( w >> PC_BITS ) == round )
-                continue;
-            const uint16_t e = T.list[ pc ][ t ];
-            if ( !( e & WTILE_LO ) || ( e & 0x7fffu ) == WTILE_NONLOCAL )
-                continue;
-            const uint32_t q   = e & 0x7fffu;
-            const uint32_t wq  = T.st[ q ], pcq = wq & PC_MASK;
-            if ( ( wq >> PC_BITS ) == round || pcq >= T.deg[ q ] || T.list[ pcq ][ q ] != (uint16_t)t )
-                continue;
+        const uint32_t cur = ( round - 1 ) & 1u, nxt = cur ^ 1u;
+        const uint32_t nq  = T.qlen[ cur ];
+        if ( nq == 0 )
+            break;
+        if ( threadIdx.x == 0 )
+            T.qlen[ nxt ] = 0;
+        for ( uint32_t i = threadIdx.x; i < nq; i += WTILE_THREADS ) {   // fire
+            const uint32_t t = T.queue[ cur ][ i ];
+            const uint32_t pc = T.st[ t ] & PC_MASK;
+            const uint32_t q  = T.list[ pc ][ t ] & 0x7fffu;
+            const uint32_t pcq = T.st[ q ] & PC_MASK;
             const ContactGeom  C = contact_geom( T.x[ t ], T.y[ t ], T.r[ t ], T.x[ q ], T.y[ q ], T.r[ q ], dt );
             float2             ua = T.v[ t ], ub = T.v[ q ];
             const ImpulseTerms I = impulse_terms( C, T.w[ t ], T.w[ q ], ua.x, ua.y, ub.x, ub.y );
@@ -858,21 +878,30 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
                 T.v[ t ] = ua;
                 T.v[ q ] = ub;
             }
-            T.st[ t ] = ( round << PC_BITS ) | ( pc + 1 );
-            T.st[ q ] = ( round << PC_BITS ) | ( pcq + 1 );
-            fired     = true;
+            T.st[ t ]       = WTILE_MOVED | ( pc + 1 );
+            T.st[ q ]       = WTILE_MOVED | ( pcq + 1 );
+            T.fired_hi[ i ] = (uint16_t)q;
         }
-        if ( fired )
-            T.fired[ round & 1 ] = round;   // two alternating flags: one barrier per round is enough
         __syncthreads();
-        if ( T.fired[ round & 1 ] != round )
-            break;
+        for ( uint32_t i = threadIdx.x; i < 2 * nq; i += WTILE_THREADS ) {   // which pairs did that make ready?
+            const uint32_t p  = ( i & 1u ) ? T.fired_hi[ i >> 1 ] : T.queue[ cur ][ i >> 1 ];
+            const uint32_t pc = T.st[ p ] & PC_MASK;
+            if ( pc >= T.deg[ p ] )
+                continue;
+            const uint16_t e = T.list[ pc ][ p ];
+            if ( ( e & 0x7fffu ) == WTILE_NONLOCAL )
+                continue;
+            const uint32_t lo = ( e & WTILE_LO ) ? p : ( e & 0x7fffu ), hi = ( e & WTILE_LO ) ? ( e & 0x7fffu ) : p;
+            if ( head_ready( lo, hi ) && atomicExch( &T.qmark[ lo ], round ) != round )
+                T.queue[ nxt ][ atomicAdd( &T.qlen[ nxt ], 1u ) ] = (uint16_t)lo;
+        }
+        __syncthreads();
     }
 
     // ---- write back what moved ----
     for ( uint32_t s = threadIdx.x; s < count; s += WTILE_THREADS ) {
         const uint32_t w = T.st[ s ];
-        if ( w >> PC_BITS ) {   // advanced at least once in this pass
+        if ( w & WTILE_MOVED ) {   // advanced at least once in this pass
             int lo = 0, hi = nrows;
             while ( hi - lo > 1 ) {
                 const int mid = ( lo + hi ) >> 1;
