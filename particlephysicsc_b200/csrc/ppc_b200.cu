@@ -64,6 +64,9 @@ struct Store {
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     size_t       wave_cap = 0;
     int          wave_grid = 0;
+    WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
+    uint32_t    *wave_n_items = nullptr;
+    size_t       wave_items_stride = 0;
     uint32_t    *h_active = nullptr;   // pinned [2]: particles with contacts, densest tile (per 1024 cells), as of a recent substep
     // last grid
     bool     grid_valid = false, pre_valid = false;
@@ -504,13 +507,29 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                     PPC_CK( cudaFuncSetAttribute( k_wave_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( WaveTileSmem ) ) );
                     configured = true;
                 }
-                const int tw = WTILE_TW;   // fixed; dense tiles subdivide themselves (see k_wave_tile)
-                for ( int pass = 0; pass < passes; pass++ ) {
-                    const int off_x = ( pass & 1 ) ? tw / 2 : 0, off_y = ( ( pass >> 1 ) & 1 ) ? tw / 2 : 0;
-                    const int tiles_x = ( G.cols + off_x + tw - 1 ) / tw, tiles_y = ( G.rows + off_y + tw - 1 ) / tw;
-                    PPC_LAUNCH( k_wave_tile, (unsigned)( tiles_x * tiles_y ), WTILE_THREADS, sizeof( WaveTileSmem ), st->stream, S, pv_out, cs,
-                                G, dt, WB, tw, off_x, off_y, tiles_x, pass == passes - 1 ? 1 : 0 );
+                const int    tw  = WTILE_TW;   // fixed; dense tiles subdivide themselves (see k_wave_plan)
+                const int    txn = ( G.cols + tw / 2 + tw - 1 ) / tw, tyn = ( G.rows + tw / 2 + tw - 1 ) / tw;
+                const size_t tiles = (size_t)txn * tyn;
+                // at most f*f items per tile, and a tile only subdivides when it holds many particles
+                size_t       stride = tiles + n / 90 + 64;
+                if ( stride > tiles * 25 )
+                    stride = tiles * 25;
+                if ( stride > st->wave_items_stride ) {
+                    PPC_CK( cudaStreamSynchronize( st->stream ) );
+                    cudaFree( st->wave_items );
+                    st->wave_items        = dev_alloc<WaveItem>( stride * 4 );
+                    st->wave_items_stride = stride;
                 }
+                if ( !st->wave_n_items )
+                    st->wave_n_items = dev_alloc<uint32_t>( 8 );
+                const int np = passes > 4 ? 4 : passes;   // the four tilings repeat after four passes
+                PPC_CK( cudaMemsetAsync( st->wave_n_items, 0, 8 * sizeof( uint32_t ), st->stream ) );
+                PPC_LAUNCH( k_wave_plan, div_up( tiles * np * 32, 256 ), 256, 0, st->stream, cs, G, tw, np, st->wave_items,
+                            (uint32_t)st->wave_items_stride, st->wave_n_items, st->wave.counters + 5 );
+                for ( int pass = 0; pass < passes; pass++ )
+                    PPC_LAUNCH( k_wave_tile, (unsigned)st->wave_items_stride, WTILE_THREADS, sizeof( WaveTileSmem ), st->stream, S, pv_out, cs,
+                                G, dt, WB, tw, pass & 3, st->wave_items, (uint32_t)st->wave_items_stride, st->wave_n_items,
+                                pass == passes - 1 ? 1 : 0 );
             }
             int       grid = st->wave_grid;
             const int want = (int)div_up( n, WAVE_THREADS );
@@ -596,6 +615,8 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFree( st->cell_start );
         cudaFree( st->d_word );
         cudaFreeHost( st->h_active );
+        cudaFree( st->wave_items );
+        cudaFree( st->wave_n_items );
         cudaEventDestroy( st->ev0 );
         cudaEventDestroy( st->ev1 );
         cudaStreamDestroy( st->stream );

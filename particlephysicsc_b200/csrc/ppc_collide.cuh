@@ -365,6 +365,7 @@ constexpr int TILE_BW      = TILE_MAX_WC + 4;   // boundary-table row stride
 struct TileSmem {
     float4   cand[ TILE_CAP ];                    // x, y, radius, API index (bits)
     float    mass[ TILE_CAP ];   // INVERSE mass 1 / (float)(uint8_t)m
+    uint8_t  ccol[ TILE_CAP ];   // cell column of the particle, relative to the first staged column
     uint32_t bound[ ( TILE_R + 2 ) * TILE_BW ];   // bound[j][i] = first staged index of cell c0 + i in staged row j
     uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_s0[ TILE_R + 1 ];
     uint32_t fallback;
@@ -468,6 +469,15 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
         const float2   a = S.rm[ g ];
         T.cand[ t ]      = make_float4( p.x, p.y, a.x, __uint_as_float( S.gid[ g ] ) );
         T.mass[ t ]      = inv_mass_u8( a.y );   // inverse mass, as the resolve reads it (:141-147)
+        int clo = 0, chi = nb - 1;               // column i with bound[j][i] <= t < bound[j][i+1]
+        while ( chi - clo > 1 ) {
+            const int mid = ( clo + chi ) >> 1;
+            if ( t >= T.bound[ j * TILE_BW + mid ] )
+                clo = mid;
+            else
+                chi = mid;
+        }
+        T.ccol[ t ] = (uint8_t)clo;
     }
     __syncthreads();
 
@@ -485,8 +495,12 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
         const int      gy = (int)( key / (uint32_t)G.cols ), gx = (int)( key - (uint32_t)gy * (uint32_t)G.cols );
         const int      lo = max( gx - 1, 0 ), hi = min( gx + 1, G.cols - 1 );
 
-        uint32_t stash[ TILE_STASH ];   // staged index | scan-cell ordinal << 16
-        uint32_t nh = 0;
+        // hits: staged index | staged row << 16, and a 64-bit key that sorts them into the reference's list order:
+        //   pairs (i, me), i < me : key = i                                   (ascending i, all before the pairs (me, *))
+        //   pairs (me, j), j > me : key = 2^40 | scan cell << 32 | ~j         (scan order, descending index inside a cell)
+        uint32_t           stash[ TILE_STASH ];
+        unsigned long long skey[ TILE_STASH ];
+        uint32_t           nh = 0;
 #pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
             const int ry = gy - 1 + d;
@@ -507,9 +521,10 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
                 const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
                 if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
                     if ( nh < (uint32_t)TILE_STASH ) {
-                        const uint32_t ord = (uint32_t)d * 4u + ( s >= B[ min( lo + 1, hi + 1 ) - c0 ] ? 1u : 0u ) +
-                                             ( s >= B[ min( lo + 2, hi + 1 ) - c0 ] ? 1u : 0u );
-                        stash[ nh ] = s | ( ord << 16 );
+                        const uint32_t g = __float_as_uint( c.w );
+                        stash[ nh ]      = s | ( (uint32_t)d << 16 );
+                        skey[ nh ]       = g < gid ? (unsigned long long)g
+                                                   : ( 1ull << 40 ) | ( (unsigned long long)( (uint32_t)d * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
                     }
                     nh++;
                 }
@@ -533,21 +548,18 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
 #pragma unroll 1
         for ( uint32_t a = 0; a < nh; a++ ) {
             uint32_t           best = a;
-            unsigned long long bkey = ~0ull;
+            unsigned long long bkey = skey[ a ];
 #pragma unroll 1
-            for ( uint32_t b = a; b < nh; b++ ) {
-                const uint32_t           e  = stash[ b ];
-                const uint32_t           g  = __float_as_uint( T.cand[ e & 0xffffu ].w );
-                const unsigned long long k2 = g < gid ? (unsigned long long)g
-                                                      : ( 1ull << 40 ) | ( (unsigned long long)( e >> 16 ) << 32 ) | ( 0xffffffffu - g );
-                if ( k2 < bkey ) {
-                    bkey = k2;
+            for ( uint32_t b = a + 1; b < nh; b++ )
+                if ( skey[ b ] < bkey ) {
+                    bkey = skey[ b ];
                     best = b;
                 }
-            }
             const uint32_t e = stash[ best ];
             stash[ best ]    = stash[ a ];
+            skey[ best ]     = skey[ a ];
             stash[ a ]       = e;
+            skey[ a ]        = bkey;
             const uint32_t s     = e & 0xffffu;
             const float4   c     = T.cand[ s ];
             const bool     me_lo = gid < __float_as_uint( c.w );
@@ -565,9 +577,7 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
                     Y = __fsub_rn( Y, P.dpy_hi );
                 }
             }
-            int jj = 0;   // staged row of the partner -> its storage slot
-            while ( jj < TILE_R + 1 && s >= T.run_s0[ jj + 1 ] )
-                jj++;
+            const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
             WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
         }
         const float4 old = S.pv[ gk ];
@@ -927,40 +937,69 @@ __device__ __forceinline__ void wave_tile_body( WaveTileSmem &T, const ParticleS
     }
 }
 
-__global__ void __launch_bounds__( WTILE_THREADS, 3 ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
-                                                                const GridDims G, const float dt, const WaveBuffers WB, const int tw,
-                                                                const int off_x, const int off_y, const int tiles_x, const int last_pass ) {
-    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
-    WaveTileSmem &T = *reinterpret_cast<WaveTileSmem *>( smem_raw );
-    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+// Work items of one tile pass.  Density varies across the box (a polydisperse pile holds ten times more small particles
+// per cell than large ones), so a tile that would overflow shared memory is cut into f x f sub-tiles, f in {3, 5}.  f is
+// ODD on purpose: the shifted passes move the tiling by tw/2 = (f/2) sub-tile widths, a half-integer, so every sub-tile
+// boundary of one pass falls in the middle of a sub-tile of the shifted pass (and an odd subdivision never shares a
+// boundary with a half-shifted odd one).  Each sub-tile is its own CTA, so their memory latencies overlap.
+struct WaveItem {
+    uint16_t tx, ty;
+    uint8_t  f, kx, ky, pad;
+};
+
+// One warp per (pass, tile): count the tile's particles, choose f, append f*f items to the pass's list.
+__global__ void __launch_bounds__( 256 ) k_wave_plan( const uint32_t *__restrict__ cell_start, const GridDims G, const int tw, const int passes,
+                                                      WaveItem *__restrict__ items, const uint32_t items_stride, uint32_t *__restrict__ n_items,
+                                                      uint32_t *__restrict__ left_flag ) {
+    const unsigned lane = threadIdx.x & 31u;
+    const size_t   w    = ( (size_t)blockIdx.x * 256 + threadIdx.x ) >> 5;
+    const int      txn = ( G.cols + tw / 2 + tw - 1 ) / tw, tyn = ( G.rows + tw / 2 + tw - 1 ) / tw;   // enough for every shift
+    const size_t   per_pass = (size_t)txn * tyn;
+    if ( w >= per_pass * passes )
+        return;
+    const int pass = (int)( w / per_pass ), tile = (int)( w % per_pass );
+    const int tx = tile % txn, ty = tile / txn;
+    const int off_x = ( pass & 1 ) ? tw / 2 : 0, off_y = ( ( pass >> 1 ) & 1 ) ? tw / 2 : 0;
     const int cxa = max( tx * tw - off_x, 0 ), cxb = min( tx * tw - off_x + tw, G.cols );
     const int cya = max( ty * tw - off_y, 0 ), cyb = min( ty * tw - off_y + tw, G.rows );
-    if ( cxa >= cxb || cya >= cyb )
-        return;
-    // Density varies across the box (a polydisperse pile holds ten times more small particles per cell than large ones),
-    // so a tile that would overflow shared memory is cut into f x f sub-tiles, f in {3, 5}.  f is ODD on purpose: the
-    // shifted passes move the tiling by tw/2 = (f/2) sub-tile widths, a half-integer, so every sub-tile boundary of one
-    // pass falls in the middle of a sub-tile of the shifted pass (and two odd subdivisions never share a boundary with
-    // a half-shifted one either).  A sub-tile that still overflows is left to the global rounds.
-    __shared__ uint32_t tile_total;
-    if ( threadIdx.x == 0 )
-        tile_total = 0;
-    __syncthreads();
-    if ( (int)threadIdx.x < cyb - cya ) {
-        const size_t row = (size_t)( cya + threadIdx.x ) * G.cols;
-        atomicAdd( &tile_total, cell_start[ row + cxb ] - cell_start[ row + cxa ] );
-    }
-    __syncthreads();
-    const uint32_t total = tile_total;
+    uint32_t  total = 0;
+    if ( cxa < cxb )
+        for ( int y = cya + (int)lane; y < cyb; y += 32 )
+            total += cell_start[ (size_t)y * G.cols + cxb ] - cell_start[ (size_t)y * G.cols + cxa ];
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        total += __shfl_xor_sync( 0xffffffffu, total, d );
     if ( total == 0 )
         return;
-    const int f  = total <= (uint32_t)( WTILE_CAP * 85 / 100 ) ? 1 : ( total <= 9u * ( WTILE_CAP / 2 ) ? 3 : 5 );
-    const int sw = tw / f;                                    // tw is a multiple of 30
-    const int ox = tx * tw - off_x, oy = ty * tw - off_y;     // unclipped origin: sub-tile boundaries do not depend on clipping
-    for ( int ky = 0; ky < f; ky++ )
-        for ( int kx = 0; kx < f; kx++ )
-            wave_tile_body( T, S, pv_out, cell_start, G, dt, WB, max( ox + kx * sw, 0 ), min( ox + ( kx + 1 ) * sw, G.cols ),
-                            max( oy + ky * sw, 0 ), min( oy + ( ky + 1 ) * sw, G.rows ), last_pass );
+    const uint32_t f    = total <= (uint32_t)( WTILE_CAP * 85 / 100 ) ? 1u : ( total <= 9u * ( WTILE_CAP / 2 ) ? 3u : 5u );
+    uint32_t       base = 0;
+    if ( lane == 0 )
+        base = atomicAdd( &n_items[ pass ], f * f );
+    base = __shfl_sync( 0xffffffffu, base, 0 );
+    if ( lane < f * f ) {
+        WaveItem it;
+        it.tx = (uint16_t)tx, it.ty = (uint16_t)ty, it.f = (uint8_t)f, it.kx = (uint8_t)( lane % f ), it.ky = (uint8_t)( lane / f ), it.pad = 0;
+        if ( base + lane < items_stride )
+            items[ (size_t)pass * items_stride + base + lane ] = it;
+        else
+            atomicAdd( left_flag, 1u );   // list full (cannot happen with the host's bound): leave the work to the global rounds
+    }
+}
+
+__global__ void __launch_bounds__( WTILE_THREADS, 3 ) k_wave_tile( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                                   const GridDims G, const float dt, const WaveBuffers WB, const int tw,
+                                                                   const int pass, const WaveItem *__restrict__ items,
+                                                                   const uint32_t items_stride, const uint32_t *__restrict__ n_items,
+                                                                   const int last_pass ) {
+    if ( blockIdx.x >= min( n_items[ pass ], items_stride ) )
+        return;
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    WaveTileSmem  &T  = *reinterpret_cast<WaveTileSmem *>( smem_raw );
+    const WaveItem it = items[ (size_t)pass * items_stride + blockIdx.x ];
+    const int      off_x = ( pass & 1 ) ? tw / 2 : 0, off_y = ( ( pass >> 1 ) & 1 ) ? tw / 2 : 0;
+    const int      sw = tw / it.f;                                       // tw is a multiple of 30
+    const int      ox = it.tx * tw - off_x + it.kx * sw, oy = it.ty * tw - off_y + it.ky * sw;   // unclipped origin of the sub-tile
+    wave_tile_body( T, S, pv_out, cell_start, G, dt, WB, max( ox, 0 ), min( ox + sw, G.cols ), max( oy, 0 ), min( oy + sw, G.rows ), last_pass );
 }
 
 // ---- candidate-pair list in the reference's order (parity exporter; not on the hot path) -----------------------
