@@ -112,8 +112,10 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *   "resolve"  1 = sequential-equivalent wavefront: replays the reference's pair order, bit-exact (default),
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
  *   "collide"  0 = auto (shared-memory tile kernel), 1 = global-memory thread-per-particle kernel
- *   "wave_passes"  shared-memory tile passes of the wavefront before the global rounds: default 4, used only while more
- *              than a quarter of the particles are in contact; 0 = global rounds only; -k = always k passes */
+ *   "wave_mode"    global rounds of the wavefront: 1 = event driven on packed records (default), 0 = polling
+ *   "wave_passes"  shared-memory tile passes ahead of the (polling) global rounds: 0 = none (default); k = k passes while
+ *              more than a quarter of the particles are in contact; -k = always k passes.  Experimental: correct, but
+ *              slower than the event-driven rounds on every workload measured so far */
 int ppc_set_option( struct Particles_t *p, const char *name, long long value );
 
 /* ---- parity exporters: state of the LAST grid build (all return 0 on success, -1 if no grid was built) ---- */

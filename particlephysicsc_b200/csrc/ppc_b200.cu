@@ -44,7 +44,7 @@ struct Store {
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
-    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 4;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -62,6 +62,8 @@ struct Store {
     size_t       scratch_words = 0;
     uint32_t    *d_word = nullptr;   // one word for small reductions
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
+    WaveRecs     recs = {};          // packed records of the event-driven rounds
+    int          events_grid = 0;
     size_t       wave_cap = 0;
     int          wave_grid = 0;
     WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
@@ -131,6 +133,9 @@ static void free_wave_buffers( Store *st ) {
     cudaFree( st->wave.list[ 0 ] );
     cudaFree( st->wave.list[ 1 ] );
     cudaFree( st->wave.counters );
+    cudaFree( st->recs.wr );
+    cudaFree( st->recs.dr );
+    st->recs     = WaveRecs{};
     st->wave     = WaveBuffers{};
     st->wave_cap = 0;
 }
@@ -162,6 +167,14 @@ static void ensure_wave_buffers( Store *st ) {
         abort();
     }
     st->wave_grid = per_sm * sms;
+    st->recs.wr   = dev_alloc<WaveRec>( cap );
+    st->recs.dr   = dev_alloc<DynRec>( cap );
+    PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_events, EV_THREADS, 0 ) );
+    if ( per_sm < 1 ) {
+        fprintf( stderr, "particlephysicsc_b200: event wavefront kernel cannot be made resident\n" );
+        abort();
+    }
+    st->events_grid = ( per_sm > 4 ? 4 : per_sm ) * sms;   // a few CTAs per SM: enough loads in flight, cheap grid barrier
 }
 
 static void check_device_flags( Store *st ) {   // after a stream synchronise
@@ -531,15 +544,27 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                                 G, dt, WB, tw, pass & 3, st->wave_items, (uint32_t)st->wave_items_stride, st->wave_n_items,
                                 pass == passes - 1 ? 1 : 0 );
             }
-            int       grid = st->wave_grid;
-            const int want = (int)div_up( n, WAVE_THREADS );
-            if ( grid > want )
-                grid = want;
-            size_t n_arg   = n;
-            int    after   = passes > 0 ? 1 : 0;
-            void  *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&after };
-            PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_wavefront, dim3( grid ), dim3( WAVE_THREADS ), args, 0, st->stream ) );
-            ++g_launches;
+            size_t n_arg = n;
+            if ( st->opt_wave_mode == 1 && passes == 0 ) {   // event-driven rounds on packed records (default)
+                const WaveRecs R = st->recs;
+                PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
+                int       grid = st->events_grid;
+                const int want = (int)div_up( n, EV_THREADS );
+                if ( grid > want )
+                    grid = want;
+                void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&R };
+                PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_events, dim3( grid ), dim3( EV_THREADS ), args, 0, st->stream ) );
+                ++g_launches;
+            } else {   // polling rounds (after tile passes, or "wave_mode"=0)
+                int       grid = st->wave_grid;
+                const int want = (int)div_up( n, WAVE_THREADS );
+                if ( grid > want )
+                    grid = want;
+                int   after   = passes > 0 ? 1 : 0;
+                void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&after };
+                PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_wavefront, dim3( grid ), dim3( WAVE_THREADS ), args, 0, st->stream ) );
+                ++g_launches;
+            }
         }
         float4 *t = S.pv;   // post-resolve state becomes current; the pre-resolve one stays readable in the other
         S.pv      = O.pv;   // set until the next substep (ppc_debug_pairs uses it)
@@ -775,6 +800,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_collide = (int)value;
     else if ( !strcmp( name, "wave_passes" ) )
         st->opt_wave_passes = (int)value;
+    else if ( !strcmp( name, "wave_mode" ) )
+        st->opt_wave_mode = (int)value;
     else
         return -1;
     return 0;

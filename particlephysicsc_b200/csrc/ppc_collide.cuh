@@ -497,7 +497,7 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
 
         // hits: staged index | staged row << 16, and a 64-bit key that sorts them into the reference's list order:
         //   pairs (i, me), i < me : key = i                                   (ascending i, all before the pairs (me, *))
-        //   pairs (me, j), j > me : key = 2^40 | scan cell << 32 | ~j         (scan order, descending index inside a cell)
+        //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j         (scan order, descending index inside a cell)
         uint32_t           stash[ TILE_STASH ];
         unsigned long long skey[ TILE_STASH ];
         uint32_t           nh = 0;
@@ -524,7 +524,7 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
                         const uint32_t g = __float_as_uint( c.w );
                         stash[ nh ]      = s | ( (uint32_t)d << 16 );
                         skey[ nh ]       = g < gid ? (unsigned long long)g
-                                                   : ( 1ull << 40 ) | ( (unsigned long long)( (uint32_t)d * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
+                                                   : ( 1ull << 48 ) | ( (unsigned long long)( (uint32_t)d * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
                     }
                     nh++;
                 }
@@ -735,6 +735,180 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
             if ( blockIdx.x == 0 )
                 WB.counters[ 4 ] = r;
         }
+        grid.sync();
+    }
+}
+
+// ---- K7b, event-driven global rounds on packed records -------------------------------------------------------------
+// The polling rounds above touch every still-active particle in every round, six scattered sectors per visit.  Here
+// (a) a particle is only examined when something changed for it: once at the start, and in the round after each of its
+// own advances (the executor of a pair queues both particles).  A pair becomes ready exactly when the later of its two
+// predecessor pairs fires, and that fire queues the particle they share, so nothing is missed;
+// (b) everything an examination or a fire needs sits in two 32-byte records per particle, one sector each:
+//     WaveRec {state, deg, first 6 contacts}  and  DynRec {x, y, r, 1/m (frozen), vx, vy (current)}.
+// Firing rule and stamps are those of k_resolve_wavefront; a pair is claimed by a compare-and-swap of its i particle's
+// state word to this round's stamp, so two threads that examine the two ends of a ready pair fire it once.
+struct __align__( 16 ) WaveRec {
+    uint32_t state;      // (round of last advance or claim << PC_BITS) | contacts already resolved
+    uint32_t deg;
+    uint32_t c[ 6 ];     // contacts 0..5: partner slot | INC_LO_FLAG; later ones stay in WaveBuffers::inc
+};
+struct __align__( 16 ) DynRec {
+    float x, y, r, w;    // frozen pass-1 geometry (:84-127) and inverse mass (:141-147)
+    float vx, vy;        // current velocity
+    float pad0, pad1;
+};
+constexpr int WREC_INLINE = 6;
+
+struct WaveRecs {
+    WaveRec *wr;
+    DynRec  *dr;
+};
+
+// Build the records of the particles that have contacts (one thread per particle).
+__global__ void __launch_bounds__( 256 ) k_wave_pack( const ParticleSet S, const float4 *__restrict__ pv_out, const WaveBuffers WB,
+                                                      const WaveRecs R, const size_t n ) {
+    const size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if ( k >= n )
+        return;
+    const uint32_t d = WB.deg[ k ];
+    if ( d == 0 )
+        return;
+    WaveRec w;
+    w.state = 0;
+    w.deg   = d;
+#pragma unroll
+    for ( int c = 0; c < WREC_INLINE; c++ )
+        w.c[ c ] = ( (uint32_t)c < d && (uint32_t)c < WB.maxdeg ) ? WB.inc[ (size_t)c * WB.stride + k ] : 0u;
+    R.wr[ k ] = w;
+    const float4 p = S.pv[ k ];
+    const float2 a = S.rm[ k ];
+    const float4 o = pv_out[ k ];
+    DynRec       q;
+    q.x = p.x, q.y = p.y, q.r = a.x, q.w = inv_mass_u8( a.y ), q.vx = o.z, q.vy = o.w, q.pad0 = q.pad1 = 0.0f;
+    R.dr[ k ] = q;
+}
+
+__device__ __forceinline__ uint32_t rec_head( const ParticleSet &S, const GlobalAccessor &acc, const GridDims &G, const WaveBuffers &WB,
+                                              const WaveRec &w, const uint32_t k, const uint32_t pc ) {
+    if ( pc < (uint32_t)WREC_INLINE )
+        return w.c[ pc ];
+    if ( w.deg <= WB.maxdeg )
+        return WB.inc[ (size_t)pc * WB.stride + k ];
+    return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
+}
+
+__device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
+    const uint4 a = __ldcg( reinterpret_cast<const uint4 *>( p ) ), b = __ldcg( reinterpret_cast<const uint4 *>( p ) + 1 );
+    WaveRec     w;
+    w.state = a.x, w.deg = a.y, w.c[ 0 ] = a.z, w.c[ 1 ] = a.w, w.c[ 2 ] = b.x, w.c[ 3 ] = b.y, w.c[ 4 ] = b.z, w.c[ 5 ] = b.w;
+    return w;
+}
+
+constexpr int EV_THREADS = 256;
+constexpr int EV_BUF     = 2048;   // per-CTA staging of queue pushes: one global atomic per flush
+
+__global__ void __launch_bounds__( EV_THREADS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                                  const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
+                                                                  const WaveRecs R ) {
+    namespace cg        = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
+    __shared__ uint32_t  buf[ EV_BUF ];
+    __shared__ uint32_t  buf_n, buf_base;
+    volatile uint32_t   *counters = WB.counters;
+    const size_t         tid_g = (size_t)blockIdx.x * EV_THREADS + threadIdx.x, nthreads = (size_t)gridDim.x * EV_THREADS;
+    if ( threadIdx.x == 0 )
+        buf_n = 0;
+    __syncthreads();
+
+    for ( uint32_t r = 1;; r++ ) {
+        const uint32_t n_q = r == 1 ? 0u : counters[ ( r - 1 ) % 3 ];
+        if ( r > 1 && n_q == 0 )
+            break;
+        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {
+            if ( blockIdx.x == 0 && threadIdx.x == 0 )
+                atomicOr( &WB.counters[ 3 ], 2u );
+            break;
+        }
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            counters[ ( r + 1 ) % 3 ] = 0;
+        const uint32_t *src   = WB.list[ ( r - 1 ) & 1 ];
+        uint32_t       *dst   = WB.list[ r & 1 ];
+        uint32_t       *d_cnt = &WB.counters[ r % 3 ];
+        const size_t    items = r == 1 ? n : (size_t)n_q;
+        const size_t    iters = ( items + nthreads - 1 ) / nthreads;
+
+        for ( size_t it = 0; it < iters; it++ ) {   // uniform trip count: the flush below uses CTA barriers
+            const size_t i = it * nthreads + tid_g;
+            uint32_t     push0 = 0xffffffffu, push1 = 0xffffffffu;
+            if ( i < items ) {
+                const uint32_t p = r == 1 ? (uint32_t)i : src[ i ];
+                if ( r > 1 || WB.deg[ p ] != 0 ) {
+                    const WaveRec  A   = load_wave_rec( R.wr + p );
+                    const uint32_t pcA = A.state & PC_MASK;
+                    if ( pcA < A.deg && ( A.state >> PC_BITS ) != r ) {
+                        const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
+                        const WaveRec  B = load_wave_rec( R.wr + o );
+                        const uint32_t pcB = B.state & PC_MASK;
+                        if ( pcB < B.deg && ( B.state >> PC_BITS ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) {
+                            const bool     p_lo = ( e & INC_LO_FLAG ) != 0;
+                            const uint32_t lo = p_lo ? p : o, hi = p_lo ? o : p;
+                            const uint32_t st_lo = p_lo ? A.state : B.state, st_hi = p_lo ? B.state : A.state;
+                            const uint32_t deg_lo = p_lo ? A.deg : B.deg, deg_hi = p_lo ? B.deg : A.deg;
+                            const uint32_t claim = ( r << PC_BITS ) | ( st_lo & PC_MASK );
+                            if ( atomicCAS( &R.wr[ lo ].state, st_lo, claim ) == st_lo ) {   // this thread fires the pair
+                                const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
+                                const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
+                                float2      *va = reinterpret_cast<float2 *>( R.dr + lo ) + 2, *vb = reinterpret_cast<float2 *>( R.dr + hi ) + 2;
+                                float2       ua = __ldcg( va ), ub = __ldcg( vb );
+                                const ImpulseTerms T =
+                                    impulse_terms( contact_geom( ga.x, ga.y, ga.z, gb.x, gb.y, gb.z, dt ), ga.w, gb.w, ua.x, ua.y, ub.x, ub.y );
+                                if ( T.impulse ) {
+                                    ua.x = __fadd_rn( ua.x, T.dvx_lo );
+                                    ua.y = __fadd_rn( ua.y, T.dvy_lo );
+                                    ub.x = __fsub_rn( ub.x, T.dvx_hi );
+                                    ub.y = __fsub_rn( ub.y, T.dvy_hi );
+                                    *va  = ua;
+                                    *vb  = ub;
+                                }
+                                const uint32_t nlo = ( st_lo & PC_MASK ) + 1, nhi = ( st_hi & PC_MASK ) + 1;
+                                R.wr[ lo ].state = ( r << PC_BITS ) | nlo;
+                                R.wr[ hi ].state = ( r << PC_BITS ) | nhi;
+                                if ( nlo < deg_lo )
+                                    push0 = lo;
+                                else
+                                    *( reinterpret_cast<float2 *>( pv_out + lo ) + 1 ) = ua;   // last contact done: final velocity
+                                if ( nhi < deg_hi )
+                                    push1 = hi;
+                                else
+                                    *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;
+                            }
+                        }
+                    }
+                }
+            }
+            // stage the pushes in shared memory; flush with one global atomic when the buffer could overflow
+            if ( push0 != 0xffffffffu )
+                buf[ atomicAdd( &buf_n, 1u ) ] = push0;
+            if ( push1 != 0xffffffffu )
+                buf[ atomicAdd( &buf_n, 1u ) ] = push1;
+            __syncthreads();
+            const uint32_t staged = buf_n;   // read between two barriers: the same value in every thread
+            __syncthreads();
+            if ( staged > (uint32_t)( EV_BUF - 2 * EV_THREADS ) || ( it + 1 == iters && staged ) ) {
+                if ( threadIdx.x == 0 ) {
+                    buf_base = atomicAdd( d_cnt, staged );
+                    buf_n    = 0;
+                }
+                __syncthreads();
+                for ( uint32_t t = threadIdx.x; t < staged; t += EV_THREADS )
+                    dst[ buf_base + t ] = buf[ t ];
+                __syncthreads();
+            }
+        }
+        if ( threadIdx.x == 0 && blockIdx.x == 0 )
+            WB.counters[ 4 ] = r;
         grid.sync();
     }
 }

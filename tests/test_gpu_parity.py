@@ -191,17 +191,19 @@ def test_tile_kernel_equals_global_kernel(oracle):
         b.Free()
 
 
-def test_wavefront_tile_passes_equal_global_rounds(oracle):
-    """Shared-memory tile passes (default 4) vs global rounds only ("wave_passes"=0) vs a single pass: same bits."""
+def test_wavefront_variants_agree(oracle):
+    """Event-driven rounds on packed records (default), polling rounds ("wave_mode"=0) and shared-memory tile passes ahead
+    of the polling rounds ("wave_passes"): all replay the same dependency order, so all give the reference's bits."""
     sc = scenes.polydisperse_pile(40000, seed=116)
     ref = state_from_scene(sc)
     for _ in range(8):
         oracle.substep(ref, sc.W, sc.H, DT, 0, False)
-    for passes in (0, -1, 4, -7):
+    for opts in ({}, {"wave_mode": 0}, {"wave_passes": -1}, {"wave_passes": -4}, {"wave_passes": -7}, {"wave_passes": 4}):
         p = gpu_store(state_from_scene(sc))
-        p.set_option("wave_passes", passes)
+        for k, v in opts.items():
+            p.set_option(k, v)
         p.run_substeps(sc.W, sc.H, DT, 8)
-        assert_state_bits(gpu_state(p), ref, f"wave_passes={passes}")
+        assert_state_bits(gpu_state(p), ref, f"wavefront options {opts}")
         p.Free()
 
 
