@@ -112,7 +112,8 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *   "resolve"  1 = sequential-equivalent wavefront: replays the reference's pair order, bit-exact (default),
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
  *   "collide"  0 = auto (shared-memory tile kernel), 1 = global-memory thread-per-particle kernel
- *   "wave_mode"    global rounds of the wavefront: 1 = event driven on packed records (default), 0 = polling
+ *   "wave_mode"    global rounds of the wavefront: 1 = event driven on packed records while more than a quarter of the
+ *              particles are in contact, else polling (default); 2 = always event driven; 0 = always polling
  *   "wave_passes"  shared-memory tile passes ahead of the (polling) global rounds: 0 = none (default); k = k passes while
  *              more than a quarter of the particles are in contact; -k = always k passes.  Experimental: correct, but
  *              slower than the event-driven rounds on every workload measured so far */

@@ -174,7 +174,7 @@ static void ensure_wave_buffers( Store *st ) {
         fprintf( stderr, "particlephysicsc_b200: event wavefront kernel cannot be made resident\n" );
         abort();
     }
-    st->events_grid = ( per_sm > 4 ? 4 : per_sm ) * sms;   // a few CTAs per SM: enough loads in flight, cheap grid barrier
+    st->events_grid = per_sm * sms;   // latency bound: as many loads in flight as the SM holds
 }
 
 static void check_device_flags( Store *st ) {   // after a stream synchronise
@@ -545,7 +545,9 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                                 pass == passes - 1 ? 1 : 0 );
             }
             size_t n_arg = n;
-            if ( st->opt_wave_mode == 1 && passes == 0 ) {   // event-driven rounds on packed records (default)
+            // packed records pay off when most particles are in contact; sparse contact sets are cheaper on the polling
+            // kernel's compact per-CTA queues (no pack pass).  "wave_mode": 1 = choose by density (default), 2 = always events.
+            if ( ( st->opt_wave_mode == 2 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
                 const WaveRecs R = st->recs;
                 PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
                 int       grid = st->events_grid;
