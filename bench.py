@@ -106,8 +106,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def time_reference_cpu(workload: str, steps: int, warmup: int):
-    """The reference's own CPU solver on a bounded sample of the workload (single-threaded, as the reference is)."""
+def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float = 0.0):
+    """The reference's own CPU solver on a bounded sample of the workload (single-threaded, as the reference is).
+
+    The sample is a field of the same generator and density with 2**k particles.  With budget_s > 0 (the ``--impl
+    reference`` arm, whose K and W come from the driver) k is chosen from a one-step calibration on 2**16 particles so
+    that the whole run takes about budget_s seconds; otherwise 2**20 particles are used."""
     from oracle import oracle as om
     if om.reference_available():
         R, kind = om.Reference(), "reference"
@@ -115,9 +119,21 @@ def time_reference_cpu(workload: str, steps: int, warmup: int):
     else:   # the reference sources are not here and no prebuilt libref.so travelled: time our C restatement
         O, kind = om.Oracle(), "port"
         step = lambda s, W, H: O.substep(s, W, H, DT, 0, True)
+
+    def field(n):
+        sc = make_scene(workload, n)
+        return sc, om.State(sc.px.copy(), sc.py.copy(), sc.vx.copy(), sc.vy.copy(), sc.mass.copy(), sc.radius.copy(), sc.rgba.copy())
+
     n = min(CPU_SAMPLE_PARTICLES, WORKLOADS[workload][0])
-    sc = make_scene(workload, n)
-    s = om.State(sc.px.copy(), sc.py.copy(), sc.vx.copy(), sc.vy.copy(), sc.mass.copy(), sc.radius.copy(), sc.rgba.copy())
+    if budget_s > 0:
+        sc, s = field(1 << 16)
+        t0 = time.perf_counter()
+        step(s, sc.W, sc.H)
+        per_particle = (time.perf_counter() - t0) / (1 << 16)
+        want = budget_s / max(1, steps + warmup) / per_particle
+        n = 1 << max(14, min(20, int(np.floor(np.log2(max(want, 1.0))))))
+        n = min(n, WORKLOADS[workload][0])
+    sc, s = field(n)
     for _ in range(warmup):
         step(s, sc.W, sc.H)
     t0 = time.perf_counter()
@@ -133,7 +149,7 @@ def time_reference_cpu(workload: str, steps: int, warmup: int):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    value, ms, base = time_reference_cpu(args.workload, args.steps, args.warmup)
+    value, ms, base = time_reference_cpu(args.workload, args.steps, args.warmup, budget_s=90.0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][1], "sample": base["sample"]},
@@ -271,7 +287,7 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--settle", type=int, default=64, help="untimed substeps that relax the synthetic field first")
-    ap.add_argument("--workload", default="uniform16m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="pile16m", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")
