@@ -57,6 +57,21 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def max_over_ranks(ms: float, dist=None, device="cpu") -> float:
+    """Slowest rank's time: every multi-GPU number is the max over ranks of a device-side duration."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(ms)
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_value(particles_per_rank: int, world: int, steps: int, ms_total: float) -> float:
+    """particle-substeps/s of the whole job: units processed by ALL ranks divided by the slowest rank's time."""
+    return particles_per_rank * world * steps / (ms_total * 1e-3)
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons, sampled every 200 ms while the timed region runs."""
 
@@ -184,12 +199,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(ms: float) -> float:
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    def max_ranks(ms: float) -> float:
+        return max_over_ranks(ms, dist, "cuda")
 
     # settle + warm-up (untimed).  State (28 B x n = %d MB at 16M) is several times the 126 MB L2, so consecutive
     # substeps cannot reuse each other's lines; no explicit flush is needed.
@@ -209,9 +220,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e1.synchronize()
     barrier()
     launches = api.kernel_launches() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_total = max_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
-    value = n * world * args.steps / (ms_total * 1e-3)
+    value = whole_job_value(n, world, args.steps, ms_total)
 
     # ---- e2e: the reference's entry points, copy-back of positions + colours every 8th substep ----
     frames = max(1, args.steps // SUBSTEPS_PER_FRAME)
@@ -228,7 +239,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     e1.record(ext)
     e1.synchronize()
     barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_ms = max_ranks(e0.elapsed_time(e1))
     e2e_value = n * world * frames * SUBSTEPS_PER_FRAME / (e2e_ms * 1e-3)
     d2h_per_step = 12.0 * n / SUBSTEPS_PER_FRAME
 
