@@ -254,10 +254,17 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     peak, peak_src = measured_peak_gbs()
     dom = max(stages, key=lambda k: stages[k][0]) if stages else None
     algo = {"integrate_walls_keys": 36.0, "collide": 40.0}.get(dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    except Exception:
+        traffic = None
     roofline = None
     if dom:
         ach = algo * n / (stages[dom][0] * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": "ncu --set full capture under profiles/ (bytes per launch)" if traffic else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_particle": algo,
                     "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
     substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * n * world * args.steps / (ms_total * 1e-3) / 1e9
