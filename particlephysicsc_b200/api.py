@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libparticlephysicsc_b200.so")
+LIB_PATH = os.environ.get("PPC_LIB") or os.path.join(HERE, "lib", "libparticlephysicsc_b200.so")   # PPC_LIB: kernel-variant experiments
 
 f32p = C.POINTER(C.c_float)
 u8p = C.POINTER(C.c_uint8)

@@ -495,7 +495,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                     configured = true;
                 }
                 const double per_cell = (double)n / (double)G.cells;
-                int          wc       = (int)( 1100.0 / ( TILE_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );   // ~1100 centre particles per tile
+                int          wc       = (int)( (double)TILE_TARGET / ( TILE_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
                 wc                    = wc < 4 ? 4 : ( wc > TILE_MAX_WC ? TILE_MAX_WC : wc );
                 const int tiles_x = ( G.cols + wc - 1 ) / wc, tiles_y = ( G.rows + TILE_R - 1 ) / TILE_R;
                 PPC_LAUNCH( k_collide_tile, (unsigned)( tiles_x * tiles_y ), TILE_THREADS, sizeof( TileSmem ), st->stream, S, O.pv,
