@@ -356,16 +356,16 @@ __global__ void __launch_bounds__( COLLIDE_THREADS ) k_collide_global( const Par
 // equal the reference's bit for bit; the ordered contact list goes to the wavefront buffers.
 // Tiles or particles that do not fit the fixed budget take the generic path.
 #ifndef PPC_TILE_MINBLOCKS
-#define PPC_TILE_MINBLOCKS 3   // 40 registers: three CTAs per SM; measured 17% faster than two on the uniform field
+#define PPC_TILE_MINBLOCKS 4   // 32 registers, four CTAs per SM: measured 26% faster than two CTAs at 60 registers (uniform16m)
 #endif
 #ifndef PPC_TILE_THREADS
 #define PPC_TILE_THREADS 512
 #endif
 #ifndef PPC_TILE_CAP
-#define PPC_TILE_CAP 3072
+#define PPC_TILE_CAP 2304
 #endif
 #ifndef PPC_TILE_TARGET
-#define PPC_TILE_TARGET 1100   // centre particles per tile the host aims for
+#define PPC_TILE_TARGET 900    // centre particles per tile the host aims for
 #endif
 #ifndef PPC_TILE_UNROLL
 #define PPC_TILE_UNROLL 2
@@ -823,10 +823,13 @@ __device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
     return w;
 }
 
+#ifndef PPC_EV_MINBLOCKS
+#define PPC_EV_MINBLOCKS 6
+#endif
 constexpr int EV_THREADS = 256;
 constexpr int EV_BUF     = 2048;   // per-CTA staging of queue pushes: one global atomic per flush
 
-__global__ void __launch_bounds__( EV_THREADS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+__global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
                                                                   const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
                                                                   const WaveRecs R ) {
     namespace cg        = cooperative_groups;
