@@ -133,8 +133,7 @@ static void free_wave_buffers( Store *st ) {
     cudaFree( st->wave.list[ 0 ] );
     cudaFree( st->wave.list[ 1 ] );
     cudaFree( st->wave.counters );
-    cudaFree( st->recs.wr );
-    cudaFree( st->recs.dr );
+    cudaFree( st->recs.rec );
     st->recs     = WaveRecs{};
     st->wave     = WaveBuffers{};
     st->wave_cap = 0;
@@ -167,8 +166,7 @@ static void ensure_wave_buffers( Store *st ) {
         abort();
     }
     st->wave_grid = per_sm * sms;
-    st->recs.wr   = dev_alloc<WaveRec>( cap );
-    st->recs.dr   = dev_alloc<DynRec>( cap );
+    st->recs.rec  = dev_alloc<WaveParticle>( cap );
     PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_events, EV_THREADS, 0 ) );
     if ( per_sm < 1 ) {
         fprintf( stderr, "particlephysicsc_b200: event wavefront kernel cannot be made resident\n" );
