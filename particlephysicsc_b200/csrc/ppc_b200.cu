@@ -133,7 +133,8 @@ static void free_wave_buffers( Store *st ) {
     cudaFree( st->wave.list[ 0 ] );
     cudaFree( st->wave.list[ 1 ] );
     cudaFree( st->wave.counters );
-    cudaFree( st->recs.rec );
+    cudaFree( st->recs.wr );
+    cudaFree( st->recs.dr );
     st->recs     = WaveRecs{};
     st->wave     = WaveBuffers{};
     st->wave_cap = 0;
@@ -166,7 +167,8 @@ static void ensure_wave_buffers( Store *st ) {
         abort();
     }
     st->wave_grid = per_sm * sms;
-    st->recs.rec  = dev_alloc<WaveParticle>( cap );
+    st->recs.wr   = dev_alloc<WaveRec>( cap );
+    st->recs.dr   = dev_alloc<DynRec>( cap );
     PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_events, EV_THREADS, 0 ) );
     if ( per_sm < 1 ) {
         fprintf( stderr, "particlephysicsc_b200: event wavefront kernel cannot be made resident\n" );

@@ -778,15 +778,9 @@ struct __align__( 16 ) DynRec {
 };
 constexpr int WREC_INLINE = 6;
 
-// One 64-byte, 64-byte-aligned record per particle: HBM is fetched in 64-byte granules (ncu: the split 2 x 32 B layout
-// read twice the bytes it used), so an examination that misses L2 brings in everything a subsequent fire needs, and a
-// fire dirties one line per particle instead of two.
-struct __align__( 64 ) WaveParticle {
-    WaveRec w;
-    DynRec  d;
-};
 struct WaveRecs {
-    WaveParticle *rec;
+    WaveRec *wr;
+    DynRec  *dr;
 };
 
 // Build the records of the particles that have contacts (one thread per particle).
@@ -804,13 +798,13 @@ __global__ void __launch_bounds__( 256 ) k_wave_pack( const ParticleSet S, const
 #pragma unroll
     for ( int c = 0; c < WREC_INLINE; c++ )
         w.c[ c ] = ( (uint32_t)c < d && (uint32_t)c < WB.maxdeg ) ? WB.inc[ (size_t)c * WB.stride + k ] : 0u;
-    R.rec[ k ].w = w;
+    R.wr[ k ] = w;
     const float4 p = S.pv[ k ];
     const float2 a = S.rm[ k ];
     const float4 o = pv_out[ k ];
     DynRec       q;
     q.x = p.x, q.y = p.y, q.r = a.x, q.w = inv_mass_u8( a.y ), q.vx = o.z, q.vy = o.w, q.pad0 = q.pad1 = 0.0f;
-    R.rec[ k ].d = q;
+    R.dr[ k ] = q;
 }
 
 __device__ __forceinline__ uint32_t rec_head( const ParticleSet &S, const GlobalAccessor &acc, const GridDims &G, const WaveBuffers &WB,
@@ -872,11 +866,11 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
             if ( i < items ) {
                 const uint32_t p = r == 1 ? (uint32_t)i : src[ i ];
                 if ( r > 1 || WB.deg[ p ] != 0 ) {
-                    const WaveRec  A   = load_wave_rec( &R.rec[ p ].w );
+                    const WaveRec  A   = load_wave_rec( R.wr + p );
                     const uint32_t pcA = A.state & PC_MASK;
                     if ( pcA < A.deg && ( A.state >> PC_BITS ) != r ) {
                         const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
-                        const WaveRec  B = load_wave_rec( &R.rec[ o ].w );
+                        const WaveRec  B = load_wave_rec( R.wr + o );
                         const uint32_t pcB = B.state & PC_MASK;
                         if ( pcB < B.deg && ( B.state >> PC_BITS ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) {
                             const bool     p_lo = ( e & INC_LO_FLAG ) != 0;
@@ -884,10 +878,10 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                             const uint32_t st_lo = p_lo ? A.state : B.state, st_hi = p_lo ? B.state : A.state;
                             const uint32_t deg_lo = p_lo ? A.deg : B.deg, deg_hi = p_lo ? B.deg : A.deg;
                             const uint32_t claim = ( r << PC_BITS ) | ( st_lo & PC_MASK );
-                            if ( atomicCAS( &R.rec[ lo ].w.state, st_lo, claim ) == st_lo ) {   // this thread fires the pair
-                                const float4 ga = __ldcg( reinterpret_cast<const float4 *>( &R.rec[ lo ].d ) );
-                                const float4 gb = __ldcg( reinterpret_cast<const float4 *>( &R.rec[ hi ].d ) );
-                                float2      *va = reinterpret_cast<float2 *>( &R.rec[ lo ].d ) + 2, *vb = reinterpret_cast<float2 *>( &R.rec[ hi ].d ) + 2;
+                            if ( atomicCAS( &R.wr[ lo ].state, st_lo, claim ) == st_lo ) {   // this thread fires the pair
+                                const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
+                                const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
+                                float2      *va = reinterpret_cast<float2 *>( R.dr + lo ) + 2, *vb = reinterpret_cast<float2 *>( R.dr + hi ) + 2;
                                 float2       ua = __ldcg( va ), ub = __ldcg( vb );
                                 const ImpulseTerms T =
                                     impulse_terms( contact_geom( ga.x, ga.y, ga.z, gb.x, gb.y, gb.z, dt ), ga.w, gb.w, ua.x, ua.y, ub.x, ub.y );
@@ -900,8 +894,8 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                     *vb  = ub;
                                 }
                                 const uint32_t nlo = ( st_lo & PC_MASK ) + 1, nhi = ( st_hi & PC_MASK ) + 1;
-                                R.rec[ lo ].w.state = ( r << PC_BITS ) | nlo;
-                                R.rec[ hi ].w.state = ( r << PC_BITS ) | nhi;
+                                R.wr[ lo ].state = ( r << PC_BITS ) | nlo;
+                                R.wr[ hi ].state = ( r << PC_BITS ) | nhi;
                                 if ( nlo < deg_lo )
                                     push0 = lo;
                                 else
