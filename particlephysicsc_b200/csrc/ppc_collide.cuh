@@ -827,7 +827,8 @@ __device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
 #define PPC_EV_MINBLOCKS 6
 #endif
 constexpr int EV_THREADS = 256;
-constexpr int EV_BUF     = 2048;   // per-CTA staging of queue pushes: one global atomic per flush
+constexpr int EV_FOLLOW  = 6;      // pairs one thread may fire in a row along a chain
+constexpr int EV_BUF     = ( EV_FOLLOW + 2 ) * EV_THREADS * 2;   // per-CTA staging of queue pushes: one global atomic per flush
 
 __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
                                                                   const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
@@ -862,7 +863,6 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
 
         for ( size_t it = 0; it < iters; it++ ) {   // uniform trip count: the flush below uses CTA barriers
             const size_t i = it * nthreads + tid_g;
-            uint32_t     push0 = 0xffffffffu, push1 = 0xffffffffu;
             if ( i < items ) {
                 const uint32_t p = r == 1 ? (uint32_t)i : src[ i ];
                 if ( r > 1 || WB.deg[ p ] != 0 ) {
@@ -890,34 +890,79 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                     ua.y = __fadd_rn( ua.y, T.dvy_lo );
                                     ub.x = __fsub_rn( ub.x, T.dvx_hi );
                                     ub.y = __fsub_rn( ub.y, T.dvy_hi );
-                                    *va  = ua;
-                                    *vb  = ub;
                                 }
-                                const uint32_t nlo = ( st_lo & PC_MASK ) + 1, nhi = ( st_hi & PC_MASK ) + 1;
-                                R.wr[ lo ].state = ( r << PC_BITS ) | nlo;
-                                R.wr[ hi ].state = ( r << PC_BITS ) | nhi;
-                                if ( nlo < deg_lo )
-                                    push0 = lo;
-                                else
-                                    *( reinterpret_cast<float2 *>( pv_out + lo ) + 1 ) = ua;   // last contact done: final velocity
+                                // the pair's j is done for this round
+                                const uint32_t nhi = ( st_hi & PC_MASK ) + 1;
+                                *vb                = ub;
+                                R.wr[ hi ].state   = ( r << PC_BITS ) | nhi;
                                 if ( nhi < deg_hi )
-                                    push1 = hi;
+                                    buf[ atomicAdd( &buf_n, 1u ) ] = hi;
                                 else
-                                    *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;
+                                    *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;   // last contact done: final velocity
+
+                                // Follow the chain from the pair's i: its list position, record and velocity stay in registers,
+                                // and its state word already carries this round's stamp, so nobody else touches it.  Its next
+                                // pair (cur, x) may fire right away iff x has not advanced in this round (its velocity was last
+                                // written before the previous grid barrier, so it is visible) and x's head is that same pair --
+                                // then no other thread can fire it: an examiner of x sees cur's stamp and backs off.
+                                const WaveRec &C   = p_lo ? A : B;   // contacts of the cursor particle
+                                const uint32_t cur = lo, cdeg = deg_lo;
+                                uint32_t       cpc = ( st_lo & PC_MASK ) + 1;
+                                float2         uc  = ua;
+                                for ( int follow = 0; follow < EV_FOLLOW && cpc < cdeg; follow++ ) {
+                                    const uint32_t e2 = rec_head( S, acc, G, WB, C, cur, cpc ), x = e2 & ~INC_LO_FLAG;
+                                    const WaveRec  X   = load_wave_rec( R.wr + x );
+                                    const uint32_t pcx = X.state & PC_MASK;
+                                    if ( ( X.state >> PC_BITS ) == r || pcx >= X.deg || ( rec_head( S, acc, G, WB, X, x, pcx ) & ~INC_LO_FLAG ) != cur )
+                                        break;
+                                    if ( atomicCAS( &R.wr[ x ].state, X.state, ( r << PC_BITS ) | pcx ) != X.state )
+                                        break;
+                                    const float4 gx = __ldcg( reinterpret_cast<const float4 *>( R.dr + x ) );
+                                    float2      *vx = reinterpret_cast<float2 *>( R.dr + x ) + 2;
+                                    float2       ux = __ldcg( vx );
+                                    if ( e2 & INC_LO_FLAG ) {   // cur is this pair's i
+                                        const ImpulseTerms F = impulse_terms( contact_geom( ga.x, ga.y, ga.z, gx.x, gx.y, gx.z, dt ), ga.w, gx.w,
+                                                                              uc.x, uc.y, ux.x, ux.y );
+                                        if ( F.impulse ) {
+                                            uc.x = __fadd_rn( uc.x, F.dvx_lo );
+                                            uc.y = __fadd_rn( uc.y, F.dvy_lo );
+                                            ux.x = __fsub_rn( ux.x, F.dvx_hi );
+                                            ux.y = __fsub_rn( ux.y, F.dvy_hi );
+                                        }
+                                    } else {   // cur is this pair's j
+                                        const ImpulseTerms F = impulse_terms( contact_geom( gx.x, gx.y, gx.z, ga.x, ga.y, ga.z, dt ), gx.w, ga.w,
+                                                                              ux.x, ux.y, uc.x, uc.y );
+                                        if ( F.impulse ) {
+                                            ux.x = __fadd_rn( ux.x, F.dvx_lo );
+                                            ux.y = __fadd_rn( ux.y, F.dvy_lo );
+                                            uc.x = __fsub_rn( uc.x, F.dvx_hi );
+                                            uc.y = __fsub_rn( uc.y, F.dvy_hi );
+                                        }
+                                    }
+                                    cpc++;
+                                    *vx              = ux;
+                                    R.wr[ x ].state = ( r << PC_BITS ) | ( pcx + 1 );
+                                    if ( pcx + 1 < X.deg )
+                                        buf[ atomicAdd( &buf_n, 1u ) ] = x;
+                                    else
+                                        *( reinterpret_cast<float2 *>( pv_out + x ) + 1 ) = ux;
+                                }
+                                *va              = uc;
+                                R.wr[ cur ].state = ( r << PC_BITS ) | cpc;
+                                if ( cpc < cdeg )
+                                    buf[ atomicAdd( &buf_n, 1u ) ] = cur;
+                                else
+                                    *( reinterpret_cast<float2 *>( pv_out + cur ) + 1 ) = uc;
                             }
                         }
                     }
                 }
             }
-            // stage the pushes in shared memory; flush with one global atomic when the buffer could overflow
-            if ( push0 != 0xffffffffu )
-                buf[ atomicAdd( &buf_n, 1u ) ] = push0;
-            if ( push1 != 0xffffffffu )
-                buf[ atomicAdd( &buf_n, 1u ) ] = push1;
+            // pushes were staged in shared memory; flush with one global atomic when the buffer could overflow
             __syncthreads();
             const uint32_t staged = buf_n;   // read between two barriers: the same value in every thread
             __syncthreads();
-            if ( staged > (uint32_t)( EV_BUF - 2 * EV_THREADS ) || ( it + 1 == iters && staged ) ) {
+            if ( staged > (uint32_t)( EV_BUF - ( EV_FOLLOW + 2 ) * EV_THREADS ) || ( it + 1 == iters && staged ) ) {
                 if ( threadIdx.x == 0 ) {
                     buf_base = atomicAdd( d_cnt, staged );
                     buf_n    = 0;

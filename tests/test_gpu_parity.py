@@ -347,6 +347,34 @@ def test_debug_scene_like_main_c(reference):
     p.Free()
 
 
+def test_zero_time_step_like_the_first_frame_of_main_c(oracle):
+    """src/main.c:63,87-90: the first frame's delta_time is 0.  With overlapping (here: coincident) particles the
+    Baumgarte term divides by it (src/particles_solver.c:121) and the reference's velocities become NaN.  The device does
+    the same operations, so it must produce NaN in exactly the same places and identical bits everywhere else; NaN
+    payload/sign bits are not compared (x86 and the GPU encode the default NaN differently)."""
+    s = State.empty(30)
+    for c in range(3):
+        s.px[c * 10:(c + 1) * 10] = 100.0 + 40.0 * c
+        s.py[c * 10:(c + 1) * 10] = 60.0
+        s.mass[c * 10:(c + 1) * 10] = 5 + c
+        s.radius[c * 10:(c + 1) * 10] = 3.0 + c
+    s.px[25:] += np.arange(5, dtype=np.float32) * 50.0   # five particles of the last cluster stand alone: they stay finite
+    ref = s.copy()
+    p = gpu_store(s)
+    for dt in (0.0, 1.0 / 144.0, 1.0 / 144.0):
+        oracle.substep(ref, 400, 200, dt, 0, False)
+        p.Update(dt)
+        p.CollisionsCheck_Grid(400, 200, dt)
+    got = gpu_state(p)
+    assert np.isnan(ref.vx).any() and np.isfinite(ref.vx).any()
+    for f in ("px", "py", "vx", "vy"):
+        a, b = getattr(got, f), getattr(ref, f)
+        assert np.array_equal(np.isnan(a), np.isnan(b)), f
+        ok = ~np.isnan(b)
+        assert_bits_equal(a[ok], b[ok], f"dt=0 {f}")
+    p.Free()
+
+
 # ---- sync policies and entry-point composition ---------------------------------------------------------------------
 def test_sync_policies_agree(oracle):
     sc = scenes.uniform_random(5000, 2.0, 0.6, seed=107, vmax=40.0)
