@@ -827,7 +827,10 @@ __device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
 #define PPC_EV_MINBLOCKS 6
 #endif
 constexpr int EV_THREADS = 256;
-constexpr int EV_FOLLOW  = 6;      // pairs one thread may fire in a row along a chain
+#ifndef PPC_EV_FOLLOW
+#define PPC_EV_FOLLOW 6
+#endif
+constexpr int EV_FOLLOW  = PPC_EV_FOLLOW;   // pairs one thread may fire in a row along a chain
 constexpr int EV_BUF     = ( EV_FOLLOW + 2 ) * EV_THREADS * 2;   // per-CTA staging of queue pushes: one global atomic per flush
 
 __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
