@@ -144,6 +144,44 @@ int                ppc_profile_read( struct Particles_t *p, int stage, double *t
 void               ppc_profile_reset( struct Particles_t *p );
 const char        *ppc_version( void );
 
+/* =====================================================================================================
+ * Part 3 -- multi-GPU slab decomposition (no reference counterpart).
+ *
+ * The field is cut into slabs of whole cell rows, one store (one process, one GPU) per slab.  A substep is
+ *     ppc_slab_begin   integrate + walls of the owned particles; how many records go to each neighbour
+ *     ppc_slab_pack    write those records (32 bytes each) into two device buffers of the caller
+ *     -- the caller moves the buffers to the neighbouring ranks (NCCL send/recv, or a device copy in one process) --
+ *     ppc_slab_finish  take the received records in, build the grid over owned + ghost rows, narrow phase, resolve
+ * With halo_rows >= (dependency rounds of the resolve) x (1 or 2, by engine) + 1 the owned particles' positions AND
+ * velocities are bit-identical to a single-GPU run of the whole field; ppc_slab_begin / ppc_slab_download return -2 when
+ * the substep just finished did not satisfy that bound.  All functions return -1 on misuse.
+ * ===================================================================================================== */
+#define PPC_SLAB_RECORD_BYTES 32
+
+/* grid of the whole field for a given maximum radius (src/particles_solver.c:231-249): rows are what gets partitioned */
+int ppc_grid_dims( uint16_t window_width, uint16_t window_height, float max_radius, ppc_grid_info *out );
+
+/* Turn the store into one slab.  The host arrays hold this rank's particles in [0, length), global_ids[k] their index
+ * in the whole field (it fixes the pair order on every rank alike); max_radius is the maximum over the WHOLE field. */
+int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids, uint16_t window_width, uint16_t window_height, float max_radius,
+                   int own_row_begin, int own_row_end, int halo_rows );
+int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] /* to lower / upper rows */ );
+int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device buffers of send_counts records */ );
+/* returns the number of owned particles after the substep */
+int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi );
+/* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index), ids alongside */
+int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids );
+
+typedef struct ppc_slab_info_t {
+    uint64_t n_owned, own_first, n_window; /* owned particles = sorted slots [own_first, own_first + n_owned) of n_window */
+    int      row_lo, row_hi;               /* window of the last grid build (owned + ghost rows) */
+    int      own_row_begin, own_row_end, halo_rows, cols, rows;
+    uint32_t rounds;                       /* dependency rounds of the last resolve */
+} ppc_slab_info_t;
+int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out );
+/* candidate pairs (i, j) whose i (lower global index) this rank owns; every pair of the field appears on exactly one rank */
+int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,12 @@ class GridInfo(C.Structure):
                 ("cells", C.c_uint64), ("n", C.c_uint64)]
 
 
+class SlabInfo(C.Structure):
+    _fields_ = [("n_owned", C.c_uint64), ("own_first", C.c_uint64), ("n_window", C.c_uint64), ("row_lo", C.c_int), ("row_hi", C.c_int),
+                ("own_row_begin", C.c_int), ("own_row_end", C.c_int), ("halo_rows", C.c_int), ("cols", C.c_int), ("rows", C.c_int),
+                ("rounds", C.c_uint32)]
+
+
 # every symbol include/ppc_b200.h declares (tests check the library exports all of them)
 REFERENCE_SYMBOLS = ["particlesCreate", "particlesFree", "particlesAddParticle", "particlesRemoveParticle", "particlesUpdate",
                      "particlesCollisionsCheck_Grid"]
@@ -56,6 +62,8 @@ EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_
                      "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
+SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_info",
+                "ppc_slab_debug_pairs"]
 
 _lib = None
 
@@ -104,6 +112,16 @@ def load_library() -> C.CDLL:
     L.ppc_profile_read.argtypes, L.ppc_profile_read.restype = [PP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)], C.c_int
     L.ppc_profile_reset.argtypes, L.ppc_profile_reset.restype = [PP], None
     L.ppc_version.argtypes, L.ppc_version.restype = [], C.c_char_p
+    L.ppc_grid_dims.argtypes, L.ppc_grid_dims.restype = [C.c_uint16, C.c_uint16, C.c_float, C.POINTER(GridInfo)], C.c_int
+    L.ppc_slab_init.argtypes = [PP, u32p, C.c_uint16, C.c_uint16, C.c_float, C.c_int, C.c_int, C.c_int]
+    L.ppc_slab_init.restype = C.c_int
+    L.ppc_slab_begin.argtypes, L.ppc_slab_begin.restype = [PP, C.c_float, C.c_int, C.POINTER(C.c_uint64)], C.c_int
+    L.ppc_slab_pack.argtypes, L.ppc_slab_pack.restype = [PP, C.c_void_p, C.c_void_p], C.c_int
+    L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.ppc_slab_finish.restype = C.c_int64
+    L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p], C.c_int
+    L.ppc_slab_info.argtypes, L.ppc_slab_info.restype = [PP, C.POINTER(SlabInfo)], C.c_int
+    L.ppc_slab_debug_pairs.argtypes, L.ppc_slab_debug_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     _lib = L
     return L
 

@@ -18,6 +18,7 @@
 #include "ppc_grid.cuh"
 #include "ppc_radix.cuh"
 #include "ppc_scan.cuh"
+#include "ppc_slab.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -26,9 +27,9 @@
 namespace ppc {
 unsigned long long g_launches = 0;
 
-enum Stage { ST_INTEGRATE = 0, ST_SCAN, ST_SORT, ST_GATHER, ST_COLLIDE, ST_WAVEFRONT, ST_UPLOAD, ST_DOWNLOAD, ST_MISC, ST_COUNT };
+enum Stage { ST_INTEGRATE = 0, ST_SCAN, ST_SORT, ST_GATHER, ST_COLLIDE, ST_WAVEFRONT, ST_UPLOAD, ST_DOWNLOAD, ST_MISC, ST_SLAB, ST_COUNT };
 static const char *k_stage_names[ ST_COUNT ] = { "integrate_walls_keys", "cell_scan", "cell_sort", "canonical_gather",
-                                                 "collide",              "resolve_wavefront", "upload", "download", "misc" };
+                                                 "collide",              "resolve_wavefront", "upload", "download", "misc", "slab_exchange_prep" };
 
 struct Store {
     // identity / host side
@@ -70,6 +71,16 @@ struct Store {
     uint32_t    *wave_n_items = nullptr;
     size_t       wave_items_stride = 0;
     uint32_t    *h_active = nullptr;   // pinned [2]: particles with contacts, densest tile (per 1024 cells), as of a recent substep
+    // slab mode (multi-GPU decomposition): this store holds the particles of one slab of cell rows
+    bool      slab = false;
+    SlabRows  slab_rows = {};
+    GridDims  slab_world = {};               // the whole field's grid
+    float     slab_wall_w = 0, slab_wall_h = 0;
+    size_t    own_first = 0, n_own = 0;      // owned particles = slots [own_first, own_first + n_own) of the current set
+    int       row_lo = 0, row_hi = 0;        // window of the last grid build
+    uint32_t *slab_counts = nullptr;         // device [8]: send counts lo/hi, lost, -, pack cursors lo/hi
+    uint32_t *h_slab = nullptr;              // pinned [8]
+    int       wave_hops = 1;                 // contacts an error can travel per wavefront round of the engine last used (0: unbounded)
     // last grid
     bool     grid_valid = false, pre_valid = false;
     GridDims grid = {};
@@ -348,6 +359,10 @@ static void refresh_max_radius( Store *st ) {
 
 // Bring the device mirror in line with what the caller did to the host struct since the last call.
 static void absorb_host_changes( Store *st, struct Particles_t *p ) {
+    if ( st->slab ) {
+        fprintf( stderr, "particlephysicsc_b200: this store is one slab of a multi-GPU field; drive it with ppc_slab_begin / _pack / _finish\n" );
+        abort();
+    }
     if ( p->size != st->cap ) {   // arrays were re-sized behind our back (adopted arrays only)
         PPC_CK( cudaStreamSynchronize( st->stream ) );
         resize_particle_arrays( st, p->size, 0 );
@@ -383,7 +398,7 @@ static void absorb_host_changes( Store *st, struct Particles_t *p ) {
 // ---- the substep ----------------------------------------------------------------------------------------------
 static void launch_integrate( Store *st, const StepParams &P ) {
     StageTimer T( st, ST_INTEGRATE );
-    if ( P.do_walls_keys )
+    if ( P.do_walls_keys && P.do_histogram )
         PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( (size_t)P.grid.cells + 1 ) * sizeof( uint32_t ), st->stream ) );
     PPC_LAUNCH( k_integrate_walls_keys, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->cell_count,
                 st->n, P );
@@ -412,43 +427,18 @@ static int bits_for( uint32_t cells ) {
     return b > 0 ? b : 1;
 }
 
-// One collisions check (reference src/particles_solver.c:197-393), with the pending particlesUpdate fused in.
-static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
-    const size_t n = st->n;
-    if ( n < 2 ) {   // reference :204-205: not even the wall pass runs
-        flush_pending_update( st );
-        return;
-    }
-    refresh_max_radius( st );
-    GridDims G;
-    G.cell_size = 2.0f * st->max_radius;                                // :244
-    G.cols      = (int)ceilf( (float)W / G.cell_size );                 // :247
-    G.rows      = (int)ceilf( (float)H / G.cell_size );                 // :248
-    if ( G.cols < 1 || G.rows < 1 ) {
-        fprintf( stderr, "particlephysicsc_b200: window %ux%u gives an empty grid\n", (unsigned)W, (unsigned)H );
-        abort();
-    }
-    G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
-    ensure_cells( st, G.cells );
-    ensure_scratch( st, radix_scratch_words( n ) + scan_scratch_words( (size_t)G.cells + 1 ) + scan_scratch_words( n + 1 ) + 64 );
+// Cell-start table, counting / radix sort and canonical gather over the first n storage slots of the current set, whose
+// keys lie in [0, bins) and whose histogram is in cell_count (K4-K6).  The sorted copy becomes the current set.
+static ParticleSet offset_view( const ParticleSet &S, const size_t first ) {
+    return ParticleSet{ S.pv + first, S.rm + first, S.gid + first, S.key + first, S.col + first };
+}
 
-    StepParams P    = {};
-    P.do_integrate  = st->pending ? 1 : 0;
-    P.dt_update     = st->pending_dt;
-    P.do_colour     = ( st->pending && st->pending_colour ) ? 1 : 0;
-    P.do_walls_keys = 1;
-    P.wall_w        = (float)(int)W;
-    P.wall_h        = (float)(int)H;
-    P.grid          = G;
-    if ( st->pending )
-        st->col_valid = st->pending_colour;
-    st->pending     = false;
-
-    ParticleSet &A = st->set[ st->cur ], &B = st->set[ st->cur ^ 1 ];
-    launch_integrate( st, P );                                                         // K1 (+K3 histogram)
+static void grid_stage( Store *st, const size_t n, const size_t bins, const size_t first = 0 ) {
+    const ParticleSet  A = offset_view( st->set[ st->cur ], first );   // input: n slots starting at `first`
+    const ParticleSet &B = st->set[ st->cur ^ 1 ];
     {
         StageTimer T( st, ST_SCAN );                                                   // K4 cell-start table
-        exclusive_scan( st->cell_count, st->cell_start, (size_t)G.cells + 1, st->scratch, st->stream );
+        exclusive_scan( st->cell_count, st->cell_start, bins + 1, st->scratch, st->stream );
     }
     const uint32_t *slot_of = st->slot_of;
     {
@@ -456,10 +446,10 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         if ( st->opt_sort == 1 ) {
             PPC_CK( cudaMemcpyAsync( st->sort_keys_a, A.key, n * sizeof( uint32_t ), cudaMemcpyDeviceToDevice, st->stream ) );
             const int where = radix_sort_pairs( st->sort_keys_a, st->slot_of, st->sort_keys_b, st->sort_vals_b, true, n,
-                                                bits_for( G.cells ), st->scratch, st->stream );
+                                                bits_for( (uint32_t)bins ), st->scratch, st->stream );
             slot_of         = where ? st->sort_vals_b : st->slot_of;
         } else {
-            PPC_CK( cudaMemsetAsync( st->cell_count, 0, (size_t)G.cells * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->cell_count, 0, bins * sizeof( uint32_t ), st->stream ) );
             PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, st->cell_count, st->cell_start,
                         st->slot_of, n );
         }
@@ -470,9 +460,11 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
                     st->col_valid ? 1 : 0 );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
+}
+
+// Narrow phase + contact resolution over the first n slots of the (sorted) current set on grid G (K7, K7b).
+static void resolve_stage( Store *st, const size_t n, const GridDims &G, const float dt ) {
     ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
-    st->grid       = G;
-    st->grid_valid = true;
     if ( st->opt_resolve ) {
         const bool jacobi = st->opt_resolve == 2;
         if ( !jacobi ) {
@@ -514,6 +506,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
             const bool      dense  = *st->h_active == 0xffffffffu || (double)*st->h_active > 0.25 * (double)n;
             const int       passes = ( st->opt_wave_passes < 0 ) ? -st->opt_wave_passes : ( dense ? st->opt_wave_passes : 0 );
             PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 2 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            st->wave_hops = passes > 0 ? 0 : 1;
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
                 static bool configured = false;
                 if ( !configured ) {
@@ -549,6 +542,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
             // kernel's compact per-CTA queues (no pack pass).  "wave_mode": 1 = choose by density (default), 2 = always events.
             if ( ( st->opt_wave_mode == 2 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
                 const WaveRecs R = st->recs;
+                st->wave_hops    = 2;   // a thread fires a star of pairs around one particle per round (chain following)
                 PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
                 int       grid = st->events_grid;
                 const int want = (int)div_up( n, EV_THREADS );
@@ -572,6 +566,46 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         S.pv      = O.pv;   // set until the next substep (ppc_debug_pairs uses it)
         O.pv      = t;
     }
+}
+
+// One collisions check (reference src/particles_solver.c:197-393), with the pending particlesUpdate fused in.
+static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
+    const size_t n = st->n;
+    if ( n < 2 ) {   // reference :204-205: not even the wall pass runs
+        flush_pending_update( st );
+        return;
+    }
+    refresh_max_radius( st );
+    GridDims G;
+    G.cell_size = 2.0f * st->max_radius;                                // :244
+    G.cols      = (int)ceilf( (float)W / G.cell_size );                 // :247
+    G.rows      = (int)ceilf( (float)H / G.cell_size );                 // :248
+    if ( G.cols < 1 || G.rows < 1 ) {
+        fprintf( stderr, "particlephysicsc_b200: window %ux%u gives an empty grid\n", (unsigned)W, (unsigned)H );
+        abort();
+    }
+    G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
+    ensure_cells( st, G.cells );
+    ensure_scratch( st, radix_scratch_words( n ) + scan_scratch_words( (size_t)G.cells + 1 ) + scan_scratch_words( n + 1 ) + 64 );
+
+    StepParams P    = {};
+    P.do_integrate  = st->pending ? 1 : 0;
+    P.dt_update     = st->pending_dt;
+    P.do_colour     = ( st->pending && st->pending_colour ) ? 1 : 0;
+    P.do_walls_keys = 1;
+    P.do_histogram  = 1;
+    P.wall_w        = (float)(int)W;
+    P.wall_h        = (float)(int)H;
+    P.grid          = G;
+    if ( st->pending )
+        st->col_valid = st->pending_colour;
+    st->pending     = false;
+
+    launch_integrate( st, P );                                                         // K1 (+K3 histogram)
+    grid_stage( st, n, G.cells );
+    st->grid       = G;
+    st->grid_valid = true;
+    resolve_stage( st, n, G, dt );
     st->pre_valid = true;
 }
 
@@ -641,6 +675,9 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFree( st->cell_count );
         cudaFree( st->cell_start );
         cudaFree( st->d_word );
+        cudaFree( st->slab_counts );
+        if ( st->h_slab )
+            cudaFreeHost( st->h_slab );
         cudaFreeHost( st->h_active );
         cudaFree( st->wave_items );
         cudaFree( st->wave_n_items );
@@ -897,6 +934,269 @@ extern "C" int ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *
     *rounds = w[ 4 ];
     *visits = ( (unsigned long long)w[ 7 ] << 32 ) | w[ 6 ];
     return 0;
+}
+
+// =================================================================================================================
+// Part 3: multi-GPU slab decomposition (one store per rank; the caller moves the exchange buffers, e.g. with
+// torch.distributed / NCCL send-recv between neighbouring ranks)
+// =================================================================================================================
+static GridDims world_grid( uint16_t W, uint16_t H, float max_radius ) {
+    GridDims G;
+    const float m = max_radius > 6.0f ? max_radius : 6.0f;            // reference src/particles_solver.c:231-236
+    G.cell_size   = 2.0f * m;                                           // :244
+    G.cols        = (int)ceilf( (float)W / G.cell_size );               // :247
+    G.rows        = (int)ceilf( (float)H / G.cell_size );               // :248
+    G.cells       = (uint32_t)G.cols * (uint32_t)G.rows;
+    return G;
+}
+
+extern "C" int ppc_grid_dims( uint16_t window_width, uint16_t window_height, float max_radius, ppc_grid_info *out ) {
+    const GridDims G = world_grid( window_width, window_height, max_radius );
+    if ( G.cols < 1 || G.rows < 1 )
+        return -1;
+    out->max_radius = max_radius > 6.0f ? max_radius : 6.0f;
+    out->cell_size  = G.cell_size;
+    out->cols       = G.cols;
+    out->rows       = G.rows;
+    out->cells      = G.cells;
+    out->n          = 0;
+    return 0;
+}
+
+extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids, uint16_t window_width, uint16_t window_height,
+                              float max_radius, int own_row_begin, int own_row_end, int halo_rows ) {
+    Store         *st = store_of( p );
+    const GridDims G  = world_grid( window_width, window_height, max_radius );
+    if ( G.cols < 1 || G.rows < 1 || own_row_begin < 0 || own_row_end > G.rows || own_row_begin >= own_row_end || halo_rows < 1 || p->length > p->size )
+        return -1;
+    if ( p->size != st->cap ) {
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        resize_particle_arrays( st, p->size, 0 );
+    }
+    st->slab        = true;
+    st->slab_world  = G;
+    st->slab_wall_w = (float)(int)window_width;
+    st->slab_wall_h = (float)(int)window_height;
+    st->max_radius  = max_radius > 6.0f ? max_radius : 6.0f;
+    st->max_radius_dirty = false;
+    st->slab_rows   = SlabRows{ own_row_begin, own_row_end, halo_rows, own_row_begin > 0 ? 1 : 0, own_row_end < G.rows ? 1 : 0, G.cols };
+    if ( !st->slab_counts )
+        st->slab_counts = dev_alloc<uint32_t>( 8 );
+    if ( !st->h_slab )
+        PPC_CK( cudaHostAlloc( (void **)&st->h_slab, 8 * sizeof( uint32_t ), cudaHostAllocDefault ) );
+    const size_t n = p->length;
+    if ( n ) {
+        StageTimer T( st, ST_UPLOAD );
+        float     *h[ 6 ];
+        host_float_arrays( p, h );
+        for ( int a = 0; a < 6; a++ )
+            PPC_CK( cudaMemcpyAsync( st->api_f[ a ], h[ a ], n * sizeof( float ), cudaMemcpyHostToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( st->api_col, p->colors, n * sizeof( uchar4 ), cudaMemcpyHostToDevice, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( st->slot_of, global_ids, n * sizeof( uint32_t ), cudaMemcpyHostToDevice, st->stream ) );
+        PPC_LAUNCH( k_slab_upload, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->api_f[ 0 ], st->api_f[ 1 ],
+                    st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, st->slot_of, n );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+    }
+    st->own_first  = 0;
+    st->n_own      = n;
+    st->n          = n;
+    st->dirty_all  = false;
+    st->pending    = false;
+    st->col_valid  = true;
+    st->grid_valid = st->pre_valid = false;
+    return 0;
+}
+
+// Depth of the last resolve's pair dependency graph against the halo (see ppc_slab.cuh): stream must be idle.
+static int slab_halo_ok( Store *st ) {
+    if ( st->opt_resolve != 1 || !st->wave.counters || !( st->slab_rows.has_lo || st->slab_rows.has_hi ) )
+        return 1;
+    uint32_t rounds = 0;
+    PPC_CK( cudaMemcpy( &rounds, st->wave.counters + 4, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
+    if ( rounds == 0 )
+        return 1;
+    // the outermost halo row starts out wrong; the error moves at most wave_hops rows per round; owned rows start `halo` rows in
+    return st->wave_hops > 0 && (long long)rounds * st->wave_hops + 1 <= (long long)st->slab_rows.halo ? 1 : 0;
+}
+
+extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    check_device_flags( st );
+    if ( st->grid_valid && !slab_halo_ok( st ) )
+        return -2;   // the previous substep's dependency depth exceeded what the halo guarantees: results may be inexact
+    const size_t n = st->n_own;
+    const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
+    StepParams   P = {};
+    P.do_integrate = 1, P.dt_update = time_step, P.do_colour = colour ? 1 : 0, P.do_walls_keys = 1, P.do_histogram = 0;
+    P.wall_w = st->slab_wall_w, P.wall_h = st->slab_wall_h, P.grid = st->slab_world;
+    if ( n ) {
+        StageTimer T( st, ST_INTEGRATE );
+        PPC_LAUNCH( k_integrate_walls_keys, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->cell_count, n, P );
+    }
+    st->col_valid = colour != 0;
+    {
+        StageTimer T( st, ST_SLAB );
+        PPC_CK( cudaMemsetAsync( st->slab_counts, 0, 8 * sizeof( uint32_t ), st->stream ) );
+        if ( n )
+            PPC_LAUNCH( k_slab_count, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key, n, st->slab_rows, st->slab_counts );
+        PPC_CK( cudaMemcpyAsync( st->h_slab, st->slab_counts, 4 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+    }
+    if ( st->h_slab[ 2 ] ) {
+        fprintf( stderr, "particlephysicsc_b200: %u particles moved more than the %d halo rows in one substep\n", st->h_slab[ 2 ], st->slab_rows.halo );
+        abort();
+    }
+    send_counts[ 0 ] = st->h_slab[ 0 ];
+    send_counts[ 1 ] = st->h_slab[ 1 ];
+    st->pre_valid    = false;
+    return 0;
+}
+
+extern "C" int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    const size_t n = st->n_own;
+    if ( n && ( st->h_slab[ 0 ] || st->h_slab[ 1 ] ) ) {
+        StageTimer T( st, ST_SLAB );
+        PPC_LAUNCH( k_slab_pack, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, offset_view( st->set[ st->cur ], st->own_first ), n,
+                    st->slab_rows, (SlabRec *)send_lo, (SlabRec *)send_hi, st->slab_counts + 4 );
+    }
+    return 0;
+}
+
+extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    const SlabRows &R     = st->slab_rows;
+    const GridDims &GW    = st->slab_world;
+    const size_t    n_loc = st->n_own + n_lo + n_hi;
+    if ( st->own_first + n_loc > st->cap ) {
+        fprintf( stderr, "particlephysicsc_b200: slab store too small: %zu owned + %llu received particles at offset %zu, capacity %zu\n", st->n_own,
+                 (unsigned long long)( n_lo + n_hi ), st->own_first, st->cap );
+        abort();
+    }
+    const int row_lo = R.own_begin - R.halo > 0 ? R.own_begin - R.halo : 0;
+    const int row_hi = R.own_end + R.halo < GW.rows ? R.own_end + R.halo : GW.rows;
+    GridDims  G;
+    G.cell_size = GW.cell_size, G.cols = GW.cols, G.rows = row_hi - row_lo, G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
+    const size_t bins = (size_t)G.cells + 1;   // + the drop bin
+    ensure_cells( st, bins );
+    ensure_scratch( st, radix_scratch_words( n_loc ) + scan_scratch_words( bins + 1 ) + scan_scratch_words( n_loc + 1 ) + 64 );
+    const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
+    {
+        StageTimer T( st, ST_SLAB );
+        if ( n_lo )
+            PPC_LAUNCH( k_slab_append, div_up( n_lo, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own, (const SlabRec *)recv_lo, (size_t)n_lo, GW );
+        if ( n_hi )
+            PPC_LAUNCH( k_slab_append, div_up( n_hi, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own + n_lo, (const SlabRec *)recv_hi, (size_t)n_hi, GW );
+        PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
+        if ( n_loc )
+            PPC_LAUNCH( k_slab_localize, div_up( n_loc, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key, n_loc, G.cols, row_lo, row_hi, G.cells,
+                        st->cell_count );
+    }
+    if ( n_loc )
+        grid_stage( st, n_loc, bins, st->own_first );
+    else {
+        PPC_CK( cudaMemsetAsync( st->cell_start, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
+        st->cur ^= 1;
+    }
+    // owned rows and the window end, as slot numbers of the sorted storage
+    const size_t c_own0 = (size_t)( R.own_begin - row_lo ) * G.cols, c_own1 = (size_t)( R.own_end - row_lo ) * G.cols;
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 4, st->cell_start + c_own0, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 5, st->cell_start + c_own1, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 6, st->cell_start + G.cells, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    const size_t n_work = st->h_slab[ 6 ];
+    st->own_first  = st->h_slab[ 4 ];
+    st->n_own      = st->h_slab[ 5 ] - st->h_slab[ 4 ];
+    st->n          = n_work;
+    st->grid       = G;
+    st->grid_valid = true;
+    st->row_lo = row_lo, st->row_hi = row_hi;
+    if ( n_work >= 1 )
+        resolve_stage( st, n_work, G, time_step );
+    st->pre_valid = true;
+    p->length     = st->n_own <= p->size ? st->n_own : p->size;
+    return (int64_t)st->n_own;
+}
+
+extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    const size_t n = st->n_own;
+    if ( n > p->size )
+        return -3;
+    if ( n ) {
+        StageTimer T( st, ST_DOWNLOAD );
+        PPC_LAUNCH( k_slab_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->own_first, n, st->api_f[ 0 ],
+                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_col, st->sort_keys_a );
+        PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
+        if ( global_ids )
+            PPC_CK( cudaMemcpyAsync( global_ids, st->sort_keys_a, n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    }
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    check_device_flags( st );
+    p->length = n;
+    return slab_halo_ok( st ) ? 0 : -2;
+}
+
+extern "C" int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    out->n_owned = st->n_own, out->own_first = st->own_first, out->n_window = st->n;
+    out->row_lo = st->row_lo, out->row_hi = st->row_hi, out->own_row_begin = st->slab_rows.own_begin, out->own_row_end = st->slab_rows.own_end;
+    out->halo_rows = st->slab_rows.halo, out->cols = st->slab_world.cols, out->rows = st->slab_world.rows;
+    uint32_t rounds = 0;
+    if ( st->wave.counters && st->opt_resolve == 1 )
+        PPC_CK( cudaMemcpy( &rounds, st->wave.counters + 4, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
+    out->rounds = rounds;
+    return 0;
+}
+
+extern "C" int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs ) {
+    Store *st = store_of( p );
+    if ( !st->slab || !st->grid_valid || !st->pre_valid )
+        return -1;
+    const size_t n = st->n_own;
+    if ( n == 0 )
+        return 0;
+    ParticleSet pre = st->set[ st->cur ];
+    if ( st->opt_resolve )
+        pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw
+    const size_t padded = ( n + 1 + 63 ) & ~(size_t)63;
+    uint32_t    *tmp    = dev_alloc<uint32_t>( 2 * padded );
+    uint32_t    *count = tmp, *offset = tmp + padded;
+    PPC_CK( cudaMemsetAsync( count, 0, ( n + 1 ) * sizeof( uint32_t ), st->stream ) );
+    ensure_scratch( st, scan_scratch_words( n + 1 ) + 64 );
+    PPC_LAUNCH( ( k_slab_pairs<false> ), div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, pre, st->cell_start, st->own_first, n, st->grid,
+                count, (int32_t *)nullptr, (size_t)0 );
+    exclusive_scan( count, offset, n + 1, st->scratch, st->stream );
+    uint32_t total = 0;
+    PPC_CK( cudaMemcpyAsync( &total, offset + n, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    if ( pairs && max_pairs && total ) {
+        const size_t keep  = total < max_pairs ? total : max_pairs;
+        int32_t     *d_out = dev_alloc<int32_t>( 2 * keep );
+        PPC_LAUNCH( ( k_slab_pairs<true> ), div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, pre, st->cell_start, st->own_first, n,
+                    st->grid, offset, d_out, keep );
+        PPC_CK( cudaMemcpyAsync( pairs, d_out, 2 * keep * sizeof( int32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        cudaFree( d_out );
+    }
+    cudaFree( tmp );
+    return (int64_t)total;
 }
 
 extern "C" void              *ppc_stream( struct Particles_t *p ) { return (void *)store_of( p )->stream; }

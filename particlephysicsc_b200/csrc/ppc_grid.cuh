@@ -19,6 +19,7 @@ struct StepParams {
     int   do_integrate;   // reference src/particles_solver.c:18-28
     int   do_colour;      // reference src/particles_solver.c:31-39 (only on substeps whose result is drawn)
     int   do_walls_keys;  // reference src/particles_solver.c:207-228 and :280-291
+    int   do_histogram;   // count particles per cell key (off in slab mode: the window's histogram is built after the exchange)
     float wall_w, wall_h; // (float)(int)window_width / height
     GridDims grid;
 };
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_integrate_walls_keys( Part
         }
         S.pv[ k ] = s;
     }
-    if ( P.do_walls_keys ) {   // whole warp arrives here: lanes of one cell elect a leader that adds their count
+    if ( P.do_walls_keys && P.do_histogram ) {   // whole warp arrives here: lanes of one cell elect a leader that adds their count
         const unsigned peers = __match_any_sync( 0xffffffffu, key );
         if ( valid && lane == (unsigned)( __ffs( peers ) - 1 ) )
             atomicAdd( &cell_count[ key ], (uint32_t)__popc( peers ) );
