@@ -39,11 +39,19 @@ WORKLOADS = {
     "uniform16m": (1 << 24, "16M equal-radius particles (r=2), uniform random, area fraction 0.30 (BASELINE configs[4] sweep point)"),
     "uniform1m": (1 << 20, "1M equal-radius particles (r=2), uniform random, area fraction 0.30, 8 substeps/frame (BASELINE configs[1])"),
 }
+# Multi-GPU (BASELINE configs[3]): 256M particles (r = 1, area fraction 0.40) over 8 slabs of cell rows = 2**25 per GPU; the box is
+# 45,916 wide (3,827 cell columns) and 478 cell rows (5,736 px) tall PER GPU, so per-GPU work is fixed as N grows (weak scaling).
+WORKLOADS["slab32m"] = (1 << 25, "256M equal-radius particles (r=1, area fraction 0.40) over 8 GPUs = 32M per GPU, slabs of 478 cell rows "
+                                 "with halo exchange and migration over NCCL send/recv (BASELINE configs[3])")
+SLAB_W, SLAB_ROWS_PER_GPU, SLAB_CELL, SLAB_RADIUS = 45916, 478, 12, 1.0
 CPU_SAMPLE_PARTICLES = 1 << 20
 
 
 def make_scene(workload: str, n: int, seed_offset: int = 0):
     from particlephysicsc_b200 import scenes
+    if workload.startswith("slab"):   # one slab's worth of the config-4 field (also the CPU sample)
+        rows = max(8, int(round(SLAB_ROWS_PER_GPU * n / float(1 << 25))))
+        return scenes.uniform_slab(n, SLAB_RADIUS, SLAB_W, rows * SLAB_CELL, 0, rows * SLAB_CELL, seed=0x5EED0004 + seed_offset)
     if workload.startswith("pile"):
         return scenes.polydisperse_pile(n, seed=0x5EED0003 + seed_offset)
     return scenes.uniform_random(n, 2.0, 0.30, seed=0x5EED0002 + seed_offset, vmax=0.0)
@@ -299,13 +307,191 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def run_slab(args, rank: int, world: int, local_rank: int):
+    """Slab decomposition: one slab of cell rows per rank, neighbour exchange of migrants + ghost rows every substep."""
+    import torch
+    from particlephysicsc_b200 import api, scenes, slab
+
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    n_per, descr = WORKLOADS["slab32m"]
+    n_per = args.particles_per_gpu or n_per
+    rows_per = max(8, int(round(SLAB_ROWS_PER_GPU * n_per / float(1 << 25))))
+
+    def make_rank(k: int, nranks: int, halo: int):
+        H = rows_per * SLAB_CELL * nranks
+        sc = scenes.uniform_slab(n_per, SLAB_RADIUS, SLAB_W, H, k * rows_per * SLAB_CELL, (k + 1) * rows_per * SLAB_CELL,
+                                 seed=0x5EED0004 + 0x100 * k)
+        ids = (np.arange(n_per, dtype=np.int64) + k * n_per).astype(np.uint32)
+        ghosts = int(2.2 * halo * n_per / rows_per)
+        cap = int(1.15 * (n_per + 3 * ghosts)) + 65536
+        r = slab.DeviceSlab(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba, ids, SLAB_W, H, 6.0, (k * rows_per, (k + 1) * rows_per), halo,
+                            capacity=cap, device=local_rank)
+        return r, H
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(me, tr, steps, colour_every=0):
+        for s in range(steps):
+            colour = bool(colour_every) and (s % colour_every == colour_every - 1)
+            if tr is None:
+                slab.local_step([me], DT, colour)
+            else:
+                slab.slab_step(me, tr, DT, colour)
+
+    def settle_and_choose_halo(me, tr, group_max):
+        """Relax the random field with a generous halo, then restart from the relaxed state with the halo this field needs:
+        (dependency rounds of the resolve) x 2 + 1 rows (csrc/ppc_slab.cuh), a few rows of margin on top."""
+        run(me, tr, args.settle)
+        rounds = 0
+        for _ in range(4):
+            run(me, tr, 1)
+            rounds = max(rounds, int(me.info().rounds))
+        rounds = group_max(rounds)
+        halo = slab.required_halo(rounds, 2) + args.halo_margin
+        me.reinit(halo)
+        return halo, rounds
+
+    def timed(me, tr, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(me.stream)
+        run(me, tr, steps)
+        e1.record(me.stream)
+        e1.synchronize()
+        barrier()
+        return e0.elapsed_time(e1)
+
+    def group_max(v: int) -> int:
+        if dist is None:
+            return v
+        t = torch.tensor([v], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # set-up only; nothing on the data path is a collective
+        return int(t.item())
+
+    me, H = make_rank(rank, world, args.settle_halo)
+    tr = slab.DistTransport(dist, dev) if dist is not None else None
+    halo, rounds = settle_and_choose_halo(me, tr, group_max)
+    run(me, tr, args.warmup)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = api.kernel_launches()
+    ms_total = max_over_ranks(timed(me, tr, args.steps), dist, "cuda")
+    launches = api.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = whole_job_value(n_per, world, args.steps, ms_total)
+
+    # e2e: owned particles copied back to the host arrays every 8th substep (colours computed on that substep)
+    frames = max(1, args.steps // SUBSTEPS_PER_FRAME)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(me.stream)
+    n_down = 0
+    for _ in range(frames):
+        run(me, tr, SUBSTEPS_PER_FRAME, colour_every=SUBSTEPS_PER_FRAME)
+        n_down = me.sync_host()
+    e1.record(me.stream)
+    e1.synchronize()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1), dist, "cuda")
+    e2e_value = n_per * world * frames * SUBSTEPS_PER_FRAME / (e2e_ms * 1e-3)
+
+    # per-stage times of this rank (serialised) and exchange volume
+    prof_steps = min(args.steps, 8)
+    me.p.profile_reset()
+    me.p.profile(True)
+    run(me, tr, prof_steps)
+    me.synchronize()
+    me.p.profile(False)
+    stages = {k: (ms / prof_steps, cnt // prof_steps) for k, (ms, cnt) in me.p.profile_read().items() if cnt}
+    info = me.info()
+    sent = me.counts
+    peak, peak_src = measured_peak_gbs()
+
+    # the same per-GPU workload on ONE GPU (a single slab, no neighbours), measured by rank 0 in this same job: the
+    # denominator of the parallel efficiency
+    ref_value = None
+    barrier()
+    if rank == 0 and world > 1 and not args.no_scaling_reference:
+        me.free()
+        solo, _ = make_rank(0, 1, 4)
+        run(solo, None, args.settle + args.warmup)
+        e0.record(solo.stream)
+        run(solo, None, args.steps)
+        e1.record(solo.stream)
+        e1.synchronize()
+        ref_value = n_per * args.steps / (e0.elapsed_time(e1) * 1e-3)
+        solo.free()
+    if dist is not None:
+        dist.barrier()
+
+    if rank == 0:
+        dom = max(stages, key=lambda k: stages[k][0]) if stages else None
+        roofline = None
+        if dom:
+            algo = {"integrate_walls_keys": 36.0, "collide": 40.0}.get(dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
+            ach = algo * info.n_window / (stages[dom][0] * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": peak_src, "algorithmic_bytes_per_particle": algo,
+                        "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
+        substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * n_per * args.steps / (ms_total * 1e-3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": descr, "particles_per_gpu": n_per, "particles": n_per * world, "box": [SLAB_W, H],
+                           "grid": [info.cols, info.rows], "rows_per_gpu": rows_per, "halo_rows": halo, "dependency_rounds": rounds, "dt": DT,
+                           "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
+                           "resolve": "sequential-equivalent wavefront (bit-exact)",
+                           "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n_per / 1e6),
+                           "parallelism": f"{world} slabs of cell rows, neighbour send/recv (NCCL) of migrants + {halo} ghost rows per substep"
+                                          if world > 1 else "one slab (no neighbours)",
+                           "records_sent_per_substep_rank0": list(sent), "bytes_sent_per_substep_rank0": 32 * sum(sent),
+                           "window_particles_rank0": int(info.n_window)},
+                "roofline": roofline,
+                "roofline_substep": {"bound": "hbm", "achieved": substep_gbs, "peak": peak, "unit": "GB/s", "frac": substep_gbs / peak,
+                                     "note": "40 B x owned particles x substeps / time, whole substep, per GPU"},
+                "scaling_reference": None if ref_value is None else {
+                    "n_gpus": 1, "value": ref_value, "unit": UNIT, "note": "the same per-GPU workload as one slab on one GPU, measured by "
+                    "rank 0 in this job; parallel efficiency = value / (n_gpus x this)", "parallel_efficiency": value / (world * ref_value)},
+                "cpu_baseline": None,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24.0 * n_down / SUBSTEPS_PER_FRAME,
+                        "note": "8 slab substeps, then the owned particles' p, v, colours and indices copied to the host arrays"},
+                "gpu_launches": int(launches), "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            _, _, line["cpu_baseline"] = time_reference_cpu("slab32m", 2, 1)
+        print(json.dumps(line), flush=True)
+    if ref_value is None or rank != 0:
+        try:
+            me.free()
+        except Exception:
+            pass
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--settle", type=int, default=64, help="untimed substeps that relax the synthetic field first")
-    ap.add_argument("--workload", default="pile16m", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="default: pile16m on one GPU (the configuration the roofline target is stated on), slab32m on several")
+    ap.add_argument("--particles-per-gpu", type=int, default=0, help="slab32m only: override 2**25")
+    ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
+    ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured dependency depth requires")
+    ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")
@@ -313,6 +499,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload is None:
+        args.workload = "pile16m" if args.gpus == 1 else "slab32m"
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -321,7 +509,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    run_b200(args, rank, world, local_rank)
+    if args.workload == "slab32m":
+        run_slab(args, rank, world, local_rank)
+    else:
+        run_b200(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

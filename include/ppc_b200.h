@@ -169,8 +169,9 @@ int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t
 int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device buffers of send_counts records */ );
 /* returns the number of owned particles after the substep */
 int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi );
-/* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index), ids alongside */
-int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids );
+/* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index), ids alongside;
+ * p_x, p_y, v_x, v_y, colors always, mass and radius too when with_mass_radius (they only change owner, never value) */
+int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, int with_mass_radius );
 
 typedef struct ppc_slab_info_t {
     uint64_t n_owned, own_first, n_window; /* owned particles = sorted slots [own_first, own_first + n_owned) of n_window */

@@ -1125,7 +1125,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     return (int64_t)st->n_own;
 }
 
-extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids ) {
+extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, int with_mass_radius ) {
     Store *st = store_of( p );
     if ( !st->slab )
         return -1;
@@ -1135,7 +1135,11 @@ extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids ) 
     if ( n ) {
         StageTimer T( st, ST_DOWNLOAD );
         PPC_LAUNCH( k_slab_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->own_first, n, st->api_f[ 0 ],
-                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_col, st->sort_keys_a );
+                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, st->sort_keys_a );
+        if ( with_mass_radius ) {
+            PPC_CK( cudaMemcpyAsync( p->mass, st->api_f[ 4 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->radius, st->api_f[ 5 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        }
         PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
         PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
         PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );

@@ -153,12 +153,15 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_upload( const Particl
 // device -> host: the owned slot range, in storage order (ascending (cell key, global index)), with its global indices
 __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_download( const ParticleSet S, const size_t first, const size_t n, float *__restrict__ px,
                                                                      float *__restrict__ py, float *__restrict__ vx, float *__restrict__ vy,
-                                                                     uchar4 *__restrict__ col, uint32_t *__restrict__ gid ) {
+                                                                     float *__restrict__ mass, float *__restrict__ radius, uchar4 *__restrict__ col,
+                                                                     uint32_t *__restrict__ gid ) {
     const size_t t = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( t >= n )
         return;
     const float4 s = S.pv[ first + t ];
+    const float2 a = S.rm[ first + t ];
     px[ t ] = s.x, py[ t ] = s.y, vx[ t ] = s.z, vy[ t ] = s.w;
+    radius[ t ] = a.x, mass[ t ] = a.y;
     col[ t ] = S.col[ first + t ];
     gid[ t ] = S.gid[ first + t ];
 }

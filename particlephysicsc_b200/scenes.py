@@ -111,6 +111,18 @@ def uniform_random(n: int, radius: float = 2.0, phi: float = 0.30, seed: int = 0
     return _finish(name, W, H, px, py, np.full(n, r, np.float32), rng, vmax)
 
 
+def uniform_slab(n: int, radius: float, W: int, H: int, y0: float, y1: float, seed: int, vmax: float = 0.0, name: str = "uniform_slab") -> Scene:
+    """One rank's share of the config-4 field (256M particles over 8 slabs, "generated per slab"): n equal-radius particles,
+    uniform random in [r, W-r] x ([y0, y1) clipped to [r, H-r]) of a W x H box."""
+    rng = Stream(seed)
+    r = np.float32(radius)
+    lo, hi = max(float(y0), radius), min(float(y1), H - radius)
+    px = r + rng.unit(n) * np.float32(W - 2 * radius)
+    py = np.float32(lo) + rng.unit(n) * np.float32(hi - lo)
+    py = np.minimum(py, np.nextafter(np.float32(hi), np.float32(0)))   # float rounding must not push a particle into the next slab
+    return _finish(name, W, H, px, py, np.full(n, r, np.float32), rng, vmax)
+
+
 def jittered_lattice(n: int, radius: float = 2.0, phi: float = 0.30, seed: int = 0x5EED0102, vmax: float = 20.0,
                      name: str = "lattice") -> Scene:
     """Non-overlapping field for the statistical comparison: a square lattice with

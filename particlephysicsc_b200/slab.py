@@ -95,15 +95,29 @@ class DeviceSlab:
         for name, src in (("p_x", px), ("p_y", py), ("v_x", vx), ("v_y", vy), ("mass", mass), ("radius", radius)):
             self.p.array(name)[:] = src
         self.p.array("colors")[:] = rgba
-        ids = np.ascontiguousarray(global_ids, dtype=np.uint32)
-        rc = self.p.lib.ppc_slab_init(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), W, H, float(max_radius), own_rows[0], own_rows[1], halo)
-        if rc != 0:
-            raise ValueError(f"ppc_slab_init failed ({rc})")
+        self.geometry = (W, H, float(max_radius), own_rows)
         self.device = torch.device("cuda", device)
-        self.stream = torch.cuda.ExternalStream(self.p.stream(), device=self.device)
-        self.halo = halo
         self.bufs = {}
         self.counts = (0, 0)
+        self._init(np.ascontiguousarray(global_ids, dtype=np.uint32), halo)
+        self.stream = torch.cuda.ExternalStream(self.p.stream(), device=self.device)
+
+    def _init(self, ids, halo):
+        W, H, max_radius, own_rows = self.geometry
+        rc = self.p.lib.ppc_slab_init(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), W, H, max_radius, own_rows[0], own_rows[1], halo)
+        if rc != 0:
+            raise ValueError(f"ppc_slab_init failed ({rc})")
+        self.halo = halo
+
+    def reinit(self, halo: int) -> None:
+        """Restart this slab from its current owned particles with another halo depth (mass and radius never leave the host
+        arrays' order on download, so the state is read back and uploaded again)."""
+        d = self.download(all_fields=True)
+        n = len(d["ids"])
+        for name in ("p_x", "p_y", "v_x", "v_y", "mass", "radius"):
+            self.p.array(name)[:n] = d[name]
+        self.p.array("colors")[:n] = d["colors"]
+        self._init(d["ids"], halo)
 
     def alloc(self, records: int):
         return self.torch.empty((max(records, 1), RECORD_BYTES), dtype=self.torch.uint8, device=self.device)
@@ -138,18 +152,30 @@ class DeviceSlab:
         self.p.lib.ppc_slab_info(C.byref(self.p.s), C.byref(out))
         return out
 
-    def download(self):
+    def download(self, all_fields: bool = False):
         """Owned particles in storage order: dict of arrays plus their global indices."""
         n_max = self.p.size
         ids = np.zeros(n_max, np.uint32)
-        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), ids.ctypes.data_as(api.u32p))
+        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), int(all_fields))
         if rc == -3:
             raise RuntimeError("host arrays too small for the owned particles")
         n = self.p.length
-        out = {k: self.p.array(k).copy() for k in ("p_x", "p_y", "v_x", "v_y", "colors")}
+        out = {k: self.p.array(k).copy() for k in ("p_x", "p_y", "v_x", "v_y", "colors") + (("mass", "radius") if all_fields else ())}
         out["ids"] = ids[:n].copy()
         out["halo_ok"] = rc == 0
         return out
+
+    def sync_host(self) -> int:
+        """Make the host arrays of the store current (owned particles, storage order) without copying them again; the global
+        indices land in ``self.host_ids``.  Returns the number of owned particles.  This is the "frame is drawn" copy-back."""
+        if getattr(self, "host_ids", None) is None or len(self.host_ids) < self.p.size:
+            self.host_ids = np.zeros(self.p.size, np.uint32)
+        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), self.host_ids.ctypes.data_as(api.u32p), 0)
+        if rc == -2:
+            raise HaloTooShallow(f"halo of {self.halo} rows is too shallow ({self.info().rounds} dependency rounds)")
+        if rc != 0:
+            raise RuntimeError(f"ppc_slab_download failed ({rc})")
+        return self.p.length
 
     def debug_pairs(self) -> np.ndarray:
         n = self.p.lib.ppc_slab_debug_pairs(C.byref(self.p.s), None, 0)
@@ -271,24 +297,30 @@ class _null:
 
 def split_scene(sc, world: int, halo: int, by_load: bool = False):
     """Cut a generated scene (particlephysicsc_b200.scenes.Scene) into `world` slabs by the cell row of the initial positions.
-    Returns (max_radius, ranges, [index arrays])."""
+    Returns (max_radius, ranges, [index arrays], [capacity each store needs for its window])."""
     max_radius = float(max(6.0, float(np.max(sc.radius)))) if sc.n else 6.0
     cell, cols, rows = grid_dims(sc.W, sc.H, max_radius)
     cy = cell_rows(sc.py, cell, rows)
-    ranges = partition_rows_by_load(np.bincount(cy, minlength=rows), world) if by_load else partition_rows(rows, world)
+    per_row = np.bincount(cy, minlength=rows)
+    ranges = partition_rows_by_load(per_row, world) if by_load else partition_rows(rows, world)
     owner = owner_of_rows(cy, ranges)
-    return max_radius, ranges, [np.nonzero(owner == k)[0] for k in range(world)]
+    cum = np.concatenate([[0], np.cumsum(per_row, dtype=np.int64)])
+    need = []
+    for b, e in ranges:   # owned + received ghosts, stored behind the lower ghosts of the previous substep
+        g_lo, g_hi = cum[b] - cum[max(b - halo, 0)], cum[min(e + halo, rows)] - cum[e]
+        need.append(int(cum[e] - cum[b] + 2 * g_lo + g_hi))
+    return max_radius, ranges, [np.nonzero(owner == k)[0] for k in range(world)], need
 
 
-def make_device_slabs(sc, world: int, halo: int, device_of=lambda k: 0, only_rank=None, options=None, by_load: bool = False, slack: float = 1.3):
+def make_device_slabs(sc, world: int, halo: int, device_of=lambda k: 0, only_rank=None, options=None, by_load: bool = False, slack: float = 1.25):
     """DeviceSlab objects for all (or one) of the `world` slabs of scene `sc`."""
-    max_radius, ranges, idx = split_scene(sc, world, halo, by_load)
+    max_radius, ranges, idx, need = split_scene(sc, world, halo, by_load)
     out = []
     for k in range(world):
         if only_rank is not None and k != only_rank:
             continue
         ii = idx[k]
-        cap = int(len(ii) * slack) + 65536
+        cap = int(need[k] * slack) + 65536
         out.append(DeviceSlab(sc.px[ii], sc.py[ii], sc.vx[ii], sc.vy[ii], sc.mass[ii], sc.radius[ii], sc.rgba[ii], ii.astype(np.uint32), sc.W, sc.H,
                               max_radius, ranges[k], halo, capacity=cap, device=device_of(k), options=options))
     return out

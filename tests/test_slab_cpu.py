@@ -41,7 +41,7 @@ def test_cell_rows_follow_the_reference_division():
 
 def model_slabs(oracle, sc, world, halo):
     from slab_model import ModelSlab
-    max_radius, ranges, idx = slab.split_scene(sc, world, halo)
+    max_radius, ranges, idx, _ = slab.split_scene(sc, world, halo)
     full = state_from_scene(sc)
     out = []
     for k in range(world):
