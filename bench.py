@@ -196,6 +196,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     p = api.Particles(n, device=local_rank)
     p.set_sync_policy(api.PPC_SYNC_MANUAL)
     p.set_option("resolve", args.resolve)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        p.set_option(k, int(v))
     p.fill(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba)
     W, H = sc.W, sc.H
     torch.cuda.set_device(local_rank)
@@ -330,7 +333,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         ghosts = int(2.2 * halo * n_per / rows_per)
         cap = int(1.15 * (n_per + 3 * ghosts)) + 65536
         r = slab.DeviceSlab(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba, ids, SLAB_W, H, 6.0, (k * rows_per, (k + 1) * rows_per), halo,
-                            capacity=cap, device=local_rank)
+                            capacity=cap, device=local_rank, options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
         return r, H
 
     def barrier():
@@ -492,6 +495,7 @@ def main():
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
     ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured dependency depth requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")

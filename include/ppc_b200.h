@@ -111,7 +111,8 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *   "stash"    per-thread contact stash: 1 = on (default), 0 = off (streaming path only; test hook)
  *   "resolve"  1 = sequential-equivalent wavefront: replays the reference's pair order, bit-exact (default),
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
- *   "collide"  0 = auto (shared-memory tile kernel), 1 = global-memory thread-per-particle kernel
+ *   "collide"  0 = auto (shared-memory tile kernel with fine x-bins), 1 = global-memory thread-per-particle kernel,
+ *              3 = shared-memory tile kernel scanning the whole 3x3 neighbourhood
  *   "wave_mode"    global rounds of the wavefront: 1 = event driven on packed records while more than a quarter of the
  *              particles are in contact, else polling (default); 2 = always event driven; 0 = always polling
  *   "wave_passes"  shared-memory tile passes ahead of the (polling) global rounds: 0 = none (default); k = k passes while

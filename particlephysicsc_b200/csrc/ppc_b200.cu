@@ -480,18 +480,25 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
                 PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else if ( jacobi )
                 PPC_LAUNCH( ( k_collide_global<0, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
-            else if ( st->opt_collide != 1 && st->opt_stash ) {   // shared-memory tile kernel (default)
+            else if ( st->opt_collide != 1 && st->opt_stash ) {   // shared-memory tile kernels
                 static bool configured = false;
                 if ( !configured ) {
                     PPC_CK( cudaFuncSetAttribute( k_collide_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( TileSmem ) ) );
+                    PPC_CK( cudaFuncSetAttribute( k_collide_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( Tile2Smem ) ) );
                     configured = true;
                 }
+                const bool   bins     = st->opt_collide != 3;   // fine x-bins (default) or the plain 3x3 scan
                 const double per_cell = (double)n / (double)G.cells;
-                int          wc       = (int)( (double)TILE_TARGET / ( TILE_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
-                wc                    = wc < 4 ? 4 : ( wc > TILE_MAX_WC ? TILE_MAX_WC : wc );
+                int          wc       = (int)( (double)( bins ? TILE2_TARGET : TILE_TARGET ) / ( TILE_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
+                const int    wc_max   = bins ? TILE2_MAXC - 2 : TILE_MAX_WC;
+                wc                    = wc < 4 ? 4 : ( wc > wc_max ? wc_max : wc );
                 const int tiles_x = ( G.cols + wc - 1 ) / wc, tiles_y = ( G.rows + TILE_R - 1 ) / TILE_R;
-                PPC_LAUNCH( k_collide_tile, (unsigned)( tiles_x * tiles_y ), TILE_THREADS, sizeof( TileSmem ), st->stream, S, O.pv,
-                            st->cell_start, G, dt, WB, wc, tiles_x );
+                if ( bins )
+                    PPC_LAUNCH( k_collide_tile2, (unsigned)( tiles_x * tiles_y ), TILE_THREADS, sizeof( Tile2Smem ), st->stream, S, O.pv,
+                                st->cell_start, G, dt, WB, wc, tiles_x );
+                else
+                    PPC_LAUNCH( k_collide_tile, (unsigned)( tiles_x * tiles_y ), TILE_THREADS, sizeof( TileSmem ), st->stream, S, O.pv,
+                                st->cell_start, G, dt, WB, wc, tiles_x );
             } else if ( st->opt_stash )
                 PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else

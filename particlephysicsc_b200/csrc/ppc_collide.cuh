@@ -633,6 +633,319 @@ __global__ void __launch_bounds__( TILE_THREADS, PPC_TILE_MINBLOCKS ) k_collide_
         atomicAdd( &WB.counters[ 8 ], n_active );
 }
 
+// ---- K7, shared-memory tile form with fine x-bins (default) ------------------------------------------------------------
+// Same tile, same staging, same per-particle ordering and arithmetic as k_collide_tile above; what changes is WHICH staged
+// particles a centre particle looks at.  The reference's 3x3 cell neighbourhood (cellSize = 2 maxRadius >= 12 px) holds
+// ~30 candidates for r = 2 at area fraction 0.30 and ~165 for r = 1 at 0.40, of which 1-3 touch.  Contacts are limited by
+// |dx| <= r_me + r_other and |dy| <= r_me + r_other (:352-357), so with R = the largest radius staged for this tile:
+//   * each staged row (one cell row of the tile + halo) is counting-sorted in shared memory into fine x-bins of a quarter
+//     cell; a particle scans only the bins overlapping [x - r - R, x + r + R] (a contiguous range of the row's index);
+//   * the cell row above / below is scanned only when y - r - R / y + r + R reaches into it.
+// Both filters are conservative (monotone float arithmetic plus a 0.02 px margin that covers every rounding step at
+// coordinates below 65,536); the reference's own AABB + circle test then decides, so the pair set is unchanged -- with
+// one extra check that the two cell columns differ by at most one, because the reference never pairs particles two
+// columns apart even in the one-ulp corner where its float division puts a touching pair there.
+constexpr int TILE2_CAP  = 2048;                  // staged particles
+constexpr int TILE2_F    = 4;                     // fine bins per cell
+constexpr int TILE2_MAXC = 64;                    // staged columns (centre + halo)
+constexpr int TILE2_NB   = TILE2_MAXC * TILE2_F;  // fine bins per staged row
+constexpr int TILE2_BINS = ( TILE_R + 2 ) * TILE2_NB;
+constexpr int TILE2_TARGET = 800;
+
+struct Tile2Smem {
+    float4   cand[ TILE2_CAP ];    // x, y, radius, API index (bits), in storage order
+    uint32_t fend[ TILE2_BINS ];   // after the scatter: end (exclusive) of fine bin f = row * TILE2_NB + bin in perm; its begin is fend[f - 1]
+    uint16_t perm[ TILE2_CAP ];    // staged indices sorted by (staged row, fine bin)
+    uint8_t  mass[ TILE2_CAP ];    // mass as the resolve reads it: truncated to uint8_t (:141-142)
+    uint8_t  ccol[ TILE2_CAP ];    // cell column relative to the first staged column
+    float    inv_lut[ 256 ];       // 1 / (float)k, the inverse masses of :146-147
+    uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_g0[ TILE_R + 1 ], cen_s0[ TILE_R + 1 ];
+    uint32_t wsum[ 16 ];
+    uint32_t rmax_bits, fallback;
+};
+
+__device__ __forceinline__ int fine_bin( const float x, const float x0, const float inv_w, const int nb ) {
+    const float q = __fmul_rn( __fsub_rn( x, x0 ), inv_w );
+    int         b = ( q >= 0.0f ) ? ( q < 16777216.0f ? __float2int_rz( q ) : nb ) : 0;   // NaN -> 0
+    return b < nb ? b : nb - 1;
+}
+
+__device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const ParticleSet &S, float4 *__restrict__ pv_out,
+                                                    const uint32_t *__restrict__ cell_start, const GridDims &G, const float dt,
+                                                    const WaveBuffers &WB, const int cx0, const int cx1, const int cy0, uint32_t &n_active ) {
+    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
+    const int nb = ( c1 - c0 ) * TILE2_F;                               // fine bins per staged row
+    __syncthreads();                                                    // shared memory may still be in use by the previous sub-tile
+
+    // ---- run table: staged row j = 0 .. TILE_R+1 is grid row cy0 - 1 + j ----
+    if ( threadIdx.x < TILE_R + 2 ) {
+        const int j = threadIdx.x, gy = cy0 - 1 + j;
+        uint32_t  g0 = 0, g1 = 0, m0 = 0, m1 = 0;
+        if ( gy >= 0 && gy < G.rows ) {
+            const size_t row = (size_t)gy * G.cols;
+            g0 = cell_start[ row + c0 ], g1 = cell_start[ row + c1 ];
+            m0 = cell_start[ row + cx0 ], m1 = cell_start[ row + cx1 ];
+        }
+        T.run_g0[ j ] = g0;
+        T.run_s0[ j ] = g1 - g0;   // length for now
+        if ( j >= 1 && j <= TILE_R ) {
+            T.cen_g0[ j - 1 ] = m0;
+            T.cen_s0[ j - 1 ] = m1 - m0;   // length for now
+        }
+    }
+    for ( int f = threadIdx.x; f < ( TILE_R + 2 ) * TILE2_NB; f += TILE_THREADS )
+        T.fend[ f ] = 0;
+    __syncthreads();
+    if ( threadIdx.x == 0 ) {
+        uint32_t run = 0;
+        for ( int j = 0; j < TILE_R + 2; j++ ) {
+            const uint32_t len = T.run_s0[ j ];
+            T.run_s0[ j ]      = run;
+            run += len;
+        }
+        T.run_s0[ TILE_R + 2 ] = run;
+        T.fallback             = run > (uint32_t)TILE2_CAP ? 1u : 0u;
+        uint32_t cen = 0;
+        for ( int j = 0; j < TILE_R; j++ ) {
+            const uint32_t len = T.cen_s0[ j ];
+            T.cen_s0[ j ]      = cen;
+            cen += len;
+        }
+        T.cen_s0[ TILE_R ] = cen;
+        T.rmax_bits        = 0u;
+    }
+    __syncthreads();
+    const uint32_t staged = T.run_s0[ TILE_R + 2 ], centre = T.cen_s0[ TILE_R ];
+    if ( staged == 0 || centre == 0 )
+        return;
+
+    if ( T.fallback ) {   // tile does not fit shared memory: thread-per-particle from global memory
+        for ( int j = 0; j < TILE_R; j++ ) {
+            const uint32_t len = T.cen_s0[ j + 1 ] - T.cen_s0[ j ];
+            for ( uint32_t t = threadIdx.x; t < len; t += TILE_THREADS )
+                collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)T.cen_g0[ j ] + t );
+        }
+        return;
+    }
+
+    // ---- stage the TILE_R + 2 runs; histogram of (row, fine bin); largest radius ----
+    const float x0 = __fmul_rn( (float)c0, G.cell_size ), inv_w = __fdiv_rn( (float)TILE2_F, G.cell_size );
+    float       rmax = 0.0f;
+    for ( uint32_t t = threadIdx.x; t < staged; t += TILE_THREADS ) {
+        int j = 0;
+        while ( j < TILE_R + 1 && t >= T.run_s0[ j + 1 ] )
+            j++;
+        const uint32_t g = T.run_g0[ j ] + ( t - T.run_s0[ j ] );
+        const float4   p = S.pv[ g ];
+        const float2   a = S.rm[ g ];
+        T.cand[ t ]      = make_float4( p.x, p.y, a.x, __uint_as_float( S.gid[ g ] ) );
+        T.mass[ t ]      = (uint8_t)( (unsigned)__float2int_rz( a.y ) & 0xffu );
+        T.ccol[ t ]      = (uint8_t)( S.key[ g ] - (uint32_t)( cy0 - 1 + j ) * (uint32_t)G.cols - (uint32_t)c0 );
+        rmax             = fmaxf( rmax, a.x );
+        atomicAdd( &T.fend[ j * TILE2_NB + fine_bin( p.x, x0, inv_w, nb ) ], 1u );
+    }
+    if ( threadIdx.x < 256 )
+        T.inv_lut[ threadIdx.x ] = __fdiv_rn( 1.0f, (float)threadIdx.x );
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        rmax = fmaxf( rmax, __shfl_xor_sync( 0xffffffffu, rmax, d ) );
+    if ( ( threadIdx.x & 31u ) == 0 && rmax > 0.0f )
+        atomicMax( &T.rmax_bits, __float_as_uint( rmax ) );   // positive floats order like their bit patterns
+    __syncthreads();
+
+    // ---- exclusive scan of the bin counts (each thread a contiguous chunk; warp scan; block scan) ----
+    {
+        constexpr int PER = ( TILE2_BINS + TILE_THREADS - 1 ) / TILE_THREADS;
+        const int     f0  = threadIdx.x * PER;
+        uint32_t      loc[ PER ], sum = 0;
+#pragma unroll
+        for ( int i = 0; i < PER; i++ ) {
+            loc[ i ] = ( f0 + i < TILE2_BINS ) ? T.fend[ f0 + i ] : 0u;
+            sum += loc[ i ];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, inc, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d )
+                inc += o;
+        }
+        if ( ( threadIdx.x & 31u ) == 31u )
+            T.wsum[ threadIdx.x >> 5 ] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for ( unsigned w = 0; w < ( threadIdx.x >> 5 ); w++ )
+            base += T.wsum[ w ];
+        uint32_t run = base + inc - sum;
+#pragma unroll
+        for ( int i = 0; i < PER; i++ ) {
+            if ( f0 + i < TILE2_BINS )
+                T.fend[ f0 + i ] = run;   // begin of the bin; the scatter below advances it to the end
+            run += loc[ i ];
+        }
+    }
+    __syncthreads();
+    for ( uint32_t t = threadIdx.x; t < staged; t += TILE_THREADS ) {
+        int j = 0;
+        while ( j < TILE_R + 1 && t >= T.run_s0[ j + 1 ] )
+            j++;
+        T.perm[ atomicAdd( &T.fend[ j * TILE2_NB + fine_bin( T.cand[ t ].x, x0, inv_w, nb ) ], 1u ) ] = (uint16_t)t;
+    }
+    __syncthreads();
+    const float R = __uint_as_float( T.rmax_bits );
+
+    // ---- one thread per centre particle ----
+    for ( uint32_t t = threadIdx.x; t < centre; t += TILE_THREADS ) {
+        int j = 1;
+        while ( j < TILE_R && t >= T.cen_s0[ j ] )
+            j++;
+        const uint32_t gk   = T.cen_g0[ j - 1 ] + ( t - T.cen_s0[ j - 1 ] );   // storage slot
+        const uint32_t self = T.run_s0[ j ] + ( gk - T.run_g0[ j ] );          // staged index
+        const float4   me4  = T.cand[ self ];
+        const float    x = me4.x, y = me4.y, r = me4.z;
+        const uint32_t gid  = __float_as_uint( me4.w );
+        const int      mycol = T.ccol[ self ];
+        const int      gy    = cy0 - 1 + j;
+        const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
+        const int      b_lo  = fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
+        const float    top   = __fmul_rn( (float)gy, G.cell_size ), bot = __fmul_rn( (float)( gy + 1 ), G.cell_size );
+
+        uint32_t           stash[ TILE_STASH ];
+        unsigned long long skey[ TILE_STASH ];
+        uint32_t           nh = 0;
+#pragma unroll 1
+        for ( int d = 0; d < 3; d++ ) {
+            const int ry = gy - 1 + d;
+            if ( ry < 0 || ry >= G.rows )
+                continue;
+            if ( d == 0 && __fsub_rn( y, reach ) >= top )   // nothing in the row above can be within reach
+                continue;
+            if ( d == 2 && __fadd_rn( y, reach ) < bot )
+                continue;
+            const int      f_lo = ( j - 1 + d ) * TILE2_NB + b_lo, f_hi = ( j - 1 + d ) * TILE2_NB + b_hi;
+            const uint32_t rb = f_lo > 0 ? T.fend[ f_lo - 1 ] : 0u, re = T.fend[ f_hi ];
+            PPC_UNROLL( PPC_TILE_UNROLL )
+            for ( uint32_t q = rb; q < re; q++ ) {
+                const uint32_t s  = T.perm[ q ];
+                const float4   c  = T.cand[ s ];
+                const float    rs = __fadd_rn( r, c.z );
+                const float    dx = __fsub_rn( x, c.x );
+                if ( fabsf( dx ) > rs )   // :353
+                    continue;
+                const float dy = __fsub_rn( y, c.y );
+                if ( fabsf( dy ) > rs )   // :356
+                    continue;
+                const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
+                if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
+                    const int dc = (int)T.ccol[ s ] - mycol;
+                    if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
+                        continue;
+                    if ( nh < (uint32_t)TILE_STASH ) {
+                        const uint32_t g = __float_as_uint( c.w );
+                        stash[ nh ]      = s | ( (uint32_t)d << 16 );
+                        skey[ nh ]       = g < gid ? (unsigned long long)g
+                                                   : ( 1ull << 48 ) | ( (unsigned long long)( (uint32_t)d * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
+                    }
+                    nh++;
+                }
+            }
+        }
+        if ( nh == 0 ) {
+            const float4 old = S.pv[ gk ];
+            pv_out[ gk ]     = make_float4( x, y, old.z, old.w );
+            WB.deg[ gk ]     = 0;
+            WB.state[ gk ]   = 0u;
+            continue;
+        }
+        n_active++;
+        if ( nh > (uint32_t)TILE_STASH ) {   // crowded particle: generic path
+            collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
+            continue;
+        }
+        // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell
+        float       X = x, Y = y;
+        const float wme = T.inv_lut[ T.mass[ self ] ];
+#pragma unroll 1
+        for ( uint32_t a = 0; a < nh; a++ ) {
+            uint32_t           best = a;
+            unsigned long long bkey = skey[ a ];
+#pragma unroll 1
+            for ( uint32_t b = a + 1; b < nh; b++ )
+                if ( skey[ b ] < bkey ) {
+                    bkey = skey[ b ];
+                    best = b;
+                }
+            const uint32_t e = stash[ best ];
+            stash[ best ]    = stash[ a ];
+            skey[ best ]     = skey[ a ];
+            stash[ a ]       = e;
+            skey[ a ]        = bkey;
+            const uint32_t s     = e & 0xffffu;
+            const float4   c     = T.cand[ s ];
+            const bool     me_lo = gid < __float_as_uint( c.w );
+            const float    wq    = T.inv_lut[ T.mass[ s ] ];
+            if ( me_lo ) {
+                const PushTerms P = push_terms( contact_geom( x, y, r, c.x, c.y, c.z, dt ), wme, wq );
+                if ( P.push ) {
+                    X = __fadd_rn( X, P.dpx_lo );
+                    Y = __fadd_rn( Y, P.dpy_lo );
+                }
+            } else {
+                const PushTerms P = push_terms( contact_geom( c.x, c.y, c.z, x, y, r, dt ), wq, wme );
+                if ( P.push ) {
+                    X = __fsub_rn( X, P.dpx_hi );
+                    Y = __fsub_rn( Y, P.dpy_hi );
+                }
+            }
+            const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
+            WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
+        }
+        const float4 old = S.pv[ gk ];
+        pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
+        WB.deg[ gk ]     = (uint16_t)nh;
+        WB.state[ gk ]   = 0u;
+    }
+}
+
+__global__ void __launch_bounds__( TILE_THREADS, PPC_TILE_MINBLOCKS ) k_collide_tile2( const ParticleSet S, float4 *__restrict__ pv_out,
+                                                                   const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
+                                                                   const WaveBuffers WB, const int wc, const int tiles_x ) {
+    extern __shared__ __align__( 16 ) unsigned char smem_raw[];
+    Tile2Smem &T = *reinterpret_cast<Tile2Smem *>( smem_raw );
+    const int tx = (int)( blockIdx.x % (unsigned)tiles_x ), ty = (int)( blockIdx.x / (unsigned)tiles_x );
+    const int cx0 = tx * wc, cy0 = ty * TILE_R;
+    const int cx1 = min( cx0 + wc, G.cols );
+    // staged particle count of the whole tile; a tile that would overflow shared memory is cut into column strips that fit
+    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );
+    __syncthreads();
+    if ( threadIdx.x < TILE_R + 2 ) {
+        const int gy = cy0 - 1 + (int)threadIdx.x;
+        uint32_t  len = 0;
+        if ( gy >= 0 && gy < G.rows )
+            len = cell_start[ (size_t)gy * G.cols + c1 ] - cell_start[ (size_t)gy * G.cols + c0 ];
+        T.run_s0[ threadIdx.x ] = len;
+    }
+    __syncthreads();
+    uint32_t total = 0;
+#pragma unroll
+    for ( int j = 0; j < TILE_R + 2; j++ )
+        total += T.run_s0[ j ];
+    if ( total == 0 )
+        return;
+    if ( threadIdx.x == 0 )   // densest tile, in particles per 1024 cells: sizes the wavefront tiles (a substep late)
+        atomicMax( &WB.counters[ 9 ], (uint32_t)( ( (unsigned long long)total << 10 ) / (unsigned)( ( TILE_R + 2 ) * ( cx1 - cx0 + 2 ) ) ) );
+    const int strips = (int)( ( total + ( TILE2_CAP * 6 / 10 ) - 1 ) / ( TILE2_CAP * 6 / 10 ) );
+    const int sw     = max( ( cx1 - cx0 + strips - 1 ) / strips, 1 );
+    uint32_t  n_active = 0;
+    for ( int sx = cx0; sx < cx1; sx += sw )
+        collide_tile2_body( T, S, pv_out, cell_start, G, dt, WB, sx, min( sx + sw, cx1 ), cy0, n_active );
+#pragma unroll
+    for ( int d = 16; d > 0; d >>= 1 )
+        n_active += __shfl_xor_sync( 0xffffffffu, n_active, d );
+    if ( ( threadIdx.x & 31u ) == 0 && n_active )
+        atomicAdd( &WB.counters[ 8 ], n_active );
+}
+
 // ---- K7b: sequential-equivalent velocity resolve, as a wavefront over the pair dependency graph ----------------
 // Cooperative launch (all CTAs co-resident).  Round r: every still-active particle looks at the head of its contact
 // list; if it is the pair's i and the partner's head is this very pair -- and neither particle was advanced earlier
