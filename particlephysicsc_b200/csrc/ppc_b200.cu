@@ -592,6 +592,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
         abort();
     }
     G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
+    G.row0  = 0;
     ensure_cells( st, G.cells );
     ensure_scratch( st, radix_scratch_words( n ) + scan_scratch_words( (size_t)G.cells + 1 ) + scan_scratch_words( n + 1 ) + 64 );
 
@@ -954,6 +955,7 @@ static GridDims world_grid( uint16_t W, uint16_t H, float max_radius ) {
     G.cols        = (int)ceilf( (float)W / G.cell_size );               // :247
     G.rows        = (int)ceilf( (float)H / G.cell_size );               // :248
     G.cells       = (uint32_t)G.cols * (uint32_t)G.rows;
+    G.row0        = 0;
     return G;
 }
 
@@ -1090,7 +1092,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     const int row_lo = R.own_begin - R.halo > 0 ? R.own_begin - R.halo : 0;
     const int row_hi = R.own_end + R.halo < GW.rows ? R.own_end + R.halo : GW.rows;
     GridDims  G;
-    G.cell_size = GW.cell_size, G.cols = GW.cols, G.rows = row_hi - row_lo, G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
+    G.cell_size = GW.cell_size, G.cols = GW.cols, G.rows = row_hi - row_lo, G.cells = (uint32_t)G.cols * (uint32_t)G.rows, G.row0 = row_lo;
     const size_t bins = (size_t)G.cells + 1;   // + the drop bin
     ensure_cells( st, bins );
     ensure_scratch( st, radix_scratch_words( n_loc ) + scan_scratch_words( bins + 1 ) + scan_scratch_words( n_loc + 1 ) + 64 );

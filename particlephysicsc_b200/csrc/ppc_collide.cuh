@@ -808,7 +808,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const int      gy    = cy0 - 1 + j;
         const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
         const int      b_lo  = fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
-        const float    top   = __fmul_rn( (float)gy, G.cell_size ), bot = __fmul_rn( (float)( gy + 1 ), G.cell_size );
+        const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
 
         uint32_t           stash[ TILE_STASH ];
         unsigned long long skey[ TILE_STASH ];

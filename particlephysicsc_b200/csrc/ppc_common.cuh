@@ -49,6 +49,7 @@ struct GridDims {
     float    cell_size;
     int      cols, rows;
     uint32_t cells;
+    int      row0;   // grid row of the whole field that row 0 of this grid is (slab windows; 0 for a whole-field grid)
 };
 
 }   // namespace ppc
