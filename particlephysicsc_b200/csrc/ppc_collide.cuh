@@ -773,10 +773,16 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         if ( ( threadIdx.x & 31u ) == 31u )
             T.wsum[ threadIdx.x >> 5 ] = inc;
         __syncthreads();
-        uint32_t base = 0;
-        for ( unsigned w = 0; w < ( threadIdx.x >> 5 ); w++ )
-            base += T.wsum[ w ];
-        uint32_t run = base + inc - sum;
+        uint32_t ws = ( threadIdx.x & 31u ) < (unsigned)( TILE_THREADS / 32 ) ? T.wsum[ threadIdx.x & 31u ] : 0u;   // every warp scans the warp sums
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, ws, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d )
+                ws += o;
+        }
+        const unsigned wid  = threadIdx.x >> 5;
+        const uint32_t base = wid ? __shfl_sync( 0xffffffffu, ws, wid - 1 ) : 0u;
+        uint32_t       run  = base + inc - sum;
 #pragma unroll
         for ( int i = 0; i < PER; i++ ) {
             if ( f0 + i < TILE2_BINS )
@@ -840,12 +846,8 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
                     const int dc = (int)T.ccol[ s ] - mycol;
                     if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
                         continue;
-                    if ( nh < (uint32_t)TILE_STASH ) {
-                        const uint32_t g = __float_as_uint( c.w );
-                        stash[ nh ]      = s | ( (uint32_t)d << 16 );
-                        skey[ nh ]       = g < gid ? (unsigned long long)g
-                                                   : ( 1ull << 48 ) | ( (unsigned long long)( (uint32_t)d * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
-                    }
+                    if ( nh < (uint32_t)TILE_STASH )
+                        stash[ nh ] = s | ( (uint32_t)d << 16 );
                     nh++;
                 }
             }
@@ -862,7 +864,15 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
             continue;
         }
-        // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell
+        // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell.
+        //   pairs (i, me), i < me : key = i
+        //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j
+#pragma unroll 1
+        for ( uint32_t a = 0; a < nh; a++ ) {
+            const uint32_t e = stash[ a ], s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
+            skey[ a ] = g < gid ? (unsigned long long)g
+                                : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
+        }
         float       X = x, Y = y;
         const float wme = T.inv_lut[ T.mass[ self ] ];
 #pragma unroll 1
@@ -884,17 +894,12 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             const float4   c     = T.cand[ s ];
             const bool     me_lo = gid < __float_as_uint( c.w );
             const float    wq    = T.inv_lut[ T.mass[ s ] ];
-            if ( me_lo ) {
-                const PushTerms P = push_terms( contact_geom( x, y, r, c.x, c.y, c.z, dt ), wme, wq );
-                if ( P.push ) {
-                    X = __fadd_rn( X, P.dpx_lo );
-                    Y = __fadd_rn( Y, P.dpy_lo );
-                }
-            } else {
-                const PushTerms P = push_terms( contact_geom( c.x, c.y, c.z, x, y, r, dt ), wq, wme );
-                if ( P.push ) {
-                    X = __fsub_rn( X, P.dpx_hi );
-                    Y = __fsub_rn( Y, P.dpy_hi );
+            {   // operands selected by role, one evaluation: lo = the pair's i
+                const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
+                                                              me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
+                if ( P.push ) {   // x + t and x - (-t) are the same float operation; the hi side subtracts its own terms (:152-155)
+                    X = me_lo ? __fadd_rn( X, P.dpx_lo ) : __fsub_rn( X, P.dpx_hi );
+                    Y = me_lo ? __fadd_rn( Y, P.dpy_lo ) : __fsub_rn( Y, P.dpy_hi );
                 }
             }
             const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
@@ -1289,6 +1294,189 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                 __syncthreads();
             }
         }
+        if ( threadIdx.x == 0 && blockIdx.x == 0 )
+            WB.counters[ 4 ] = r;
+        grid.sync();
+    }
+}
+
+// ---- K7b, event-driven global rounds on a BITMAP of particles to examine (default for dense contact sets) --------------
+// Same records, same firing rule, same claim by compare-and-swap and the same chain following as k_resolve_events; what
+// changes is how the work of a round is handed out.  The queue version pays two CTA barriers per item and thread (its
+// pushes are staged in shared memory), so every thread of a CTA waits for the slowest chain of dependent loads of that
+// iteration, and the queue order scatters neighbouring particles over the whole grid.  Here "examine p next round" is one
+// fire-and-forget atomicOr into a bitmap (one bit per storage slot, 2 MB for 16M particles: it lives in L2), and a round is
+// a sweep over that bitmap: every warp owns a fixed, contiguous range of slots, so
+//   * there is no barrier and no shared counter inside a round -- a warp's lanes wait only for their own loads;
+//   * lanes of a warp examine neighbouring slots, whose records and partners share cache lines (storage is cell-sorted).
+// Termination: each warp adds its number of pushes to the round's counter (one atomic per warp and round).
+struct WaveBitmaps {
+    uint32_t *bits[ 2 ];   // [round parity][slot / 32]; the reader zeroes what it read, so the map is clean when it becomes "next"
+    uint32_t  words;
+};
+
+// first round's map: every particle with contacts (also writes the zero words)
+__global__ void __launch_bounds__( 256 ) k_wave_bitmap_init( const WaveBuffers WB, const WaveBitmaps M, const size_t n ) {
+    const size_t   k   = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const unsigned any = __ballot_sync( 0xffffffffu, k < n && WB.deg[ k ] != 0 );
+    if ( ( threadIdx.x & 31u ) == 0 && ( k >> 5 ) < M.words )
+        M.bits[ 1 ][ k >> 5 ] = any;   // round 1 reads parity 1 ... see k_resolve_bitmap
+}
+
+__global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_bitmap( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
+                                                                  const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
+                                                                  const WaveRecs R, const WaveBitmaps M ) {
+    namespace cg        = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
+    volatile uint32_t   *counters = WB.counters;
+    const unsigned       lane = threadIdx.x & 31u;
+    const uint32_t       warp_g = ( blockIdx.x * EV_THREADS + threadIdx.x ) >> 5, nwarps = ( gridDim.x * EV_THREADS ) >> 5;
+    // contiguous word range of this warp, a multiple of 32 words (one word per lane and sweep step)
+    const uint32_t per_warp = ( ( ( M.words + nwarps - 1 ) / nwarps ) + 31u ) & ~31u;
+    const uint32_t w_begin = warp_g * per_warp, w_end = min( w_begin + per_warp, M.words );
+
+    for ( uint32_t r = 1;; r++ ) {
+        if ( r > 1 && counters[ ( r - 1 ) % 3 ] == 0 )
+            break;
+        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {
+            if ( blockIdx.x == 0 && threadIdx.x == 0 )
+                atomicOr( &WB.counters[ 3 ], 2u );
+            break;
+        }
+        if ( blockIdx.x == 0 && threadIdx.x == 0 )
+            counters[ ( r + 1 ) % 3 ] = 0;
+        uint32_t *cur = M.bits[ r & 1 ], *nxt = M.bits[ ( r & 1 ) ^ 1 ];
+        uint32_t  pushed = 0;
+        auto push = [ & ]( const uint32_t q ) {
+            atomicOr( &nxt[ q >> 5 ], 1u << ( q & 31u ) );
+            pushed++;
+        };
+
+        for ( uint32_t w0 = w_begin; w0 < w_end; w0 += 32 ) {
+            const uint32_t wi   = w0 + lane;
+            uint32_t       word = 0;
+            if ( wi < w_end ) {
+                word = __ldcg( &cur[ wi ] );
+                if ( word )
+                    cur[ wi ] = 0;
+            }
+            // distribute the set bits of these 32 words over the lanes, 32 at a time
+            uint32_t cnt = (uint32_t)__popc( word ), incl = cnt;
+#pragma unroll
+            for ( int d = 1; d < 32; d <<= 1 ) {
+                const uint32_t o = __shfl_up_sync( 0xffffffffu, incl, d );
+                if ( lane >= (unsigned)d )
+                    incl += o;
+            }
+            const uint32_t total = __shfl_sync( 0xffffffffu, incl, 31 );
+            for ( uint32_t t0 = 0; t0 < total; t0 += 32 ) {
+                const uint32_t t = t0 + lane;
+                // owner lane L of item t: the first lane whose inclusive prefix exceeds t
+                uint32_t lo_l = 0, hi_l = 31;
+#pragma unroll
+                for ( int it = 0; it < 5; it++ ) {
+                    const uint32_t mid = ( lo_l + hi_l ) >> 1;
+                    const uint32_t pm  = __shfl_sync( 0xffffffffu, incl, mid );
+                    if ( pm > t )
+                        hi_l = mid;
+                    else
+                        lo_l = mid + 1;
+                }
+                const uint32_t L     = lo_l;
+                const uint32_t wordL = __shfl_sync( 0xffffffffu, word, L );
+                const uint32_t inclL = __shfl_sync( 0xffffffffu, incl, L ), cntL = __shfl_sync( 0xffffffffu, cnt, L );
+                if ( t >= total )
+                    continue;
+                const uint32_t kth = t - ( inclL - cntL );                    // 0-based rank of the bit inside its word
+                const uint32_t p   = ( ( w0 + L ) << 5 ) + (uint32_t)__fns( wordL, 0, (int)kth + 1 );
+
+                const WaveRec  A   = load_wave_rec( R.wr + p );
+                const uint32_t pcA = A.state & PC_MASK;
+                if ( !( pcA < A.deg && ( A.state >> PC_BITS ) != r ) )
+                    continue;
+                const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
+                const WaveRec  B = load_wave_rec( R.wr + o );
+                const uint32_t pcB = B.state & PC_MASK;
+                if ( !( pcB < B.deg && ( B.state >> PC_BITS ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) )
+                    continue;
+                const bool     p_lo = ( e & INC_LO_FLAG ) != 0;
+                const uint32_t lo = p_lo ? p : o, hi = p_lo ? o : p;
+                const uint32_t st_lo = p_lo ? A.state : B.state, st_hi = p_lo ? B.state : A.state;
+                const uint32_t deg_lo = p_lo ? A.deg : B.deg, deg_hi = p_lo ? B.deg : A.deg;
+                const uint32_t claim = ( r << PC_BITS ) | ( st_lo & PC_MASK );
+                if ( atomicCAS( &R.wr[ lo ].state, st_lo, claim ) != st_lo )
+                    continue;   // the thread examining the other end fires this pair
+                const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
+                const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
+                float2      *va = reinterpret_cast<float2 *>( R.dr + lo ) + 2, *vb = reinterpret_cast<float2 *>( R.dr + hi ) + 2;
+                float2       ua = __ldcg( va ), ub = __ldcg( vb );
+                const ImpulseTerms T = impulse_terms( contact_geom( ga.x, ga.y, ga.z, gb.x, gb.y, gb.z, dt ), ga.w, gb.w, ua.x, ua.y, ub.x, ub.y );
+                if ( T.impulse ) {
+                    ua.x = __fadd_rn( ua.x, T.dvx_lo );
+                    ua.y = __fadd_rn( ua.y, T.dvy_lo );
+                    ub.x = __fsub_rn( ub.x, T.dvx_hi );
+                    ub.y = __fsub_rn( ub.y, T.dvy_hi );
+                }
+                const uint32_t nhi = ( st_hi & PC_MASK ) + 1;   // the pair's j is done for this round
+                *vb                = ub;
+                R.wr[ hi ].state   = ( r << PC_BITS ) | nhi;
+                if ( nhi < deg_hi )
+                    push( hi );
+                else
+                    *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;   // last contact done: final velocity
+
+                // follow the chain from the pair's i (see k_resolve_events)
+                const WaveRec &C   = p_lo ? A : B;
+                const uint32_t cur_p = lo, cdeg = deg_lo;
+                uint32_t       cpc = ( st_lo & PC_MASK ) + 1;
+                float2         uc  = ua;
+                for ( int follow = 0; follow < EV_FOLLOW && cpc < cdeg; follow++ ) {
+                    const uint32_t e2 = rec_head( S, acc, G, WB, C, cur_p, cpc ), x = e2 & ~INC_LO_FLAG;
+                    const WaveRec  X   = load_wave_rec( R.wr + x );
+                    const uint32_t pcx = X.state & PC_MASK;
+                    if ( ( X.state >> PC_BITS ) == r || pcx >= X.deg || ( rec_head( S, acc, G, WB, X, x, pcx ) & ~INC_LO_FLAG ) != cur_p )
+                        break;
+                    if ( atomicCAS( &R.wr[ x ].state, X.state, ( r << PC_BITS ) | pcx ) != X.state )
+                        break;
+                    const float4 gx = __ldcg( reinterpret_cast<const float4 *>( R.dr + x ) );
+                    float2      *vx = reinterpret_cast<float2 *>( R.dr + x ) + 2;
+                    float2       ux = __ldcg( vx );
+                    const bool   c_lo = ( e2 & INC_LO_FLAG ) != 0;   // cur is this pair's i
+                    const ImpulseTerms F = impulse_terms( contact_geom( c_lo ? ga.x : gx.x, c_lo ? ga.y : gx.y, c_lo ? ga.z : gx.z, c_lo ? gx.x : ga.x,
+                                                                         c_lo ? gx.y : ga.y, c_lo ? gx.z : ga.z, dt ),
+                                                           c_lo ? ga.w : gx.w, c_lo ? gx.w : ga.w, c_lo ? uc.x : ux.x, c_lo ? uc.y : ux.y,
+                                                           c_lo ? ux.x : uc.x, c_lo ? ux.y : uc.y );
+                    if ( F.impulse ) {
+                        if ( c_lo ) {
+                            uc.x = __fadd_rn( uc.x, F.dvx_lo ), uc.y = __fadd_rn( uc.y, F.dvy_lo );
+                            ux.x = __fsub_rn( ux.x, F.dvx_hi ), ux.y = __fsub_rn( ux.y, F.dvy_hi );
+                        } else {
+                            ux.x = __fadd_rn( ux.x, F.dvx_lo ), ux.y = __fadd_rn( ux.y, F.dvy_lo );
+                            uc.x = __fsub_rn( uc.x, F.dvx_hi ), uc.y = __fsub_rn( uc.y, F.dvy_hi );
+                        }
+                    }
+                    cpc++;
+                    *vx              = ux;
+                    R.wr[ x ].state = ( r << PC_BITS ) | ( pcx + 1 );
+                    if ( pcx + 1 < X.deg )
+                        push( x );
+                    else
+                        *( reinterpret_cast<float2 *>( pv_out + x ) + 1 ) = ux;
+                }
+                *va                 = uc;
+                R.wr[ cur_p ].state = ( r << PC_BITS ) | cpc;
+                if ( cpc < cdeg )
+                    push( cur_p );
+                else
+                    *( reinterpret_cast<float2 *>( pv_out + cur_p ) + 1 ) = uc;
+            }
+        }
+#pragma unroll
+        for ( int d = 16; d > 0; d >>= 1 )
+            pushed += __shfl_xor_sync( 0xffffffffu, pushed, d );
+        if ( lane == 0 && pushed )
+            atomicAdd( &WB.counters[ r % 3 ], pushed );
         if ( threadIdx.x == 0 && blockIdx.x == 0 )
             WB.counters[ 4 ] = r;
         grid.sync();
