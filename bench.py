@@ -352,16 +352,17 @@ def run_slab(args, rank: int, world: int, local_rank: int):
 
     def settle_and_choose_halo(me, tr, group_max):
         """Relax the random field with a generous halo, then restart from the relaxed state with the halo this field needs:
-        (dependency rounds of the resolve) x 2 + 1 rows (csrc/ppc_slab.cuh), a few rows of margin on top."""
+        the rows the resolve's inexactness mark travels into the window (csrc/ppc_collide.cuh ST_TAINT), plus a margin."""
         run(me, tr, args.settle)
-        rounds = 0
-        for _ in range(4):
+        travelled = rounds = 0
+        for _ in range(6):
             run(me, tr, 1)
-            rounds = max(rounds, int(me.info().rounds))
-        rounds = group_max(rounds)
-        halo = slab.required_halo(rounds, 2) + args.halo_margin
+            i = me.info()
+            travelled, rounds = max(travelled, int(i.taint_rows)), max(rounds, int(i.rounds))
+        travelled, rounds = group_max(travelled), group_max(rounds)
+        halo = slab.required_halo(travelled, args.halo_margin)
         me.reinit(halo)
-        return halo, rounds
+        return halo, rounds, travelled
 
     def timed(me, tr, steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -382,7 +383,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
 
     me, H = make_rank(rank, world, args.settle_halo)
     tr = slab.DistTransport(dist, dev) if dist is not None else None
-    halo, rounds = settle_and_choose_halo(me, tr, group_max)
+    halo, rounds, travelled = settle_and_choose_halo(me, tr, group_max)
     run(me, tr, args.warmup)
 
     sampler = ClockSampler(local_rank)
@@ -419,6 +420,12 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     stages = {k: (ms / prof_steps, cnt // prof_steps) for k, (ms, cnt) in me.p.profile_read().items() if cnt}
     info = me.info()
     sent = me.counts
+    phase_ms = None
+    if tr is not None:   # where a distributed substep spends its wall time (every phase synchronised: diagnostics, not the metric)
+        timers = {}
+        for _ in range(prof_steps):
+            slab.slab_step(me, tr, DT, False, timers)
+        phase_ms = {k: round(v / prof_steps, 4) for k, v in timers.items()}
     peak, peak_src = measured_peak_gbs()
 
     # the same per-GPU workload on ONE GPU (a single slab, no neighbours), measured by rank 0 in this same job: the
@@ -452,14 +459,15 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": descr, "particles_per_gpu": n_per, "particles": n_per * world, "box": [SLAB_W, H],
-                           "grid": [info.cols, info.rows], "rows_per_gpu": rows_per, "halo_rows": halo, "dependency_rounds": rounds, "dt": DT,
+                           "grid": [info.cols, info.rows], "rows_per_gpu": rows_per, "halo_rows": halo, "dependency_rounds": rounds,
+                           "inexactness_travel_rows": travelled, "dt": DT,
                            "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
                            "resolve": "sequential-equivalent wavefront (bit-exact)",
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n_per / 1e6),
                            "parallelism": f"{world} slabs of cell rows, neighbour send/recv (NCCL) of migrants + {halo} ghost rows per substep"
                                           if world > 1 else "one slab (no neighbours)",
                            "records_sent_per_substep_rank0": list(sent), "bytes_sent_per_substep_rank0": 32 * sum(sent),
-                           "window_particles_rank0": int(info.n_window)},
+                           "window_particles_rank0": int(info.n_window), "phase_wall_ms_rank0_synchronised": phase_ms},
                 "roofline": roofline,
                 "roofline_substep": {"bound": "hbm", "achieved": substep_gbs, "peak": peak, "unit": "GB/s", "frac": substep_gbs / peak,
                                      "note": "40 B x owned particles x substeps / time, whole substep, per GPU"},
@@ -493,7 +501,7 @@ def main():
                     help="default: pile16m on one GPU (the configuration the roofline target is stated on), slab32m on several")
     ap.add_argument("--particles-per-gpu", type=int, default=0, help="slab32m only: override 2**25")
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
-    ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured dependency depth requires")
+    ap.add_argument("--halo-margin", type=int, default=2, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

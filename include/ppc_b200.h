@@ -153,9 +153,10 @@ const char        *ppc_version( void );
  *     ppc_slab_pack    write those records (32 bytes each) into two device buffers of the caller
  *     -- the caller moves the buffers to the neighbouring ranks (NCCL send/recv, or a device copy in one process) --
  *     ppc_slab_finish  take the received records in, build the grid over owned + ghost rows, narrow phase, resolve
- * With halo_rows >= (dependency rounds of the resolve) x (1 or 2, by engine) + 1 the owned particles' positions AND
- * velocities are bit-identical to a single-GPU run of the whole field; ppc_slab_begin / ppc_slab_download return -2 when
- * the substep just finished did not satisfy that bound.  All functions return -1 on misuse.
+ * The particles of a window's outermost ghost row miss their outward contacts; the resolve marks them and everything that
+ * resolves a pair with a marked particle.  While the mark does not reach an owned particle, owned positions AND velocities
+ * are bit-identical to a single-GPU run of the whole field; ppc_slab_begin / ppc_slab_download return -2 when it did in the
+ * substep just finished (halo_rows too small; ppc_slab_info reports how far the mark travelled).  -1 on misuse.
  * ===================================================================================================== */
 #define PPC_SLAB_RECORD_BYTES 32
 
@@ -179,6 +180,7 @@ typedef struct ppc_slab_info_t {
     int      row_lo, row_hi;               /* window of the last grid build (owned + ghost rows) */
     int      own_row_begin, own_row_end, halo_rows, cols, rows;
     uint32_t rounds;                       /* dependency rounds of the last resolve */
+    uint32_t taint_rows;                   /* rows the inexactness of the window's outermost rows travelled inwards in the last resolve */
 } ppc_slab_info_t;
 int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out );
 /* candidate pairs (i, j) whose i (lower global index) this rank owns; every pair of the field appears on exactly one rank */

@@ -64,7 +64,7 @@ struct Store {
     uint32_t    *d_word = nullptr;   // one word for small reductions
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     WaveRecs     recs = {};          // packed records of the event-driven rounds
-    int          events_grid = 0, bitmap_grid = 0;
+    int          events_grid = 0;
     size_t       wave_cap = 0;
     int          wave_grid = 0;
     WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
@@ -80,6 +80,7 @@ struct Store {
     int       row_lo = 0, row_hi = 0;        // window of the last grid build
     uint32_t *slab_counts = nullptr;         // device [8]: send counts lo/hi, lost, -, pack cursors lo/hi
     uint32_t *h_slab = nullptr;              // pinned [8]
+    uint32_t  slab_own_first = 0, slab_own_end = 0, slab_taint_rows = 0;
     int       wave_hops = 1;                 // contacts an error can travel per wavefront round of the engine last used (0: unbounded)
     // last grid
     bool     grid_valid = false, pre_valid = false;
@@ -186,12 +187,6 @@ static void ensure_wave_buffers( Store *st ) {
         abort();
     }
     st->events_grid = per_sm * sms;   // latency bound: as many loads in flight as the SM holds
-    PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_bitmap, EV_THREADS, 0 ) );
-    if ( per_sm < 1 ) {
-        fprintf( stderr, "particlephysicsc_b200: bitmap wavefront kernel cannot be made resident\n" );
-        abort();
-    }
-    st->bitmap_grid = per_sm * sms;
 }
 
 static void check_device_flags( Store *st ) {   // after a stream synchronise
@@ -476,9 +471,10 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
-            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 6 * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 8 * sizeof( uint32_t ), st->stream ) );
         }
-        const WaveBuffers WB = st->wave;
+        WaveBuffers WB = st->wave;
+        WB.own_first = st->slab ? st->slab_own_first : 0u, WB.own_end = st->slab ? st->slab_own_end : 0u;
         {
             StageTimer T( st, ST_COLLIDE );                                            // K7: narrow phase + position pushes
             const unsigned blocks = div_up( n, COLLIDE_THREADS );
@@ -553,23 +549,7 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             size_t n_arg = n;
             // packed records pay off when most particles are in contact; sparse contact sets are cheaper on the polling
             // kernel's compact per-CTA queues (no pack pass).  "wave_mode": 1 = choose by density (default), 2 = always events.
-            if ( st->opt_wave_mode == 3 && passes == 0 ) {   // event driven, work handed out through a bitmap
-                const WaveRecs R = st->recs;
-                st->wave_hops    = 2;
-                WaveBitmaps M;
-                M.words     = (uint32_t)( ( n + 31 ) / 32 );
-                M.bits[ 0 ] = st->wave.list[ 0 ], M.bits[ 1 ] = st->wave.list[ 1 ];
-                PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
-                PPC_CK( cudaMemsetAsync( M.bits[ 0 ], 0, (size_t)M.words * sizeof( uint32_t ), st->stream ) );
-                PPC_LAUNCH( k_wave_bitmap_init, div_up( (size_t)M.words * 32, 256 ), 256, 0, st->stream, WB, M, n );
-                int       grid = st->bitmap_grid;
-                const int want = (int)div_up( (size_t)M.words, ( EV_THREADS / 32 ) * 32 );   // at least 32 words per warp
-                if ( grid > want )
-                    grid = want;
-                void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&R, (void *)&M };
-                PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_bitmap, dim3( grid ), dim3( EV_THREADS ), args, 0, st->stream ) );
-                ++g_launches;
-            } else if ( ( st->opt_wave_mode == 2 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
+            if ( ( st->opt_wave_mode == 2 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
                 const WaveRecs R = st->recs;
                 st->wave_hops    = 2;   // a thread fires a star of pairs around one particle per round (chain following)
                 PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
@@ -615,6 +595,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     }
     G.cells = (uint32_t)G.cols * (uint32_t)G.rows;
     G.row0  = 0;
+    G.taint_lo = G.taint_hi = -1;
     ensure_cells( st, G.cells );
     ensure_scratch( st, radix_scratch_words( n ) + scan_scratch_words( (size_t)G.cells + 1 ) + scan_scratch_words( n + 1 ) + 64 );
 
@@ -978,6 +959,7 @@ static GridDims world_grid( uint16_t W, uint16_t H, float max_radius ) {
     G.rows        = (int)ceilf( (float)H / G.cell_size );               // :248
     G.cells       = (uint32_t)G.cols * (uint32_t)G.rows;
     G.row0        = 0;
+    G.taint_lo = G.taint_hi = -1;
     return G;
 }
 
@@ -1038,16 +1020,17 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
     return 0;
 }
 
-// Depth of the last resolve's pair dependency graph against the halo (see ppc_slab.cuh): stream must be idle.
+// Did the last resolve keep the owned particles exact?  The resolve marks every particle whose result may differ from the
+// whole-field run (ST_TAINT, csrc/ppc_collide.cuh) and reports when the mark reaches an owned particle.  Stream must be idle.
 static int slab_halo_ok( Store *st ) {
     if ( st->opt_resolve != 1 || !st->wave.counters || !( st->slab_rows.has_lo || st->slab_rows.has_hi ) )
         return 1;
-    uint32_t rounds = 0;
-    PPC_CK( cudaMemcpy( &rounds, st->wave.counters + 4, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
-    if ( rounds == 0 )
-        return 1;
-    // the outermost halo row starts out wrong; the error moves at most wave_hops rows per round; owned rows start `halo` rows in
-    return st->wave_hops > 0 && (long long)rounds * st->wave_hops + 1 <= (long long)st->slab_rows.halo ? 1 : 0;
+    if ( st->wave_hops == 0 )
+        return 0;   // shared-memory tile passes do not carry the mark
+    uint32_t w[ 2 ] = { 0, 0 };
+    PPC_CK( cudaMemcpy( w, st->wave.counters + 10, sizeof( w ), cudaMemcpyDeviceToHost ) );
+    st->slab_taint_rows = w[ 1 ];
+    return w[ 0 ] == 0u ? 1 : 0;
 }
 
 extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] ) {
@@ -1115,6 +1098,8 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     const int row_hi = R.own_end + R.halo < GW.rows ? R.own_end + R.halo : GW.rows;
     GridDims  G;
     G.cell_size = GW.cell_size, G.cols = GW.cols, G.rows = row_hi - row_lo, G.cells = (uint32_t)G.cols * (uint32_t)G.rows, G.row0 = row_lo;
+    G.taint_lo = row_lo > 0 ? 0 : -1;                    // the window's first / last row misses contacts beyond the window
+    G.taint_hi = row_hi < GW.rows ? G.rows - 1 : -1;
     const size_t bins = (size_t)G.cells + 1;   // + the drop bin
     ensure_cells( st, bins );
     ensure_scratch( st, radix_scratch_words( n_loc ) + scan_scratch_words( bins + 1 ) + scan_scratch_words( n_loc + 1 ) + 64 );
@@ -1149,6 +1134,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     st->grid       = G;
     st->grid_valid = true;
     st->row_lo = row_lo, st->row_hi = row_hi;
+    st->slab_own_first = (uint32_t)st->own_first, st->slab_own_end = (uint32_t)( st->own_first + st->n_own );
     if ( n_work >= 1 )
         resolve_stage( st, n_work, G, time_step );
     st->pre_valid = true;
@@ -1197,6 +1183,8 @@ extern "C" int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out ) {
     if ( st->wave.counters && st->opt_resolve == 1 )
         PPC_CK( cudaMemcpy( &rounds, st->wave.counters + 4, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
     out->rounds = rounds;
+    slab_halo_ok( st );
+    out->taint_rows = st->slab_taint_rows;
     return 0;
 }
 

@@ -37,6 +37,17 @@ constexpr int      INC_MAXDEG      = 16;    // contacts per particle the TILE ke
 constexpr uint32_t INC_LO_FLAG     = 0x80000000u;   // this particle is the pair's i (lower API index)
 constexpr uint32_t PC_BITS         = 12;    // wavefront state word: (round << 12) | contacts already resolved
 constexpr uint32_t PC_MASK         = ( 1u << PC_BITS ) - 1u;
+// Bit 31 of the state word: TAINT.  Slab windows only (GridDims::taint_lo / taint_hi): the particles of the outermost ghost
+// row miss their outward contacts, so what the resolve computes for them -- and for every particle that resolves a pair
+// with a tainted one -- may differ from the whole-field run.  The bit travels with the pairs; the resolve reports whether
+// it reached an owned particle (counters[10]) and how many rows it got into the window (counters[11]).
+constexpr uint32_t ST_TAINT        = 0x80000000u;
+constexpr uint32_t ST_ROUND_LIMIT  = ( 1u << ( 31 - PC_BITS ) ) - 1u;
+__device__ __forceinline__ uint32_t st_round( const uint32_t w ) { return ( w & ~ST_TAINT ) >> PC_BITS; }
+__device__ __forceinline__ uint32_t initial_state( const GridDims &G, const uint32_t key ) {
+    const int row = (int)( key / (uint32_t)G.cols );
+    return ( row == G.taint_lo || row == G.taint_hi ) ? ST_TAINT : 0u;
+}
 constexpr int      WAVE_THREADS    = 256;
 
 struct Cand {
@@ -298,9 +309,11 @@ struct WaveBuffers {
     size_t    stride;    // particle capacity
     uint32_t  maxdeg;    // list positions stored per particle (>= INC_MAXDEG); longer lists are recomputed on demand
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
+    uint32_t  own_first, own_end;   // slab mode: storage slots of the owned particles (taint reports); 0, 0 otherwise
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
                          // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
-                         // [8] particles with at least one contact in this substep, [9] densest tile in particles per 1024 cells (from k_collide_tile)
+                         // [8] particles with at least one contact in this substep, [9] densest tile in particles per 1024 cells (from k_collide_tile),
+                         // [10] slab mode: the taint reached an owned particle, [11] rows the taint travelled into the window
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
@@ -331,7 +344,7 @@ __device__ __noinline__ void collide_one_generic( const ParticleSet &S, float4 *
             cnt = PC_MASK;
         }
         WB.deg[ k ]   = (uint16_t)cnt;
-        WB.state[ k ] = 0u;
+        WB.state[ k ] = initial_state( G, S.key[ k ] );
     }
 }
 
@@ -552,7 +565,7 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
             const float4 old = S.pv[ gk ];
             pv_out[ gk ]     = make_float4( x, y, old.z, old.w );
             WB.deg[ gk ]     = 0;
-            WB.state[ gk ]   = 0u;
+            WB.state[ gk ]   = initial_state( G, key );
             continue;
         }
         n_active++;
@@ -601,7 +614,7 @@ __device__ __forceinline__ void collide_tile_body( TileSmem &T, const ParticleSe
         const float4 old = S.pv[ gk ];
         pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
         WB.deg[ gk ]     = (uint16_t)nh;
-        WB.state[ gk ]   = 0u;
+        WB.state[ gk ]   = initial_state( G, key );
     }
 }
 
@@ -815,6 +828,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
         const int      b_lo  = fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
+        const uint32_t st0   = ( gy == G.taint_lo || gy == G.taint_hi ) ? ST_TAINT : 0u;   // outermost ghost row of a slab window
 
         uint32_t           stash[ TILE_STASH ];
         unsigned long long skey[ TILE_STASH ];
@@ -856,7 +870,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             const float4 old = S.pv[ gk ];
             pv_out[ gk ]     = make_float4( x, y, old.z, old.w );
             WB.deg[ gk ]     = 0;
-            WB.state[ gk ]   = 0u;
+            WB.state[ gk ]   = st0;
             continue;
         }
         n_active++;
@@ -908,7 +922,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const float4 old = S.pv[ gk ];
         pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
         WB.deg[ gk ]     = (uint16_t)nh;
-        WB.state[ gk ]   = 0u;
+        WB.state[ gk ]   = st0;
     }
 }
 
@@ -964,6 +978,24 @@ __device__ __forceinline__ uint32_t head_contact( const ParticleSet &S, const Gl
     return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
 }
 
+// A pair with a tainted end fires: whichever end was clean becomes tainted now.  Tell the host if that particle is owned,
+// and how many rows into the window the taint has come.
+__device__ __forceinline__ void report_taint( const ParticleSet &S, const GridDims &G, const WaveBuffers &WB, const uint32_t a, const uint32_t wa,
+                                              const uint32_t b, const uint32_t wb ) {
+    if ( ( wa & wb & ST_TAINT ) != 0u )
+        return;   // both were tainted already
+    const uint32_t fresh = ( wa & ST_TAINT ) ? b : a;
+    if ( fresh >= WB.own_first && fresh < WB.own_end )
+        atomicOr( &WB.counters[ 10 ], 1u );
+    const int row = (int)( S.key[ fresh ] / (uint32_t)G.cols );
+    int       depth = 0x7fffffff;
+    if ( G.taint_lo >= 0 )
+        depth = row - G.taint_lo;
+    if ( G.taint_hi >= 0 )
+        depth = min( depth, G.taint_hi - row );
+    atomicMax( &WB.counters[ 11 ], (uint32_t)max( depth, 0 ) );
+}
+
 // One wavefront step for particle `me` in round r.  Returns true while the particle still has unresolved contacts.
 __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const GlobalAccessor &acc, float4 *pv_out, const GridDims &G,
                                                  const float dt, const WaveBuffers &WB, const uint32_t me, const uint32_t r ) {
@@ -974,7 +1006,7 @@ __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const Glo
     const uint32_t pc = w & PC_MASK;
     if ( pc >= deg )
         return false;
-    if ( ( w >> PC_BITS ) == r )   // advanced earlier in this round by the partner's thread: look again next round
+    if ( st_round( w ) == r )   // advanced earlier in this round by the partner's thread: look again next round
         return true;
     const uint32_t entry = head_contact( S, acc, G, WB, me, pc, deg );
     if ( !( entry & INC_LO_FLAG ) )   // the pair's j waits for the pair's i to execute it
@@ -983,7 +1015,7 @@ __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const Glo
     const uint32_t wq   = __ldcg( &WB.state[ q ] );
     const uint32_t pcq  = wq & PC_MASK;
     const uint32_t degq = WB.deg[ q ];
-    if ( ( wq >> PC_BITS ) == r || pcq >= degq || head_contact( S, acc, G, WB, q, pcq, degq ) != me )
+    if ( st_round( wq ) == r || pcq >= degq || head_contact( S, acc, G, WB, q, pcq, degq ) != me )
         return true;   // the partner still has earlier pairs to resolve
     const Self a = load_self( S, me ), b = load_self( S, q );   // frozen geometry (pass 1, :84-127)
     float2    *va = reinterpret_cast<float2 *>( pv_out + me ) + 1;
@@ -999,8 +1031,11 @@ __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const Glo
         *va  = ua;
         *vb  = ub;
     }
-    WB.state[ me ] = ( r << PC_BITS ) | ( pc + 1 );
-    WB.state[ q ]  = ( r << PC_BITS ) | ( pcq + 1 );
+    const uint32_t taint = ( w | wq ) & ST_TAINT;
+    if ( taint )
+        report_taint( S, G, WB, me, w, q, wq );
+    WB.state[ me ] = taint | ( r << PC_BITS ) | ( pc + 1 );
+    WB.state[ q ]  = taint | ( r << PC_BITS ) | ( pcq + 1 );
     return pc + 1 < deg;
 }
 
@@ -1030,7 +1065,7 @@ __global__ void __launch_bounds__( WAVE_THREADS ) k_resolve_wavefront( const Par
     for ( uint32_t r = 1;; r++ ) {
         if ( r > 1 && counters[ ( r - 1 ) % 3 ] == 0 )   // nobody has contacts left
             break;
-        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {     // round stamp would overflow: flag and stop
+        if ( r >= ST_ROUND_LIMIT ) {     // round stamp would overflow: flag and stop
             if ( blockIdx.x == 0 && threadIdx.x == 0 )
                 atomicOr( &WB.counters[ 3 ], 2u );
             break;
@@ -1111,7 +1146,7 @@ __global__ void __launch_bounds__( 256 ) k_wave_pack( const ParticleSet S, const
     if ( d == 0 )
         return;
     WaveRec w;
-    w.state = 0;
+    w.state = WB.state[ k ] & ST_TAINT;
     w.deg   = d;
 #pragma unroll
     for ( int c = 0; c < WREC_INLINE; c++ )
@@ -1169,7 +1204,7 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
         const uint32_t n_q = r == 1 ? 0u : counters[ ( r - 1 ) % 3 ];
         if ( r > 1 && n_q == 0 )
             break;
-        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {
+        if ( r >= ST_ROUND_LIMIT ) {
             if ( blockIdx.x == 0 && threadIdx.x == 0 )
                 atomicOr( &WB.counters[ 3 ], 2u );
             break;
@@ -1189,16 +1224,16 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                 if ( r > 1 || WB.deg[ p ] != 0 ) {
                     const WaveRec  A   = load_wave_rec( R.wr + p );
                     const uint32_t pcA = A.state & PC_MASK;
-                    if ( pcA < A.deg && ( A.state >> PC_BITS ) != r ) {
+                    if ( pcA < A.deg && st_round( A.state ) != r ) {
                         const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
                         const WaveRec  B = load_wave_rec( R.wr + o );
                         const uint32_t pcB = B.state & PC_MASK;
-                        if ( pcB < B.deg && ( B.state >> PC_BITS ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) {
+                        if ( pcB < B.deg && st_round( B.state ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) {
                             const bool     p_lo = ( e & INC_LO_FLAG ) != 0;
                             const uint32_t lo = p_lo ? p : o, hi = p_lo ? o : p;
                             const uint32_t st_lo = p_lo ? A.state : B.state, st_hi = p_lo ? B.state : A.state;
                             const uint32_t deg_lo = p_lo ? A.deg : B.deg, deg_hi = p_lo ? B.deg : A.deg;
-                            const uint32_t claim = ( r << PC_BITS ) | ( st_lo & PC_MASK );
+                            const uint32_t claim = ( st_lo & ST_TAINT ) | ( r << PC_BITS ) | ( st_lo & PC_MASK );
                             if ( atomicCAS( &R.wr[ lo ].state, st_lo, claim ) == st_lo ) {   // this thread fires the pair
                                 const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
                                 const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
@@ -1214,8 +1249,11 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                 }
                                 // the pair's j is done for this round
                                 const uint32_t nhi = ( st_hi & PC_MASK ) + 1;
+                                uint32_t       taint = ( st_lo | st_hi ) & ST_TAINT;   // of the chain's particle from here on
+                                if ( taint )
+                                    report_taint( S, G, WB, lo, st_lo, hi, st_hi );
                                 *vb                = ub;
-                                R.wr[ hi ].state   = ( r << PC_BITS ) | nhi;
+                                R.wr[ hi ].state   = taint | ( r << PC_BITS ) | nhi;
                                 if ( nhi < deg_hi )
                                     buf[ atomicAdd( &buf_n, 1u ) ] = hi;
                                 else
@@ -1234,9 +1272,9 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                     const uint32_t e2 = rec_head( S, acc, G, WB, C, cur, cpc ), x = e2 & ~INC_LO_FLAG;
                                     const WaveRec  X   = load_wave_rec( R.wr + x );
                                     const uint32_t pcx = X.state & PC_MASK;
-                                    if ( ( X.state >> PC_BITS ) == r || pcx >= X.deg || ( rec_head( S, acc, G, WB, X, x, pcx ) & ~INC_LO_FLAG ) != cur )
+                                    if ( st_round( X.state ) == r || pcx >= X.deg || ( rec_head( S, acc, G, WB, X, x, pcx ) & ~INC_LO_FLAG ) != cur )
                                         break;
-                                    if ( atomicCAS( &R.wr[ x ].state, X.state, ( r << PC_BITS ) | pcx ) != X.state )
+                                    if ( atomicCAS( &R.wr[ x ].state, X.state, ( X.state & ST_TAINT ) | ( r << PC_BITS ) | pcx ) != X.state )
                                         break;
                                     const float4 gx = __ldcg( reinterpret_cast<const float4 *>( R.dr + x ) );
                                     float2      *vx = reinterpret_cast<float2 *>( R.dr + x ) + 2;
@@ -1261,15 +1299,19 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                         }
                                     }
                                     cpc++;
+                                    if ( ( taint | X.state ) & ST_TAINT ) {
+                                        report_taint( S, G, WB, cur, taint, x, X.state );
+                                        taint = ST_TAINT;
+                                    }
                                     *vx              = ux;
-                                    R.wr[ x ].state = ( r << PC_BITS ) | ( pcx + 1 );
+                                    R.wr[ x ].state = taint | ( r << PC_BITS ) | ( pcx + 1 );
                                     if ( pcx + 1 < X.deg )
                                         buf[ atomicAdd( &buf_n, 1u ) ] = x;
                                     else
                                         *( reinterpret_cast<float2 *>( pv_out + x ) + 1 ) = ux;
                                 }
                                 *va              = uc;
-                                R.wr[ cur ].state = ( r << PC_BITS ) | cpc;
+                                R.wr[ cur ].state = taint | ( r << PC_BITS ) | cpc;
                                 if ( cpc < cdeg )
                                     buf[ atomicAdd( &buf_n, 1u ) ] = cur;
                                 else
@@ -1294,189 +1336,6 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                 __syncthreads();
             }
         }
-        if ( threadIdx.x == 0 && blockIdx.x == 0 )
-            WB.counters[ 4 ] = r;
-        grid.sync();
-    }
-}
-
-// ---- K7b, event-driven global rounds on a BITMAP of particles to examine (default for dense contact sets) --------------
-// Same records, same firing rule, same claim by compare-and-swap and the same chain following as k_resolve_events; what
-// changes is how the work of a round is handed out.  The queue version pays two CTA barriers per item and thread (its
-// pushes are staged in shared memory), so every thread of a CTA waits for the slowest chain of dependent loads of that
-// iteration, and the queue order scatters neighbouring particles over the whole grid.  Here "examine p next round" is one
-// fire-and-forget atomicOr into a bitmap (one bit per storage slot, 2 MB for 16M particles: it lives in L2), and a round is
-// a sweep over that bitmap: every warp owns a fixed, contiguous range of slots, so
-//   * there is no barrier and no shared counter inside a round -- a warp's lanes wait only for their own loads;
-//   * lanes of a warp examine neighbouring slots, whose records and partners share cache lines (storage is cell-sorted).
-// Termination: each warp adds its number of pushes to the round's counter (one atomic per warp and round).
-struct WaveBitmaps {
-    uint32_t *bits[ 2 ];   // [round parity][slot / 32]; the reader zeroes what it read, so the map is clean when it becomes "next"
-    uint32_t  words;
-};
-
-// first round's map: every particle with contacts (also writes the zero words)
-__global__ void __launch_bounds__( 256 ) k_wave_bitmap_init( const WaveBuffers WB, const WaveBitmaps M, const size_t n ) {
-    const size_t   k   = (size_t)blockIdx.x * 256 + threadIdx.x;
-    const unsigned any = __ballot_sync( 0xffffffffu, k < n && WB.deg[ k ] != 0 );
-    if ( ( threadIdx.x & 31u ) == 0 && ( k >> 5 ) < M.words )
-        M.bits[ 1 ][ k >> 5 ] = any;   // round 1 reads parity 1 ... see k_resolve_bitmap
-}
-
-__global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_bitmap( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
-                                                                  const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
-                                                                  const WaveRecs R, const WaveBitmaps M ) {
-    namespace cg        = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
-    volatile uint32_t   *counters = WB.counters;
-    const unsigned       lane = threadIdx.x & 31u;
-    const uint32_t       warp_g = ( blockIdx.x * EV_THREADS + threadIdx.x ) >> 5, nwarps = ( gridDim.x * EV_THREADS ) >> 5;
-    // contiguous word range of this warp, a multiple of 32 words (one word per lane and sweep step)
-    const uint32_t per_warp = ( ( ( M.words + nwarps - 1 ) / nwarps ) + 31u ) & ~31u;
-    const uint32_t w_begin = warp_g * per_warp, w_end = min( w_begin + per_warp, M.words );
-
-    for ( uint32_t r = 1;; r++ ) {
-        if ( r > 1 && counters[ ( r - 1 ) % 3 ] == 0 )
-            break;
-        if ( r >= ( 1u << ( 32 - PC_BITS ) ) - 1u ) {
-            if ( blockIdx.x == 0 && threadIdx.x == 0 )
-                atomicOr( &WB.counters[ 3 ], 2u );
-            break;
-        }
-        if ( blockIdx.x == 0 && threadIdx.x == 0 )
-            counters[ ( r + 1 ) % 3 ] = 0;
-        uint32_t *cur = M.bits[ r & 1 ], *nxt = M.bits[ ( r & 1 ) ^ 1 ];
-        uint32_t  pushed = 0;
-        auto push = [ & ]( const uint32_t q ) {
-            atomicOr( &nxt[ q >> 5 ], 1u << ( q & 31u ) );
-            pushed++;
-        };
-
-        for ( uint32_t w0 = w_begin; w0 < w_end; w0 += 32 ) {
-            const uint32_t wi   = w0 + lane;
-            uint32_t       word = 0;
-            if ( wi < w_end ) {
-                word = __ldcg( &cur[ wi ] );
-                if ( word )
-                    cur[ wi ] = 0;
-            }
-            // distribute the set bits of these 32 words over the lanes, 32 at a time
-            uint32_t cnt = (uint32_t)__popc( word ), incl = cnt;
-#pragma unroll
-            for ( int d = 1; d < 32; d <<= 1 ) {
-                const uint32_t o = __shfl_up_sync( 0xffffffffu, incl, d );
-                if ( lane >= (unsigned)d )
-                    incl += o;
-            }
-            const uint32_t total = __shfl_sync( 0xffffffffu, incl, 31 );
-            for ( uint32_t t0 = 0; t0 < total; t0 += 32 ) {
-                const uint32_t t = t0 + lane;
-                // owner lane L of item t: the first lane whose inclusive prefix exceeds t
-                uint32_t lo_l = 0, hi_l = 31;
-#pragma unroll
-                for ( int it = 0; it < 5; it++ ) {
-                    const uint32_t mid = ( lo_l + hi_l ) >> 1;
-                    const uint32_t pm  = __shfl_sync( 0xffffffffu, incl, mid );
-                    if ( pm > t )
-                        hi_l = mid;
-                    else
-                        lo_l = mid + 1;
-                }
-                const uint32_t L     = lo_l;
-                const uint32_t wordL = __shfl_sync( 0xffffffffu, word, L );
-                const uint32_t inclL = __shfl_sync( 0xffffffffu, incl, L ), cntL = __shfl_sync( 0xffffffffu, cnt, L );
-                if ( t >= total )
-                    continue;
-                const uint32_t kth = t - ( inclL - cntL );                    // 0-based rank of the bit inside its word
-                const uint32_t p   = ( ( w0 + L ) << 5 ) + (uint32_t)__fns( wordL, 0, (int)kth + 1 );
-
-                const WaveRec  A   = load_wave_rec( R.wr + p );
-                const uint32_t pcA = A.state & PC_MASK;
-                if ( !( pcA < A.deg && ( A.state >> PC_BITS ) != r ) )
-                    continue;
-                const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
-                const WaveRec  B = load_wave_rec( R.wr + o );
-                const uint32_t pcB = B.state & PC_MASK;
-                if ( !( pcB < B.deg && ( B.state >> PC_BITS ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) )
-                    continue;
-                const bool     p_lo = ( e & INC_LO_FLAG ) != 0;
-                const uint32_t lo = p_lo ? p : o, hi = p_lo ? o : p;
-                const uint32_t st_lo = p_lo ? A.state : B.state, st_hi = p_lo ? B.state : A.state;
-                const uint32_t deg_lo = p_lo ? A.deg : B.deg, deg_hi = p_lo ? B.deg : A.deg;
-                const uint32_t claim = ( r << PC_BITS ) | ( st_lo & PC_MASK );
-                if ( atomicCAS( &R.wr[ lo ].state, st_lo, claim ) != st_lo )
-                    continue;   // the thread examining the other end fires this pair
-                const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
-                const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
-                float2      *va = reinterpret_cast<float2 *>( R.dr + lo ) + 2, *vb = reinterpret_cast<float2 *>( R.dr + hi ) + 2;
-                float2       ua = __ldcg( va ), ub = __ldcg( vb );
-                const ImpulseTerms T = impulse_terms( contact_geom( ga.x, ga.y, ga.z, gb.x, gb.y, gb.z, dt ), ga.w, gb.w, ua.x, ua.y, ub.x, ub.y );
-                if ( T.impulse ) {
-                    ua.x = __fadd_rn( ua.x, T.dvx_lo );
-                    ua.y = __fadd_rn( ua.y, T.dvy_lo );
-                    ub.x = __fsub_rn( ub.x, T.dvx_hi );
-                    ub.y = __fsub_rn( ub.y, T.dvy_hi );
-                }
-                const uint32_t nhi = ( st_hi & PC_MASK ) + 1;   // the pair's j is done for this round
-                *vb                = ub;
-                R.wr[ hi ].state   = ( r << PC_BITS ) | nhi;
-                if ( nhi < deg_hi )
-                    push( hi );
-                else
-                    *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;   // last contact done: final velocity
-
-                // follow the chain from the pair's i (see k_resolve_events)
-                const WaveRec &C   = p_lo ? A : B;
-                const uint32_t cur_p = lo, cdeg = deg_lo;
-                uint32_t       cpc = ( st_lo & PC_MASK ) + 1;
-                float2         uc  = ua;
-                for ( int follow = 0; follow < EV_FOLLOW && cpc < cdeg; follow++ ) {
-                    const uint32_t e2 = rec_head( S, acc, G, WB, C, cur_p, cpc ), x = e2 & ~INC_LO_FLAG;
-                    const WaveRec  X   = load_wave_rec( R.wr + x );
-                    const uint32_t pcx = X.state & PC_MASK;
-                    if ( ( X.state >> PC_BITS ) == r || pcx >= X.deg || ( rec_head( S, acc, G, WB, X, x, pcx ) & ~INC_LO_FLAG ) != cur_p )
-                        break;
-                    if ( atomicCAS( &R.wr[ x ].state, X.state, ( r << PC_BITS ) | pcx ) != X.state )
-                        break;
-                    const float4 gx = __ldcg( reinterpret_cast<const float4 *>( R.dr + x ) );
-                    float2      *vx = reinterpret_cast<float2 *>( R.dr + x ) + 2;
-                    float2       ux = __ldcg( vx );
-                    const bool   c_lo = ( e2 & INC_LO_FLAG ) != 0;   // cur is this pair's i
-                    const ImpulseTerms F = impulse_terms( contact_geom( c_lo ? ga.x : gx.x, c_lo ? ga.y : gx.y, c_lo ? ga.z : gx.z, c_lo ? gx.x : ga.x,
-                                                                         c_lo ? gx.y : ga.y, c_lo ? gx.z : ga.z, dt ),
-                                                           c_lo ? ga.w : gx.w, c_lo ? gx.w : ga.w, c_lo ? uc.x : ux.x, c_lo ? uc.y : ux.y,
-                                                           c_lo ? ux.x : uc.x, c_lo ? ux.y : uc.y );
-                    if ( F.impulse ) {
-                        if ( c_lo ) {
-                            uc.x = __fadd_rn( uc.x, F.dvx_lo ), uc.y = __fadd_rn( uc.y, F.dvy_lo );
-                            ux.x = __fsub_rn( ux.x, F.dvx_hi ), ux.y = __fsub_rn( ux.y, F.dvy_hi );
-                        } else {
-                            ux.x = __fadd_rn( ux.x, F.dvx_lo ), ux.y = __fadd_rn( ux.y, F.dvy_lo );
-                            uc.x = __fsub_rn( uc.x, F.dvx_hi ), uc.y = __fsub_rn( uc.y, F.dvy_hi );
-                        }
-                    }
-                    cpc++;
-                    *vx              = ux;
-                    R.wr[ x ].state = ( r << PC_BITS ) | ( pcx + 1 );
-                    if ( pcx + 1 < X.deg )
-                        push( x );
-                    else
-                        *( reinterpret_cast<float2 *>( pv_out + x ) + 1 ) = ux;
-                }
-                *va                 = uc;
-                R.wr[ cur_p ].state = ( r << PC_BITS ) | cpc;
-                if ( cpc < cdeg )
-                    push( cur_p );
-                else
-                    *( reinterpret_cast<float2 *>( pv_out + cur_p ) + 1 ) = uc;
-            }
-        }
-#pragma unroll
-        for ( int d = 16; d > 0; d >>= 1 )
-            pushed += __shfl_xor_sync( 0xffffffffu, pushed, d );
-        if ( lane == 0 && pushed )
-            atomicAdd( &WB.counters[ r % 3 ], pushed );
         if ( threadIdx.x == 0 && blockIdx.x == 0 )
             WB.counters[ 4 ] = r;
         grid.sync();

@@ -50,6 +50,7 @@ struct GridDims {
     int      cols, rows;
     uint32_t cells;
     int      row0;   // grid row of the whole field that row 0 of this grid is (slab windows; 0 for a whole-field grid)
+    int      taint_lo, taint_hi;   // slab windows: rows whose particles miss contacts beyond the window (-1: none)
 };
 
 }   // namespace ppc

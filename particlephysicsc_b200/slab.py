@@ -69,9 +69,11 @@ def owner_of_rows(cy: np.ndarray, ranges) -> np.ndarray:
     return np.searchsorted(ends, cy, side="right")
 
 
-def required_halo(rounds: int, hops_per_round: int = 2) -> int:
-    """Ghost rows that make owned velocities exact for a resolve of `rounds` dependency rounds (csrc/ppc_slab.cuh)."""
-    return rounds * hops_per_round + 1
+def required_halo(taint_rows: int, margin: int = 2) -> int:
+    """Ghost rows for a field whose inexactness mark travelled `taint_rows` rows into the window (ppc_slab_info): the mark
+    starts in the window's outermost row and must stop short of the first owned row; `margin` rows absorb its fluctuation
+    from substep to substep (too thin a halo is always reported, never silent)."""
+    return int(taint_rows) + 1 + margin
 
 
 class HaloTooShallow(RuntimeError):
@@ -132,7 +134,8 @@ class DeviceSlab:
         c = (C.c_uint64 * 2)()
         rc = self.p.lib.ppc_slab_begin(C.byref(self.p.s), dt, int(colour), c)
         if rc == -2:
-            raise HaloTooShallow(f"halo of {self.halo} rows is too shallow for the last substep's dependency depth ({self.info().rounds} rounds)")
+            raise HaloTooShallow(f"halo of {self.halo} rows is too thin: the last resolve's inexactness mark travelled {self.info().taint_rows} rows "
+                                 "and reached an owned particle")
         if rc != 0:
             raise RuntimeError(f"ppc_slab_begin failed ({rc})")
         self.counts = (int(c[0]), int(c[1]))
@@ -172,7 +175,7 @@ class DeviceSlab:
             self.host_ids = np.zeros(self.p.size, np.uint32)
         rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), self.host_ids.ctypes.data_as(api.u32p), 0)
         if rc == -2:
-            raise HaloTooShallow(f"halo of {self.halo} rows is too shallow ({self.info().rounds} dependency rounds)")
+            raise HaloTooShallow(f"halo of {self.halo} rows is too thin (the inexactness mark travelled {self.info().taint_rows} rows)")
         if rc != 0:
             raise RuntimeError(f"ppc_slab_download failed ({rc})")
         return self.p.length
@@ -248,17 +251,35 @@ class DistTransport:
         self._run(ops)
 
 
-def slab_step(rank, transport: DistTransport, dt: float, colour: bool = False) -> int:
-    """One substep of one rank of a distributed job.  Device work and NCCL traffic are ordered on the store's stream."""
+def slab_step(rank, transport: DistTransport, dt: float, colour: bool = False, timers: dict | None = None) -> int:
+    """One substep of one rank of a distributed job.  Device work and NCCL traffic are ordered on the store's stream.
+    With `timers` (diagnostics only) every phase is followed by a device synchronise and its wall time accumulated."""
+    import time
     ctx = rank.torch.cuda.stream(rank.stream) if getattr(rank, "stream", None) is not None else _null()
+
+    def lap(name, t0):
+        if timers is None:
+            return t0
+        rank.torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        timers[name] = timers.get(name, 0.0) + (t1 - t0) * 1e3
+        return t1
+
     with ctx:
+        t = time.perf_counter()
         n_lo, n_hi = rank.begin(dt, colour)
+        t = lap("begin (integrate, walls, count)", t)
         s_lo, s_hi = rank.buffer("send_lo", n_lo), rank.buffer("send_hi", n_hi)
         rank.pack(s_lo, s_hi)
+        t = lap("pack", t)
         r_lo, r_hi = transport.exchange_counts(n_lo, n_hi)
+        t = lap("exchange counts", t)
         b_lo, b_hi = rank.buffer("recv_lo", r_lo), rank.buffer("recv_hi", r_hi)
         transport.exchange(s_lo[:n_lo], s_hi[:n_hi], b_lo[:r_lo], b_hi[:r_hi])
-        return rank.finish(dt, b_lo, r_lo, b_hi, r_hi)
+        t = lap("exchange records", t)
+        n = rank.finish(dt, b_lo, r_lo, b_hi, r_hi)
+        lap("finish (grid, narrow phase, resolve)", t)
+        return n
 
 
 def local_step(ranks, dt: float, colour: bool = False):

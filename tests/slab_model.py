@@ -29,6 +29,16 @@ def dependency_depth(pairs: np.ndarray) -> int:
     return depth
 
 
+def taint_travel(pairs: np.ndarray, tainted: np.ndarray):
+    """The product's exactness criterion (csrc/ppc_collide.cuh, ST_TAINT): particles of the window's outermost rows start
+    out marked; a pair with a marked end marks both ends, in the reference's pair order.  Returns the final marks."""
+    t = tainted.copy()
+    for i, j in pairs.tolist():
+        if t[i] or t[j]:
+            t[i] = t[j] = True
+    return t
+
+
 class ModelSlab:
     torch = torch
     stream = None
@@ -115,6 +125,11 @@ class ModelSlab:
         self.rounds = dependency_depth(pairs)
         gids = r["gid"]
         owned = (cy >= self.own[0]) & (cy < self.own[1])
+        edge = ((cy == row_lo) & (row_lo > 0)) | ((cy == row_hi - 1) & (row_hi < self.rows))
+        marked = taint_travel(pairs, edge)
+        self.taint_reached_owned = bool((marked & owned).any())
+        depth = np.minimum(np.where(row_lo > 0, cy - row_lo, 1 << 30), np.where(row_hi < self.rows, row_hi - 1 - cy, 1 << 30))
+        self.taint_rows = int(depth[marked].max()) if marked.any() else 0
         self.last_pairs = np.stack([gids[pairs[:, 0]], gids[pairs[:, 1]]], 1)[owned[pairs[:, 0]]] if len(pairs) else np.zeros((0, 2), np.uint32)
         self.last_keys = dict(gid=gids[owned], key=grid["keys"][owned])
         self.o.resolve(u, pairs, dt)
