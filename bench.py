@@ -362,6 +362,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         travelled, rounds = group_max(travelled), group_max(rounds)
         halo = slab.required_halo(travelled, args.halo_margin)
         me.reinit(halo)
+        if tr is not None:
+            tr.reset()
         return halo, rounds, travelled
 
     def timed(me, tr, steps):

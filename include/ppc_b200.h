@@ -168,9 +168,12 @@ int ppc_grid_dims( uint16_t window_width, uint16_t window_height, float max_radi
 int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids, uint16_t window_width, uint16_t window_height, float max_radius,
                    int own_row_begin, int own_row_end, int halo_rows );
 int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] /* to lower / upper rows */ );
-int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device buffers of send_counts records */ );
+/* with_header: messages of a fixed, agreed size -- record 0 of each buffer holds the number of records that follow, so the
+ * receiver needs no count in advance (ppc_slab_finish then takes the buffers' CAPACITIES and reports the counts received) */
+int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device buffers of send_counts (+1) records */, int with_header );
 /* returns the number of owned particles after the substep */
-int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi );
+int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi,
+                         int with_header, uint64_t received[ 2 ] /* may be NULL */ );
 /* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index), ids alongside;
  * p_x, p_y, v_x, v_y, colors always, mass and radius too when with_mass_radius (they only change owner, never value) */
 int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, int with_mass_radius );

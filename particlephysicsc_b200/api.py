@@ -116,8 +116,8 @@ def load_library() -> C.CDLL:
     L.ppc_slab_init.argtypes = [PP, u32p, C.c_uint16, C.c_uint16, C.c_float, C.c_int, C.c_int, C.c_int]
     L.ppc_slab_init.restype = C.c_int
     L.ppc_slab_begin.argtypes, L.ppc_slab_begin.restype = [PP, C.c_float, C.c_int, C.POINTER(C.c_uint64)], C.c_int
-    L.ppc_slab_pack.argtypes, L.ppc_slab_pack.restype = [PP, C.c_void_p, C.c_void_p], C.c_int
-    L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.ppc_slab_pack.argtypes, L.ppc_slab_pack.restype = [PP, C.c_void_p, C.c_void_p, C.c_int], C.c_int
+    L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.ppc_slab_finish.restype = C.c_int64
     L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p, C.c_int], C.c_int
     L.ppc_slab_info.argtypes, L.ppc_slab_info.restype = [PP, C.POINTER(SlabInfo)], C.c_int

@@ -1023,14 +1023,21 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
 // Did the last resolve keep the owned particles exact?  The resolve marks every particle whose result may differ from the
 // whole-field run (ST_TAINT, csrc/ppc_collide.cuh) and reports when the mark reaches an owned particle.  Stream must be idle.
 static int slab_halo_ok( Store *st ) {
-    if ( st->opt_resolve != 1 || !st->wave.counters || !( st->slab_rows.has_lo || st->slab_rows.has_hi ) )
+    if ( !st->wave.counters )
+        return 1;
+    uint32_t w[ 12 ];   // one read: error flags [3], taint reached an owned particle [10], rows it travelled [11]
+    PPC_CK( cudaMemcpy( w, st->wave.counters, sizeof( w ), cudaMemcpyDeviceToHost ) );
+    if ( w[ 3 ] ) {
+        fprintf( stderr, "particlephysicsc_b200: resolve failed (%s%s)\n", ( w[ 3 ] & 1u ) ? "a particle has more than 4095 simultaneous contacts " : "",
+                 ( w[ 3 ] & 2u ) ? "pair dependency chain too long" : "" );
+        abort();
+    }
+    if ( st->opt_resolve != 1 || !( st->slab_rows.has_lo || st->slab_rows.has_hi ) )
         return 1;
     if ( st->wave_hops == 0 )
         return 0;   // shared-memory tile passes do not carry the mark
-    uint32_t w[ 2 ] = { 0, 0 };
-    PPC_CK( cudaMemcpy( w, st->wave.counters + 10, sizeof( w ), cudaMemcpyDeviceToHost ) );
-    st->slab_taint_rows = w[ 1 ];
-    return w[ 0 ] == 0u ? 1 : 0;
+    st->slab_taint_rows = w[ 11 ];
+    return w[ 10 ] == 0u ? 1 : 0;
 }
 
 extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] ) {
@@ -1038,7 +1045,6 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     if ( !st->slab )
         return -1;
     PPC_CK( cudaStreamSynchronize( st->stream ) );
-    check_device_flags( st );
     if ( st->grid_valid && !slab_halo_ok( st ) )
         return -2;   // the previous substep's dependency depth exceeded what the halo guarantees: results may be inexact
     const size_t n = st->n_own;
@@ -1069,20 +1075,28 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     return 0;
 }
 
-extern "C" int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi ) {
+extern "C" int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi, int with_header ) {
     Store *st = store_of( p );
     if ( !st->slab )
         return -1;
     const size_t n = st->n_own;
-    if ( n && ( st->h_slab[ 0 ] || st->h_slab[ 1 ] ) ) {
-        StageTimer T( st, ST_SLAB );
-        PPC_LAUNCH( k_slab_pack, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, offset_view( st->set[ st->cur ], st->own_first ), n,
-                    st->slab_rows, (SlabRec *)send_lo, (SlabRec *)send_hi, st->slab_counts + 4 );
+    StageTimer   T( st, ST_SLAB );
+    SlabRec     *lo = (SlabRec *)send_lo, *hi = (SlabRec *)send_hi;
+    if ( with_header ) {   // fixed-size messages: record 0 carries the number of records that follow
+        if ( st->slab_rows.has_lo )
+            PPC_CK( cudaMemcpyAsync( lo, st->h_slab + 0, sizeof( uint32_t ), cudaMemcpyHostToDevice, st->stream ) );
+        if ( st->slab_rows.has_hi )
+            PPC_CK( cudaMemcpyAsync( hi, st->h_slab + 1, sizeof( uint32_t ), cudaMemcpyHostToDevice, st->stream ) );
+        lo += 1, hi += 1;
     }
+    if ( n && ( st->h_slab[ 0 ] || st->h_slab[ 1 ] ) )
+        PPC_LAUNCH( k_slab_pack, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, offset_view( st->set[ st->cur ], st->own_first ), n,
+                    st->slab_rows, lo, hi, st->slab_counts + 4 );
     return 0;
 }
 
-extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi ) {
+extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi,
+                                    int with_header, uint64_t received[ 2 ] ) {
     Store *st = store_of( p );
     if ( !st->slab )
         return -1;
@@ -1107,9 +1121,16 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     {
         StageTimer T( st, ST_SLAB );
         if ( n_lo )
-            PPC_LAUNCH( k_slab_append, div_up( n_lo, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own, (const SlabRec *)recv_lo, (size_t)n_lo, GW );
+            PPC_LAUNCH( k_slab_append, div_up( n_lo, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own, (const SlabRec *)recv_lo, (size_t)n_lo, GW,
+                        with_header );
         if ( n_hi )
-            PPC_LAUNCH( k_slab_append, div_up( n_hi, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own + n_lo, (const SlabRec *)recv_hi, (size_t)n_hi, GW );
+            PPC_LAUNCH( k_slab_append, div_up( n_hi, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->n_own + n_lo, (const SlabRec *)recv_hi, (size_t)n_hi, GW,
+                        with_header );
+        st->h_slab[ 3 ] = (uint32_t)n_lo, st->h_slab[ 7 ] = (uint32_t)n_hi;
+        if ( with_header && n_lo )
+            PPC_CK( cudaMemcpyAsync( st->h_slab + 3, recv_lo, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+        if ( with_header && n_hi )
+            PPC_CK( cudaMemcpyAsync( st->h_slab + 7, recv_hi, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
         PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
         if ( n_loc )
             PPC_LAUNCH( k_slab_localize, div_up( n_loc, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key, n_loc, G.cols, row_lo, row_hi, G.cells,
@@ -1128,6 +1149,8 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     PPC_CK( cudaMemcpyAsync( st->h_slab + 6, st->cell_start + G.cells, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaStreamSynchronize( st->stream ) );
     const size_t n_work = st->h_slab[ 6 ];
+    if ( received )
+        received[ 0 ] = st->h_slab[ 3 ], received[ 1 ] = st->h_slab[ 7 ];
     st->own_first  = st->h_slab[ 4 ];
     st->n_own      = st->h_slab[ 5 ] - st->h_slab[ 4 ];
     st->n          = n_work;

@@ -14,8 +14,9 @@
 // (cellSize = 2 maxRadius, :241-244).  Position pushes are sums of terms frozen before anything moves (:84-156): one row.
 // Velocities follow the reference's sequential pair order; an error made at the outer edge of the halo (whose particles
 // miss their outward contacts) can travel one contact, i.e. at most one cell row, per level of the pair dependency graph.
-// With `halo` >= rounds + 2 (rounds = depth of the local dependency graph, measured every substep) it cannot reach an
-// owned row, so owned velocities are bit-identical to the single-GPU run; the host checks that bound every substep.
+// The resolve therefore marks those particles, and every particle that resolves a pair with a marked one (ST_TAINT in
+// ppc_collide.cuh); while no owned particle gets marked, owned velocities are bit-identical to the single-GPU run.  The
+// host checks that every substep, and sizes the halo from how far the mark was seen to travel (1-5 rows in practice).
 #pragma once
 #include "ppc_collide.cuh"
 #include "ppc_common.cuh"
@@ -101,14 +102,25 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_pack( const ParticleS
     }
 }
 
-// received records -> storage slots [first, first + count), with their global cell key (:280-291, same float operations as K1)
+// received records -> storage slots [first, first + capacity), with their global cell key (:280-291, same float operations
+// as K1).  With a header (fixed-size messages: record 0 holds the number of records that follow) the slots past that number
+// get a key beyond every window, which the sort puts into the drop bin.
 __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_append( const ParticleSet S, const size_t first, const SlabRec *__restrict__ recv,
-                                                                   const size_t count, const GridDims G ) {
+                                                                   const size_t capacity, const GridDims G, const int with_header ) {
     const size_t t = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
-    if ( t >= count )
+    if ( t >= capacity )
         return;
+    const size_t k = first + t;
+    if ( with_header ) {
+        const uint32_t count = *reinterpret_cast<const uint32_t *>( recv );
+        if ( t >= count ) {
+            S.key[ k ] = 0xffffffffu;
+            S.gid[ k ] = 0xffffffffu;
+            return;
+        }
+        recv += 1;
+    }
     const SlabRec r = recv[ t ];
-    const size_t  k = first + t;
     S.pv[ k ]  = r.pv;
     S.rm[ k ]  = make_float2( r.radius, r.mass );
     S.gid[ k ] = r.gid;

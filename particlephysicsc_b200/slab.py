@@ -101,6 +101,8 @@ class DeviceSlab:
         self.device = torch.device("cuda", device)
         self.bufs = {}
         self.counts = (0, 0)
+        self.received = (0, 0)
+        self.fixed_size_messages = True   # distributed steps: one message per neighbour, capacity agreed from the previous count
         self._init(np.ascontiguousarray(global_ids, dtype=np.uint32), halo)
         self.stream = torch.cuda.ExternalStream(self.p.stream(), device=self.device)
 
@@ -141,11 +143,15 @@ class DeviceSlab:
         self.counts = (int(c[0]), int(c[1]))
         return self.counts
 
-    def pack(self, buf_lo, buf_hi) -> None:
-        self.p.lib.ppc_slab_pack(C.byref(self.p.s), buf_lo.data_ptr(), buf_hi.data_ptr())
+    def pack(self, buf_lo, buf_hi, header: bool = False) -> None:
+        self.p.lib.ppc_slab_pack(C.byref(self.p.s), buf_lo.data_ptr(), buf_hi.data_ptr(), int(header))
 
-    def finish(self, dt: float, buf_lo, n_lo: int, buf_hi, n_hi: int) -> int:
-        return int(self.p.lib.ppc_slab_finish(C.byref(self.p.s), dt, buf_lo.data_ptr(), n_lo, buf_hi.data_ptr(), n_hi))
+    def finish(self, dt: float, buf_lo, n_lo: int, buf_hi, n_hi: int, header: bool = False) -> int:
+        """With header=True n_lo / n_hi are the capacities of fixed-size messages; self.received holds the counts they carried."""
+        got = (C.c_uint64 * 2)()
+        n = int(self.p.lib.ppc_slab_finish(C.byref(self.p.s), dt, buf_lo.data_ptr(), n_lo, buf_hi.data_ptr(), n_hi, int(header), got))
+        self.received = (int(got[0]), int(got[1]))
+        return n
 
     def synchronize(self) -> None:
         self.p.synchronize()
@@ -235,6 +241,29 @@ class DistTransport:
         r = got.tolist()
         return int(r[0]), int(r[1])
 
+    # fixed-size messages: both ends derive the capacity of the next message from the count of the last one, so no count
+    # has to cross before the records do (one send/recv per neighbour and substep instead of two)
+    @staticmethod
+    def next_capacity(count: int) -> int:
+        return ((count + count // 16 + 4096 + 1023) // 1024) * 1024
+
+    def negotiate(self, n_lo: int, n_hi: int) -> None:
+        """Once, before the first fixed-size exchange: tell the neighbours the current counts."""
+        r_lo, r_hi = self.exchange_counts(n_lo, n_hi)
+        self.cap_send = [self.next_capacity(n_lo) if self.lo is not None else 0, self.next_capacity(n_hi) if self.hi is not None else 0]
+        self.cap_recv = [self.next_capacity(r_lo) if self.lo is not None else 0, self.next_capacity(r_hi) if self.hi is not None else 0]
+
+    def reset(self) -> None:
+        """Forget the agreed capacities (the slabs were restarted with another halo): the next step negotiates again."""
+        for a in ("cap_send", "cap_recv"):
+            if hasattr(self, a):
+                delattr(self, a)
+
+    def advance(self, sent, received) -> None:
+        for k, nb in enumerate((self.lo, self.hi)):
+            if nb is not None:
+                self.cap_send[k], self.cap_recv[k] = self.next_capacity(sent[k]), self.next_capacity(received[k])
+
     def exchange(self, send_lo, send_hi, recv_lo, recv_hi):
         """send_* / recv_* are [count, 32] uint8 tensors (count may be 0: nothing is posted for it)."""
         d, ops = self.dist, []
@@ -269,15 +298,32 @@ def slab_step(rank, transport: DistTransport, dt: float, colour: bool = False, t
         t = time.perf_counter()
         n_lo, n_hi = rank.begin(dt, colour)
         t = lap("begin (integrate, walls, count)", t)
-        s_lo, s_hi = rank.buffer("send_lo", n_lo), rank.buffer("send_hi", n_hi)
-        rank.pack(s_lo, s_hi)
+        if not getattr(rank, "fixed_size_messages", False):   # counts first, then exactly that many records
+            s_lo, s_hi = rank.buffer("send_lo", n_lo), rank.buffer("send_hi", n_hi)
+            rank.pack(s_lo, s_hi)
+            t = lap("pack", t)
+            r_lo, r_hi = transport.exchange_counts(n_lo, n_hi)
+            t = lap("exchange counts", t)
+            b_lo, b_hi = rank.buffer("recv_lo", r_lo), rank.buffer("recv_hi", r_hi)
+            transport.exchange(s_lo[:n_lo], s_hi[:n_hi], b_lo[:r_lo], b_hi[:r_hi])
+            t = lap("exchange records", t)
+            n = rank.finish(dt, b_lo, r_lo, b_hi, r_hi)
+            lap("finish (grid, narrow phase, resolve)", t)
+            return n
+        if not hasattr(transport, "cap_send"):
+            transport.negotiate(n_lo, n_hi)
+        cs, cr = transport.cap_send, transport.cap_recv
+        if n_lo > cs[0] or n_hi > cs[1]:
+            raise RuntimeError(f"halo message grew from a capacity of {cs} to {(n_lo, n_hi)} records within one substep")
+        s_lo, s_hi = rank.buffer("send_lo", cs[0] + 1), rank.buffer("send_hi", cs[1] + 1)
+        rank.pack(s_lo, s_hi, header=True)
         t = lap("pack", t)
-        r_lo, r_hi = transport.exchange_counts(n_lo, n_hi)
-        t = lap("exchange counts", t)
-        b_lo, b_hi = rank.buffer("recv_lo", r_lo), rank.buffer("recv_hi", r_hi)
-        transport.exchange(s_lo[:n_lo], s_hi[:n_hi], b_lo[:r_lo], b_hi[:r_hi])
+        b_lo, b_hi = rank.buffer("recv_lo", cr[0] + 1), rank.buffer("recv_hi", cr[1] + 1)
+        transport.exchange(s_lo[:cs[0] + 1 if cs[0] else 0], s_hi[:cs[1] + 1 if cs[1] else 0], b_lo[:cr[0] + 1 if cr[0] else 0],
+                           b_hi[:cr[1] + 1 if cr[1] else 0])
         t = lap("exchange records", t)
-        n = rank.finish(dt, b_lo, r_lo, b_hi, r_hi)
+        n = rank.finish(dt, b_lo, cr[0], b_hi, cr[1], header=True)
+        transport.advance((n_lo, n_hi), rank.received)
         lap("finish (grid, narrow phase, resolve)", t)
         return n
 

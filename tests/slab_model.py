@@ -53,6 +53,7 @@ class ModelSlab:
         self.has_lo, self.has_hi = own_rows[0] > 0, own_rows[1] < self.rows
         self.s, self.gid = st, np.asarray(gid, np.uint32).copy()
         self.bufs, self.rounds, self.last_pairs = {}, 0, None
+        self.fixed_size_messages, self.received = False, (0, 0)
 
     # -- plumbing ------------------------------------------------------------------------------------------------
     def alloc(self, records):
@@ -98,16 +99,27 @@ class ModelSlab:
         r["gid"], r["rgba"] = self.gid[idx], s.rgba[idx]
         return r
 
-    def pack(self, buf_lo, buf_hi):
+    def pack(self, buf_lo, buf_hi, header=False):
         for buf, idx in ((buf_lo, self.to_lo), (buf_hi, self.to_hi)):
+            b = buf.numpy()
+            if header:   # record 0 = number of records that follow
+                b[0, :4] = np.array([len(idx)], "<u4").view(np.uint8)
+                b = b[1:]
             if len(idx):
-                buf.numpy()[:len(idx)] = self.records(idx).view(np.uint8).reshape(len(idx), slab.RECORD_BYTES)
+                b[:len(idx)] = self.records(idx).view(np.uint8).reshape(len(idx), slab.RECORD_BYTES)
 
-    def finish(self, dt, buf_lo, n_lo, buf_hi, n_hi):
+    def finish(self, dt, buf_lo, n_lo, buf_hi, n_hi, header=False):
         parts = [self.records(np.arange(self.s.n))]
+        got = []
         for buf, n in ((buf_lo, n_lo), (buf_hi, n_hi)):
+            b = buf.numpy()
+            if header and n:   # n is the capacity; the header says how many records are real
+                n = int(np.ascontiguousarray(b[0, :4]).view("<u4")[0])
+                b = b[1:]
+            got.append(n)
             if n:
-                parts.append(np.ascontiguousarray(buf.numpy()[:n]).view(REC).reshape(n))
+                parts.append(np.ascontiguousarray(b[:n]).view(REC).reshape(n))
+        self.received = tuple(got)
         r = np.concatenate(parts)
         r = r[np.argsort(r["gid"], kind="stable")]   # local index order = global index order: the pair order carries over
         assert len(np.unique(r["gid"])) == len(r), "a particle arrived twice"

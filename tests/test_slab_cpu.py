@@ -33,6 +33,13 @@ def test_partition_by_load_balances_particles():
     assert max(loads) <= 1.1 * counts.sum() / 4 + 1000
 
 
+def test_next_capacity_is_a_pure_function_of_the_last_count():
+    # both ends of a link compute it independently from the count the last message carried
+    f = slab.DistTransport.next_capacity
+    assert f(0) >= 4096 and f(1000000) >= 1000000 * 17 // 16 and f(12345) % 1024 == 0
+    assert all(f(n) >= n + 4096 for n in (0, 1, 5000, 10 ** 6, 10 ** 8))
+
+
 def test_cell_rows_follow_the_reference_division():
     py = np.array([0.0, 11.999999, 12.0, 35.9, 1e9, -5.0, np.nan], np.float32)
     assert slab.cell_rows(py, 12.0, 3).tolist() == [0, 0, 1, 2, 2, 0, 0]
@@ -129,7 +136,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, fixed):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -139,6 +146,7 @@ def _worker(rank, world, port, out):
     sc = scenes.jittered_lattice(12000, 2.0, 0.30, seed=304, vmax=600.0)
     ranks = model_slabs(Oracle(), sc, world, 12)
     me = ranks[rank]
+    me.fixed_size_messages = fixed
     tr = slab.DistTransport(dist, torch.device("cpu"))
     for _ in range(6):
         slab.slab_step(me, tr, DT)
@@ -147,10 +155,11 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_ranks_over_gloo_equal_whole_field(oracle):
+@pytest.mark.parametrize("fixed", [False, True], ids=["counts_then_records", "fixed_size_messages"])
+def test_two_ranks_over_gloo_equal_whole_field(oracle, fixed):
     ctx = mp.get_context("spawn")
     out, port = ctx.Queue(), _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out, fixed)) for r in range(2)]
     for p in procs:
         p.start()
     got = [out.get(timeout=300) for _ in procs]
