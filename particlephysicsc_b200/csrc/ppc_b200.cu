@@ -434,7 +434,7 @@ static ParticleSet offset_view( const ParticleSet &S, const size_t first ) {
     return ParticleSet{ S.pv + first, S.rm + first, S.gid + first, S.key + first, S.col + first };
 }
 
-static void grid_stage( Store *st, const size_t n, const size_t bins, const size_t first = 0 ) {
+static void grid_stage( Store *st, const size_t n, const size_t bins, const size_t first = 0, const uint32_t unranked_cell = 0xffffffffu ) {
     const ParticleSet  A = offset_view( st->set[ st->cur ], first );   // input: n slots starting at `first`
     const ParticleSet &B = st->set[ st->cur ^ 1 ];
     {
@@ -458,7 +458,7 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const size
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
         PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
-                    st->col_valid ? 1 : 0 );
+                    st->col_valid ? 1 : 0, unranked_cell );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
 }
@@ -1137,7 +1137,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
                         st->cell_count );
     }
     if ( n_loc )
-        grid_stage( st, n_loc, bins, st->own_first );
+        grid_stage( st, n_loc, bins, st->own_first, G.cells );
     else {
         PPC_CK( cudaMemsetAsync( st->cell_start, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
         st->cur ^= 1;

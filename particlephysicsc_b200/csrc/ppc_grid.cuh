@@ -105,7 +105,7 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
 __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const ParticleSet In, const ParticleSet Out,
                                                                         const uint32_t *__restrict__ slot_of,
                                                                         const uint32_t *__restrict__ cell_start, const size_t n,
-                                                                        const int move_colour ) {
+                                                                        const int move_colour, const uint32_t unranked_cell ) {
     const size_t pos = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( pos >= n )
         return;
@@ -114,8 +114,11 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
     const uint32_t g   = In.gid[ src ];
     const uint32_t b = cell_start[ c ], e = cell_start[ c + 1 ];
     uint32_t       rank = 0;
-    for ( uint32_t q = b; q < e; q++ )
-        rank += ( In.gid[ slot_of[ q ] ] < g ) ? 1u : 0u;
+    if ( c == unranked_cell )   // a slab window's drop bin: thousands of slots nobody reads, any order will do
+        rank = (uint32_t)pos - b;
+    else
+        for ( uint32_t q = b; q < e; q++ )
+            rank += ( In.gid[ slot_of[ q ] ] < g ) ? 1u : 0u;
     const uint32_t dst = b + rank;
     Out.pv[ dst ]  = In.pv[ src ];
     Out.rm[ dst ]  = In.rm[ src ];
