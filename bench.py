@@ -477,8 +477,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                     "n_gpus": 1, "value": ref_value, "unit": UNIT, "note": "the same per-GPU workload as one slab on one GPU, measured by "
                     "rank 0 in this job; parallel efficiency = value / (n_gpus x this)", "parallel_efficiency": value / (world * ref_value)},
                 "cpu_baseline": None,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 24.0 * n_down / SUBSTEPS_PER_FRAME,
-                        "note": "8 slab substeps, then the owned particles' p, v, colours and indices copied to the host arrays"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12.0 * n_down / SUBSTEPS_PER_FRAME,
+                        "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             _, _, line["cpu_baseline"] = time_reference_cpu("slab32m", 2, 1)

@@ -174,9 +174,10 @@ int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device
 /* returns the number of owned particles after the substep */
 int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi,
                          int with_header, uint64_t received[ 2 ] /* may be NULL */ );
-/* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index), ids alongside;
- * p_x, p_y, v_x, v_y, colors always, mass and radius too when with_mass_radius (they only change owner, never value) */
-int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, int with_mass_radius );
+/* owned particles -> host arrays [0, length) in storage order (ascending cell key, global index); mask = PPC_DL_* bits
+ * (a drawn frame needs PPC_DL_POS | PPC_DL_COLOR only; mass and radius change owner, never value) */
+enum { PPC_DL_IDS = 8, PPC_DL_MASS_RADIUS = 16 };
+int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, unsigned mask );
 
 typedef struct ppc_slab_info_t {
     uint64_t n_owned, own_first, n_window; /* owned particles = sorted slots [own_first, own_first + n_owned) of n_window */

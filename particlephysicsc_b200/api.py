@@ -27,6 +27,7 @@ i32p = C.POINTER(C.c_int32)
 
 PPC_SYNC_EVERY_CALL, PPC_SYNC_FRAME, PPC_SYNC_MANUAL = 0, 1, 2
 PPC_DL_POS, PPC_DL_VEL, PPC_DL_COLOR, PPC_DL_ALL = 1, 2, 4, 7
+PPC_DL_IDS, PPC_DL_MASS_RADIUS = 8, 16
 
 
 class Particles_t(C.Structure):
@@ -119,7 +120,7 @@ def load_library() -> C.CDLL:
     L.ppc_slab_pack.argtypes, L.ppc_slab_pack.restype = [PP, C.c_void_p, C.c_void_p, C.c_int], C.c_int
     L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.ppc_slab_finish.restype = C.c_int64
-    L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p, C.c_int], C.c_int
+    L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p, C.c_uint], C.c_int
     L.ppc_slab_info.argtypes, L.ppc_slab_info.restype = [PP, C.POINTER(SlabInfo)], C.c_int
     L.ppc_slab_debug_pairs.argtypes, L.ppc_slab_debug_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     _lib = L

@@ -1165,31 +1165,36 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     return (int64_t)st->n_own;
 }
 
-extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, int with_mass_radius ) {
+extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, unsigned mask ) {
     Store *st = store_of( p );
     if ( !st->slab )
         return -1;
     const size_t n = st->n_own;
     if ( n > p->size )
         return -3;
-    if ( n ) {
+    if ( n && mask ) {
         StageTimer T( st, ST_DOWNLOAD );
         PPC_LAUNCH( k_slab_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->own_first, n, st->api_f[ 0 ],
                     st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, st->sort_keys_a );
-        if ( with_mass_radius ) {
-            PPC_CK( cudaMemcpyAsync( p->mass, st->api_f[ 4 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->radius, st->api_f[ 5 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+        const size_t fb = n * sizeof( float );
+        if ( mask & PPC_DL_POS ) {
+            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
         }
-        PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-        PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-        PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-        PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-        PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
-        if ( global_ids )
+        if ( mask & PPC_DL_VEL ) {
+            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+        }
+        if ( mask & PPC_DL_MASS_RADIUS ) {
+            PPC_CK( cudaMemcpyAsync( p->mass, st->api_f[ 4 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->radius, st->api_f[ 5 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+        }
+        if ( mask & PPC_DL_COLOR )
+            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
+        if ( ( mask & PPC_DL_IDS ) && global_ids )
             PPC_CK( cudaMemcpyAsync( global_ids, st->sort_keys_a, n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     }
     PPC_CK( cudaStreamSynchronize( st->stream ) );
-    check_device_flags( st );
     p->length = n;
     return slab_halo_ok( st ) ? 0 : -2;
 }

@@ -165,7 +165,8 @@ class DeviceSlab:
         """Owned particles in storage order: dict of arrays plus their global indices."""
         n_max = self.p.size
         ids = np.zeros(n_max, np.uint32)
-        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), int(all_fields))
+        mask = api.PPC_DL_ALL | api.PPC_DL_IDS | (api.PPC_DL_MASS_RADIUS if all_fields else 0)
+        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), mask)
         if rc == -3:
             raise RuntimeError("host arrays too small for the owned particles")
         n = self.p.length
@@ -174,12 +175,13 @@ class DeviceSlab:
         out["halo_ok"] = rc == 0
         return out
 
-    def sync_host(self) -> int:
-        """Make the host arrays of the store current (owned particles, storage order) without copying them again; the global
-        indices land in ``self.host_ids``.  Returns the number of owned particles.  This is the "frame is drawn" copy-back."""
+    def sync_host(self, mask: int = api.PPC_DL_POS | api.PPC_DL_COLOR) -> int:
+        """Make host arrays of the store current (owned particles, storage order) without copying them again; with
+        PPC_DL_IDS the global indices land in ``self.host_ids``.  Returns the number of owned particles.  The default mask is
+        the "frame is drawn" copy-back: positions and colours."""
         if getattr(self, "host_ids", None) is None or len(self.host_ids) < self.p.size:
             self.host_ids = np.zeros(self.p.size, np.uint32)
-        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), self.host_ids.ctypes.data_as(api.u32p), 0)
+        rc = self.p.lib.ppc_slab_download(C.byref(self.p.s), self.host_ids.ctypes.data_as(api.u32p), mask)
         if rc == -2:
             raise HaloTooShallow(f"halo of {self.halo} rows is too thin (the inexactness mark travelled {self.info().taint_rows} rows)")
         if rc != 0:
