@@ -441,7 +441,7 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const size
         StageTimer T( st, ST_SCAN );                                                   // K4 cell-start table
         exclusive_scan( st->cell_count, st->cell_start, bins + 1, st->scratch, st->stream );
     }
-    const uint32_t *slot_of = st->slot_of, *gid_of = nullptr;
+    const uint32_t *slot_of = st->slot_of;
     {
         StageTimer T( st, ST_SORT );                                                   // K5
         if ( st->opt_sort == 1 ) {
@@ -451,14 +451,13 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const size
             slot_of         = where ? st->sort_vals_b : st->slot_of;
         } else {
             PPC_CK( cudaMemsetAsync( st->cell_count, 0, bins * sizeof( uint32_t ), st->stream ) );
-            PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, A.gid, st->cell_count, st->cell_start,
-                        st->slot_of, st->sort_keys_b, n );
-            gid_of = st->sort_keys_b;
+            PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, st->cell_count, st->cell_start,
+                        st->slot_of, n );
         }
     }
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
-        PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, gid_of, st->cell_start, n,
+        PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
                     st->col_valid ? 1 : 0, unranked_cell );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state

@@ -813,15 +813,13 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
     __syncthreads();
     const float R = __uint_as_float( T.rmax_bits );
 
-    // ---- one thread per centre particle; whole warps iterate together so that the phases below can re-converge ----
-    for ( uint32_t t0 = 0; t0 < centre; t0 += TILE_THREADS ) {
-        const uint32_t t     = t0 + threadIdx.x;
-        const bool     valid = t < centre;
-        int            j     = 1;
-        while ( valid && j < TILE_R && t >= T.cen_s0[ j ] )
+    // ---- one thread per centre particle ----
+    for ( uint32_t t = threadIdx.x; t < centre; t += TILE_THREADS ) {
+        int j = 1;
+        while ( j < TILE_R && t >= T.cen_s0[ j ] )
             j++;
-        const uint32_t gk   = valid ? T.cen_g0[ j - 1 ] + ( t - T.cen_s0[ j - 1 ] ) : 0u;   // storage slot
-        const uint32_t self = valid ? T.run_s0[ j ] + ( gk - T.run_g0[ j ] ) : 0u;          // staged index
+        const uint32_t gk   = T.cen_g0[ j - 1 ] + ( t - T.cen_s0[ j - 1 ] );   // storage slot
+        const uint32_t self = T.run_s0[ j ] + ( gk - T.run_g0[ j ] );          // staged index
         const float4   me4  = T.cand[ self ];
         const float    x = me4.x, y = me4.y, r = me4.z;
         const uint32_t gid  = __float_as_uint( me4.w );
@@ -832,40 +830,26 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
         const uint32_t st0   = ( gy == G.taint_lo || gy == G.taint_hi ) ? ST_TAINT : 0u;   // outermost ghost row of a slab window
 
-        // index ranges of the candidates in the row above (0), the own row (1) and the row below (2); empty when the row does
-        // not exist or nothing in it can be within reach
-        uint32_t rb0 = 0, re0 = 0, rb1 = 0, re1 = 0, rb2 = 0, re2 = 0;
-        if ( valid ) {
-            const int f1 = j * TILE2_NB;
-            rb1 = T.fend[ f1 + b_lo - 1 ], re1 = T.fend[ f1 + b_hi ];   // j >= 1, so f1 + b_lo - 1 >= 0
-            if ( gy - 1 >= 0 && !( __fsub_rn( y, reach ) >= top ) ) {
-                const int f0 = f1 - TILE2_NB + b_lo;
-                rb0 = f0 > 0 ? T.fend[ f0 - 1 ] : 0u, re0 = T.fend[ f1 - TILE2_NB + b_hi ];
-            }
-            if ( gy + 1 < G.rows && !( __fadd_rn( y, reach ) < bot ) )
-                rb2 = T.fend[ f1 + TILE2_NB + b_lo - 1 ], re2 = T.fend[ f1 + TILE2_NB + b_hi ];
-        }
-
-        // one flat loop over the three ranges: lanes that are in different rows still execute the same instructions
         uint32_t           stash[ TILE_STASH ];
         unsigned long long skey[ TILE_STASH ];
         uint32_t           nh = 0;
-        {
-            uint32_t q = rb0, e = re0, d = 0;
 #pragma unroll 1
-            for ( ;; ) {
-                if ( q >= e ) {
-                    if ( d == 2 )
-                        break;
-                    d++;
-                    q = d == 1 ? rb1 : rb2, e = d == 1 ? re1 : re2;
-                    continue;
-                }
+        for ( int d = 0; d < 3; d++ ) {
+            const int ry = gy - 1 + d;
+            if ( ry < 0 || ry >= G.rows )
+                continue;
+            if ( d == 0 && __fsub_rn( y, reach ) >= top )   // nothing in the row above can be within reach
+                continue;
+            if ( d == 2 && __fadd_rn( y, reach ) < bot )
+                continue;
+            const int      f_lo = ( j - 1 + d ) * TILE2_NB + b_lo, f_hi = ( j - 1 + d ) * TILE2_NB + b_hi;
+            const uint32_t rb = f_lo > 0 ? T.fend[ f_lo - 1 ] : 0u, re = T.fend[ f_hi ];
+            PPC_UNROLL( PPC_TILE_UNROLL )
+            for ( uint32_t q = rb; q < re; q++ ) {
                 const uint32_t s  = T.perm[ q ];
                 const float4   c  = T.cand[ s ];
-                q++;
-                const float rs = __fadd_rn( r, c.z );
-                const float dx = __fsub_rn( x, c.x );
+                const float    rs = __fadd_rn( r, c.z );
+                const float    dx = __fsub_rn( x, c.x );
                 if ( fabsf( dx ) > rs )   // :353
                     continue;
                 const float dy = __fsub_rn( y, c.y );
@@ -877,32 +861,40 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
                     if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
                         continue;
                     if ( nh < (uint32_t)TILE_STASH )
-                        stash[ nh ] = s | ( d << 16 );
+                        stash[ nh ] = s | ( (uint32_t)d << 16 );
                     nh++;
                 }
             }
         }
-        if ( valid && nh > (uint32_t)TILE_STASH ) {   // crowded particle: generic path
-            n_active++;
-            collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
-            nh = 0xffffffffu;
+        if ( nh == 0 ) {
+            const float4 old = S.pv[ gk ];
+            pv_out[ gk ]     = make_float4( x, y, old.z, old.w );
+            WB.deg[ gk ]     = 0;
+            WB.state[ gk ]   = st0;
+            continue;
         }
-        const uint32_t nhe = ( valid && nh != 0xffffffffu ) ? nh : 0u;   // hits this thread resolves itself
+        n_active++;
+        if ( nh > (uint32_t)TILE_STASH ) {   // crowded particle: generic path
+            collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
+            continue;
+        }
         // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell.
         //   pairs (i, me), i < me : key = i
         //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j
 #pragma unroll 1
-        for ( uint32_t a = 0; a < nhe; a++ ) {
+        for ( uint32_t a = 0; a < nh; a++ ) {
             const uint32_t e = stash[ a ], s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
             skey[ a ] = g < gid ? (unsigned long long)g
                                 : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
         }
+        float       X = x, Y = y;
+        const float wme = T.inv_lut[ T.mass[ self ] ];
 #pragma unroll 1
-        for ( uint32_t a = 0; a + 1 < nhe; a++ ) {   // selection sort (a handful of hits)
+        for ( uint32_t a = 0; a < nh; a++ ) {
             uint32_t           best = a;
             unsigned long long bkey = skey[ a ];
 #pragma unroll 1
-            for ( uint32_t b = a + 1; b < nhe; b++ )
+            for ( uint32_t b = a + 1; b < nh; b++ )
                 if ( skey[ b ] < bkey ) {
                     bkey = skey[ b ];
                     best = b;
@@ -912,37 +904,25 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             skey[ best ]     = skey[ a ];
             stash[ a ]       = e;
             skey[ a ]        = bkey;
-        }
-        // contact geometry of the a-th hit of every lane that has one: the warp walks a = 0, 1, ... together
-        float          X = x, Y = y;
-        const float    wme   = T.inv_lut[ T.mass[ self ] ];
-        const uint32_t max_h = __reduce_max_sync( 0xffffffffu, nhe );
-#pragma unroll 1
-        for ( uint32_t a = 0; a < max_h; a++ ) {
-            __syncwarp();
-            if ( a < nhe ) {
-                const uint32_t e     = stash[ a ], s = e & 0xffffu;
-                const float4   c     = T.cand[ s ];
-                const bool     me_lo = gid < __float_as_uint( c.w );
-                const float    wq    = T.inv_lut[ T.mass[ s ] ];
-                // operands selected by role, one evaluation: lo = the pair's i
+            const uint32_t s     = e & 0xffffu;
+            const float4   c     = T.cand[ s ];
+            const bool     me_lo = gid < __float_as_uint( c.w );
+            const float    wq    = T.inv_lut[ T.mass[ s ] ];
+            {   // operands selected by role, one evaluation: lo = the pair's i
                 const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
                                                               me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
-                if ( P.push ) {   // the hi side subtracts its own terms (:152-155)
+                if ( P.push ) {   // x + t and x - (-t) are the same float operation; the hi side subtracts its own terms (:152-155)
                     X = me_lo ? __fadd_rn( X, P.dpx_lo ) : __fsub_rn( X, P.dpx_hi );
                     Y = me_lo ? __fadd_rn( Y, P.dpy_lo ) : __fsub_rn( Y, P.dpy_hi );
                 }
-                const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
-                WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
             }
+            const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
+            WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
         }
-        if ( valid && nh != 0xffffffffu ) {
-            const float4 old = S.pv[ gk ];
-            pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
-            WB.deg[ gk ]     = (uint16_t)nhe;
-            WB.state[ gk ]   = st0;
-            n_active += nhe ? 1u : 0u;
-        }
+        const float4 old = S.pv[ gk ];
+        pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
+        WB.deg[ gk ]     = (uint16_t)nh;
+        WB.state[ gk ]   = st0;
     }
 }
 

@@ -80,9 +80,9 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_max_radius( const float2 *
 // ---- K5: counting-sort scatter ------------------------------------------------------------------------------
 // slot_of[pos] = storage slot that lands at sorted position pos; positions inside a cell are handed out by a
 // warp-aggregated atomic, so the order inside a cell is arbitrary here and fixed by k_canonical_gather.
-__global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32_t *__restrict__ key, const uint32_t *__restrict__ gid,
-                                                                    uint32_t *__restrict__ cell_fill, const uint32_t *__restrict__ cell_start,
-                                                                    uint32_t *__restrict__ slot_of, uint32_t *__restrict__ gid_of, const size_t n ) {
+__global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32_t *__restrict__ key, uint32_t *__restrict__ cell_fill,
+                                                                    const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ slot_of,
+                                                                    const size_t n ) {
     const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     const bool     valid = k < n;
     const unsigned lane  = threadIdx.x & 31u;
@@ -93,11 +93,8 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
     if ( valid && lane == leader )
         base = atomicAdd( &cell_fill[ c ], (uint32_t)__popc( peers ) );
     base = __shfl_sync( peers, base, leader );
-    if ( valid ) {
-        const uint32_t pos = cell_start[ c ] + base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) );
-        slot_of[ pos ] = (uint32_t)k;
-        gid_of[ pos ]  = gid[ k ];   // the gather ranks a cell's occupants by index: keep the indices contiguous per cell
-    }
+    if ( valid )
+        slot_of[ cell_start[ c ] + base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) ) ] = (uint32_t)k;
 }
 
 // ---- K6: canonicalise + gather ------------------------------------------------------------------------------
@@ -106,7 +103,7 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
 // order -- the canonical form of the reference's chains (:293-294) -- whatever order the scatter or the radix
 // sort left inside the cell.  Then the whole particle record moves from the old set to the new one.
 __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const ParticleSet In, const ParticleSet Out,
-                                                                        const uint32_t *__restrict__ slot_of, const uint32_t *__restrict__ gid_of,
+                                                                        const uint32_t *__restrict__ slot_of,
                                                                         const uint32_t *__restrict__ cell_start, const size_t n,
                                                                         const int move_colour, const uint32_t unranked_cell ) {
     const size_t pos = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
@@ -119,9 +116,6 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
     uint32_t       rank = 0;
     if ( c == unranked_cell )   // a slab window's drop bin: thousands of slots nobody reads, any order will do
         rank = (uint32_t)pos - b;
-    else if ( gid_of )
-        for ( uint32_t q = b; q < e; q++ )
-            rank += ( gid_of[ q ] < g ) ? 1u : 0u;
     else
         for ( uint32_t q = b; q < e; q++ )
             rank += ( In.gid[ slot_of[ q ] ] < g ) ? 1u : 0u;
