@@ -473,8 +473,7 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
             PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 8 * sizeof( uint32_t ), st->stream ) );
         }
-        WaveBuffers WB = st->wave;
-        WB.own_first = st->slab ? st->slab_own_first : 0u, WB.own_end = st->slab ? st->slab_own_end : 0u;
+        const WaveBuffers WB = st->wave;
         {
             StageTimer T( st, ST_COLLIDE );                                            // K7: narrow phase + position pushes
             const unsigned blocks = div_up( n, COLLIDE_THREADS );
@@ -996,7 +995,7 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
     if ( !st->slab_counts )
         st->slab_counts = dev_alloc<uint32_t>( 8 );
     if ( !st->h_slab )
-        PPC_CK( cudaHostAlloc( (void **)&st->h_slab, 8 * sizeof( uint32_t ), cudaHostAllocDefault ) );
+        PPC_CK( cudaHostAlloc( (void **)&st->h_slab, 16 * sizeof( uint32_t ), cudaHostAllocDefault ) );
     const size_t n = p->length;
     if ( n ) {
         StageTimer T( st, ST_UPLOAD );
@@ -1147,6 +1146,9 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     PPC_CK( cudaMemcpyAsync( st->h_slab + 4, st->cell_start + c_own0, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaMemcpyAsync( st->h_slab + 5, st->cell_start + c_own1, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaMemcpyAsync( st->h_slab + 6, st->cell_start + G.cells, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    // end of the first owned row / begin of the last owned row (taint scan, below)
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 8, st->cell_start + c_own0 + G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 9, st->cell_start + c_own1 - G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaStreamSynchronize( st->stream ) );
     const size_t n_work = st->h_slab[ 6 ];
     if ( received )
@@ -1160,6 +1162,17 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     st->slab_own_first = (uint32_t)st->own_first, st->slab_own_end = (uint32_t)( st->own_first + st->n_own );
     if ( n_work >= 1 )
         resolve_stage( st, n_work, G, time_step );
+    if ( n_work >= 1 && st->opt_resolve == 1 && st->wave_hops > 0 && ( G.taint_lo >= 0 || G.taint_hi >= 0 ) ) {
+        StageTimer     T( st, ST_SLAB );
+        const uint32_t lo_end = G.taint_lo >= 0 ? st->h_slab[ 8 ] : 0u, hi_begin = G.taint_hi >= 0 ? st->h_slab[ 9 ] : (uint32_t)n_work;
+        const uint32_t items  = lo_end + ( (uint32_t)n_work - ( hi_begin > lo_end ? hi_begin : lo_end ) );
+        const bool     events = st->wave_hops == 2;   // which engine ran, hence where the state words are
+        if ( items )
+            PPC_LAUNCH( k_slab_taint_scan, div_up( items, STREAM_THREADS ), STREAM_THREADS, 0, st->stream,
+                        events ? &st->recs.wr->state : st->wave.state, events ? (uint32_t)( sizeof( WaveRec ) / 4 ) : 1u, st->wave.deg,
+                        st->set[ st->cur ].key, G, lo_end, hi_begin > lo_end ? hi_begin : lo_end, (uint32_t)n_work, st->slab_own_first,
+                        st->slab_own_end, st->wave.counters );
+    }
     st->pre_valid = true;
     p->length     = st->n_own <= p->size ? st->n_own : p->size;
     return (int64_t)st->n_own;

@@ -40,7 +40,8 @@ constexpr uint32_t PC_MASK         = ( 1u << PC_BITS ) - 1u;
 // Bit 31 of the state word: TAINT.  Slab windows only (GridDims::taint_lo / taint_hi): the particles of the outermost ghost
 // row miss their outward contacts, so what the resolve computes for them -- and for every particle that resolves a pair
 // with a tainted one -- may differ from the whole-field run.  The bit travels with the pairs; the resolve reports whether
-// it reached an owned particle (counters[10]) and how many rows it got into the window (counters[11]).
+// bit travels with the pairs; afterwards k_slab_taint_scan (ppc_slab.cuh) looks whether it reached an owned particle
+// (counters[10]) and how many rows it got into the window (counters[11]).
 constexpr uint32_t ST_TAINT        = 0x80000000u;
 constexpr uint32_t ST_ROUND_LIMIT  = ( 1u << ( 31 - PC_BITS ) ) - 1u;
 __device__ __forceinline__ uint32_t st_round( const uint32_t w ) { return ( w & ~ST_TAINT ) >> PC_BITS; }
@@ -309,7 +310,6 @@ struct WaveBuffers {
     size_t    stride;    // particle capacity
     uint32_t  maxdeg;    // list positions stored per particle (>= INC_MAXDEG); longer lists are recomputed on demand
     uint32_t *list[ 2 ]; // active-particle queues (ping-pong between rounds); CTA b of the wavefront owns [b*chunk, (b+1)*chunk)
-    uint32_t  own_first, own_end;   // slab mode: storage slots of the owned particles (taint reports); 0, 0 otherwise
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
                          // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
                          // [8] particles with at least one contact in this substep, [9] densest tile in particles per 1024 cells (from k_collide_tile),
@@ -978,24 +978,6 @@ __device__ __forceinline__ uint32_t head_contact( const ParticleSet &S, const Gl
     return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
 }
 
-// A pair with a tainted end fires: whichever end was clean becomes tainted now.  Tell the host if that particle is owned,
-// and how many rows into the window the taint has come.
-__device__ __forceinline__ void report_taint( const ParticleSet &S, const GridDims &G, const WaveBuffers &WB, const uint32_t a, const uint32_t wa,
-                                              const uint32_t b, const uint32_t wb ) {
-    if ( ( wa & wb & ST_TAINT ) != 0u )
-        return;   // both were tainted already
-    const uint32_t fresh = ( wa & ST_TAINT ) ? b : a;
-    if ( fresh >= WB.own_first && fresh < WB.own_end )
-        atomicOr( &WB.counters[ 10 ], 1u );
-    const int row = (int)( S.key[ fresh ] / (uint32_t)G.cols );
-    int       depth = 0x7fffffff;
-    if ( G.taint_lo >= 0 )
-        depth = row - G.taint_lo;
-    if ( G.taint_hi >= 0 )
-        depth = min( depth, G.taint_hi - row );
-    atomicMax( &WB.counters[ 11 ], (uint32_t)max( depth, 0 ) );
-}
-
 // One wavefront step for particle `me` in round r.  Returns true while the particle still has unresolved contacts.
 __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const GlobalAccessor &acc, float4 *pv_out, const GridDims &G,
                                                  const float dt, const WaveBuffers &WB, const uint32_t me, const uint32_t r ) {
@@ -1032,8 +1014,6 @@ __device__ __forceinline__ bool wavefront_visit( const ParticleSet &S, const Glo
         *vb  = ub;
     }
     const uint32_t taint = ( w | wq ) & ST_TAINT;
-    if ( taint )
-        report_taint( S, G, WB, me, w, q, wq );
     WB.state[ me ] = taint | ( r << PC_BITS ) | ( pc + 1 );
     WB.state[ q ]  = taint | ( r << PC_BITS ) | ( pcq + 1 );
     return pc + 1 < deg;
@@ -1250,8 +1230,6 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                 // the pair's j is done for this round
                                 const uint32_t nhi = ( st_hi & PC_MASK ) + 1;
                                 uint32_t       taint = ( st_lo | st_hi ) & ST_TAINT;   // of the chain's particle from here on
-                                if ( taint )
-                                    report_taint( S, G, WB, lo, st_lo, hi, st_hi );
                                 *vb                = ub;
                                 R.wr[ hi ].state   = taint | ( r << PC_BITS ) | nhi;
                                 if ( nhi < deg_hi )
@@ -1299,10 +1277,7 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                         }
                                     }
                                     cpc++;
-                                    if ( ( taint | X.state ) & ST_TAINT ) {
-                                        report_taint( S, G, WB, cur, taint, x, X.state );
-                                        taint = ST_TAINT;
-                                    }
+                                    taint |= X.state & ST_TAINT;
                                     *vx              = ux;
                                     R.wr[ x ].state = taint | ( r << PC_BITS ) | ( pcx + 1 );
                                     if ( pcx + 1 < X.deg )

@@ -147,6 +147,31 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_localize( uint32_t *_
         atomicAdd( &cell_count[ lk ], (uint32_t)__popc( peers ) );
 }
 
+// After the resolve: did the inexactness mark (ST_TAINT) reach an owned particle, and how many rows did it travel?  A contact
+// spans at most one cell row, so a mark inside the owned rows implies a marked particle in the first or the last owned
+// row: only the two ghost bands plus those two rows are looked at (slots [0, lo_end) and [hi_begin, n)).
+// `state` is the array the resolve engine kept its state words in (stride in words: 1 for WaveBuffers::state, 8 for WaveRec).
+__global__ void __launch_bounds__( STREAM_THREADS ) k_slab_taint_scan( const uint32_t *__restrict__ state, const uint32_t stride, const uint16_t *__restrict__ deg,
+                                                                       const uint32_t *__restrict__ key, const GridDims G, const uint32_t lo_end,
+                                                                       const uint32_t hi_begin, const uint32_t n, const uint32_t own_first,
+                                                                       const uint32_t own_end, uint32_t *__restrict__ counters ) {
+    const uint32_t t = blockIdx.x * STREAM_THREADS + threadIdx.x;
+    const uint32_t k = t < lo_end ? t : hi_begin + ( t - lo_end );
+    if ( k >= n || ( t >= lo_end && k < lo_end ) )
+        return;
+    if ( deg[ k ] == 0 || !( __ldcg( &state[ (size_t)k * stride ] ) & ST_TAINT ) )
+        return;
+    if ( k >= own_first && k < own_end )
+        atomicOr( &counters[ 10 ], 1u );
+    const int row = (int)( key[ k ] / (uint32_t)G.cols );
+    int       depth = 0x7fffffff;
+    if ( G.taint_lo >= 0 )
+        depth = row - G.taint_lo;
+    if ( G.taint_hi >= 0 )
+        depth = min( depth, G.taint_hi - row );
+    atomicMax( &counters[ 11 ], (uint32_t)max( depth, 0 ) );
+}
+
 // host -> device with explicit global indices (slab ranks hold an arbitrary subset of the particles)
 __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_upload( const ParticleSet S, const float *__restrict__ px, const float *__restrict__ py,
                                                                    const float *__restrict__ vx, const float *__restrict__ vy,
