@@ -280,11 +280,36 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
     substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * n * world * args.steps / (ms_total * 1e-3) / 1e9
 
+    def quick_value(workload: str, steps: int = 16):
+        """particle-substeps/s of another single-GPU configuration (state resident, same timing rules), for context."""
+        m, _ = WORKLOADS[workload]
+        sc2 = make_scene(workload, m)
+        q = api.Particles(m, device=local_rank)
+        q.set_sync_policy(api.PPC_SYNC_MANUAL)
+        q.set_option("resolve", args.resolve)
+        q.fill(sc2.px, sc2.py, sc2.vx, sc2.vy, sc2.mass, sc2.radius, sc2.rgba)
+        q.run_substeps(sc2.W, sc2.H, DT, args.settle + args.warmup)
+        ext2 = torch.cuda.ExternalStream(q.stream(), device=torch.device("cuda", local_rank))
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(ext2)
+        q.run_substeps(sc2.W, sc2.H, DT, steps)
+        a1.record(ext2)
+        a1.synchronize()
+        ms = a0.elapsed_time(a1) / steps
+        q.Free()
+        return {"workload": WORKLOADS[workload][1], "value": m / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                "roofline_substep_frac": ALGO_BYTES_PER_PARTICLE_SUBSTEP * m / (ms * 1e-3) / 1e9 / peak,
+                "l2": "state larger than L2" if 28.0 * m > 126e6 else "state fits the 126 MB L2 (no flush): not an HBM-roofline number"}
+
     line = None
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             _, _, cpu = time_reference_cpu(args.workload, 3, 1)
+        others = None
+        if world == 1 and not args.no_other_configs:
+            others = {w: quick_value(w) for w in ("uniform16m", "uniform1m") if w != args.workload}
         g = p.grid_info()
         wave = p.wave_stats()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -299,6 +324,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "roofline_substep": {"bound": "hbm", "achieved": substep_gbs / world, "peak": peak, "unit": "GB/s",
                                      "frac": substep_gbs / world / peak, "note": "40 B x particles x substeps / time, whole substep, per GPU"},
                 "cpu_baseline": cpu,
+                "other_configs": others,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step,
                         "note": "particlesUpdate + particlesCollisionsCheck_Grid x8, then p_x, p_y, colors copied to the host arrays"},
                 "resolve_wavefront": None if wave is None else {"rounds_last_substep": wave[0], "particle_visits_last_substep": wave[1]},
@@ -508,6 +534,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the context measurements of the other single-GPU configurations")
     ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

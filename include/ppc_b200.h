@@ -190,6 +190,19 @@ int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out );
 /* candidate pairs (i, j) whose i (lower global index) this rank owns; every pair of the field appears on exactly one rank */
 int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
 
+/* =====================================================================================================
+ * Part 4 -- state snapshots (the reference has no on-disk format; this one is ours).
+ *   header: 8 x uint64 little endian = magic "PPCB2001", version 1, n, window width, window height, 0, 0, 0
+ *   body:   p_x[n], p_y[n], v_x[n], v_y[n], mass[n], radius[n] (float32), colors[n] (4 x uint8): the seven arrays
+ *           of struct Particles_t (includes/structs.h:9-22) in API order, 28 n bytes.
+ * Used to keep settled piles and to replay parity cases.
+ * ===================================================================================================== */
+/* makes the host arrays current, then writes them; 0 on success, -2 cannot open, -3 short write */
+int ppc_snapshot_write( struct Particles_t *p, uint16_t window_width, uint16_t window_height, const char *path );
+/* fills the host arrays of a store created with particlesCreate( >= n ) and sets length = n; returns n,
+ * -2 cannot open, -3 not a snapshot / truncated, -(n + 16) when the store holds fewer than n particles */
+int64_t ppc_snapshot_read( struct Particles_t *p, const char *path, uint16_t *window_width, uint16_t *window_height );
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_
                      "ppc_version"]
 SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_info",
                 "ppc_slab_debug_pairs"]
+SNAPSHOT_SYMBOLS = ["ppc_snapshot_write", "ppc_snapshot_read"]
 
 _lib = None
 
@@ -113,6 +114,9 @@ def load_library() -> C.CDLL:
     L.ppc_profile_read.argtypes, L.ppc_profile_read.restype = [PP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)], C.c_int
     L.ppc_profile_reset.argtypes, L.ppc_profile_reset.restype = [PP], None
     L.ppc_version.argtypes, L.ppc_version.restype = [], C.c_char_p
+    L.ppc_snapshot_write.argtypes, L.ppc_snapshot_write.restype = [PP, C.c_uint16, C.c_uint16, C.c_char_p], C.c_int
+    L.ppc_snapshot_read.argtypes = [PP, C.c_char_p, C.POINTER(C.c_uint16), C.POINTER(C.c_uint16)]
+    L.ppc_snapshot_read.restype = C.c_int64
     L.ppc_grid_dims.argtypes, L.ppc_grid_dims.restype = [C.c_uint16, C.c_uint16, C.c_float, C.POINTER(GridInfo)], C.c_int
     L.ppc_slab_init.argtypes = [PP, u32p, C.c_uint16, C.c_uint16, C.c_float, C.c_int, C.c_int, C.c_int]
     L.ppc_slab_init.restype = C.c_int
@@ -254,6 +258,19 @@ class Particles:
         if self.lib.ppc_debug_wave_stats(C.byref(self.s), C.byref(r), C.byref(v)) != 0:
             return None
         return int(r.value), int(v.value)
+
+    def snapshot_write(self, W: int, H: int, path: str) -> None:
+        rc = self.lib.ppc_snapshot_write(C.byref(self.s), W, H, path.encode())
+        if rc != 0:
+            raise OSError(f"ppc_snapshot_write({path}) failed ({rc})")
+
+    def snapshot_read(self, path: str):
+        """Load a snapshot into this store (capacity permitting); returns (n, W, H)."""
+        w, h = C.c_uint16(), C.c_uint16()
+        n = self.lib.ppc_snapshot_read(C.byref(self.s), path.encode(), C.byref(w), C.byref(h))
+        if n < 0:
+            raise OSError(f"ppc_snapshot_read({path}) failed ({n})")
+        return int(n), int(w.value), int(h.value)
 
     def stream(self) -> int:
         return int(self.lib.ppc_stream(C.byref(self.s)) or 0)

@@ -1263,6 +1263,69 @@ extern "C" int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, 
     return (int64_t)total;
 }
 
+// =================================================================================================================
+// Part 4: state snapshots (the reference has no on-disk format, so this one is ours):
+//   header  8 x uint64, little endian: magic "PPCB2001", version 1, n, window width, window height, 3 x reserved (0)
+//   body    p_x[n], p_y[n], v_x[n], v_y[n], mass[n], radius[n] as float32, then colors[n] as 4 x uint8   (28 n bytes)
+// Arrays are in API order (index i of every array is particle i), exactly the seven arrays of struct Particles_t.
+// =================================================================================================================
+static const uint64_t k_snapshot_magic = 0x3130303242435050ull;   // "PPCB2001"
+
+extern "C" int ppc_snapshot_write( struct Particles_t *p, uint16_t window_width, uint16_t window_height, const char *path ) {
+    Store *st = store_of( p );
+    if ( st->slab )
+        return -1;
+    absorb_host_changes( st, p );
+    download( st, p, PPC_DL_ALL );   // mass and radius never change on the device
+    FILE *f = fopen( path, "wb" );
+    if ( !f )
+        return -2;
+    const uint64_t n = p->length;
+    const uint64_t header[ 8 ] = { k_snapshot_magic, 1, n, window_width, window_height, 0, 0, 0 };
+    bool           ok = fwrite( header, sizeof( header ), 1, f ) == 1;
+    float         *h[ 6 ] = { p->p_x, p->p_y, p->v_x, p->v_y, p->mass, p->radius };
+    for ( int a = 0; a < 6 && ok; a++ )
+        ok = n == 0 || fwrite( h[ a ], sizeof( float ), n, f ) == n;
+    ok = ok && ( n == 0 || fwrite( p->colors, 4, n, f ) == n );
+    ok = ( fclose( f ) == 0 ) && ok;
+    return ok ? 0 : -3;
+}
+
+extern "C" int64_t ppc_snapshot_read( struct Particles_t *p, const char *path, uint16_t *window_width, uint16_t *window_height ) {
+    Store *st = store_of( p );
+    if ( st->slab )
+        return -1;
+    FILE *f = fopen( path, "rb" );
+    if ( !f )
+        return -2;
+    uint64_t header[ 8 ];
+    if ( fread( header, sizeof( header ), 1, f ) != 1 || header[ 0 ] != k_snapshot_magic || header[ 1 ] != 1 ) {
+        fclose( f );
+        return -3;
+    }
+    const uint64_t n = header[ 2 ];
+    if ( n > p->size ) {   // the caller's store is too small; say how large it has to be
+        fclose( f );
+        return -(int64_t)n - 16;
+    }
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    float *h[ 6 ] = { p->p_x, p->p_y, p->v_x, p->v_y, p->mass, p->radius };
+    bool   ok = true;
+    for ( int a = 0; a < 6 && ok; a++ )
+        ok = n == 0 || fread( h[ a ], sizeof( float ), n, f ) == n;
+    ok = ok && ( n == 0 || fread( p->colors, 4, n, f ) == n );
+    fclose( f );
+    if ( !ok )
+        return -3;
+    p->length     = n;
+    st->dirty_all = true;   // the host arrays are the truth now
+    if ( window_width )
+        *window_width = (uint16_t)header[ 3 ];
+    if ( window_height )
+        *window_height = (uint16_t)header[ 4 ];
+    return (int64_t)n;
+}
+
 extern "C" void              *ppc_stream( struct Particles_t *p ) { return (void *)store_of( p )->stream; }
 extern "C" unsigned long long ppc_kernel_launches( void ) { return g_launches; }
 extern "C" void               ppc_profile( struct Particles_t *p, int enable ) { store_of( p )->profiling = enable != 0; }

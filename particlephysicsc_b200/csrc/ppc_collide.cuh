@@ -658,12 +658,21 @@ __global__ void __launch_bounds__( TILE_THREADS, PPC_TILE_MINBLOCKS ) k_collide_
 // coordinates below 65,536); the reference's own AABB + circle test then decides, so the pair set is unchanged -- with
 // one extra check that the two cell columns differ by at most one, because the reference never pairs particles two
 // columns apart even in the one-ulp corner where its float division puts a touching pair there.
-constexpr int TILE2_CAP  = 2048;                  // staged particles
-constexpr int TILE2_F    = 4;                     // fine bins per cell
+#ifndef PPC_TILE2_CAP
+#define PPC_TILE2_CAP 2048
+#endif
+#ifndef PPC_TILE2_TARGET
+#define PPC_TILE2_TARGET 800
+#endif
+#ifndef PPC_TILE2_F
+#define PPC_TILE2_F 4
+#endif
+constexpr int TILE2_CAP  = PPC_TILE2_CAP;         // staged particles
+constexpr int TILE2_F    = PPC_TILE2_F;           // fine bins per cell
 constexpr int TILE2_MAXC = 64;                    // staged columns (centre + halo)
 constexpr int TILE2_NB   = TILE2_MAXC * TILE2_F;  // fine bins per staged row
 constexpr int TILE2_BINS = ( TILE_R + 2 ) * TILE2_NB;
-constexpr int TILE2_TARGET = 800;
+constexpr int TILE2_TARGET = PPC_TILE2_TARGET;
 
 struct Tile2Smem {
     float4   cand[ TILE2_CAP ];    // x, y, radius, API index (bits), in storage order
@@ -1172,8 +1181,18 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
     namespace cg        = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
+#ifdef PPC_EV_WARPBUF   // queue pushes staged per WARP: no CTA barrier inside a round
+    constexpr int        WBUF = EV_BUF / ( EV_THREADS / 32 );
+    __shared__ uint32_t  wbuf[ EV_THREADS / 32 ][ WBUF ];
+    __shared__ uint32_t  wbuf_n[ EV_THREADS / 32 ];
+    uint32_t            *buf   = wbuf[ threadIdx.x >> 5 ];
+    uint32_t            &buf_n = wbuf_n[ threadIdx.x >> 5 ];
+    if ( ( threadIdx.x & 31u ) == 0 )
+        buf_n = 0;
+#else
     __shared__ uint32_t  buf[ EV_BUF ];
     __shared__ uint32_t  buf_n, buf_base;
+#endif
     volatile uint32_t   *counters = WB.counters;
     const size_t         tid_g = (size_t)blockIdx.x * EV_THREADS + threadIdx.x, nthreads = (size_t)gridDim.x * EV_THREADS;
     if ( threadIdx.x == 0 )
@@ -1297,6 +1316,22 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                 }
             }
             // pushes were staged in shared memory; flush with one global atomic when the buffer could overflow
+#ifdef PPC_EV_WARPBUF
+            __syncwarp();
+            const uint32_t staged = buf_n;
+            __syncwarp();
+            if ( staged > (uint32_t)( WBUF - ( EV_FOLLOW + 2 ) * 32 ) || ( it + 1 == iters && staged ) ) {
+                uint32_t base = 0;
+                if ( ( threadIdx.x & 31u ) == 0 ) {
+                    base  = atomicAdd( d_cnt, staged );
+                    buf_n = 0;
+                }
+                base = __shfl_sync( 0xffffffffu, base, 0 );
+                for ( uint32_t t = threadIdx.x & 31u; t < staged; t += 32 )
+                    dst[ base + t ] = buf[ t ];
+                __syncwarp();
+            }
+#else
             __syncthreads();
             const uint32_t staged = buf_n;   // read between two barriers: the same value in every thread
             __syncthreads();
@@ -1310,6 +1345,7 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                     dst[ buf_base + t ] = buf[ t ];
                 __syncthreads();
             }
+#endif
         }
         if ( threadIdx.x == 0 && blockIdx.x == 0 )
             WB.counters[ 4 ] = r;

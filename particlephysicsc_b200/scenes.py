@@ -201,3 +201,29 @@ def debug_scene_frames(frames: int = 4500, per_frame: int = 10, W: int = 1200, H
         m = int(rng.ints(1, 5, 10)[0])
         r = int(rng.ints(1, 2, 8)[0])
         yield float(x), float(y), float(m), float(r), per_frame
+
+
+# ---- snapshot files (format of ppc_snapshot_write / ppc_snapshot_read, include/ppc_b200.h part 4) ---------------------
+SNAPSHOT_MAGIC = 0x3130303242435050  # "PPCB2001"
+
+
+def write_snapshot(path: str, sc: Scene) -> None:
+    """Write a scene in the library's snapshot format (host only; the library reads it with ppc_snapshot_read)."""
+    with open(path, "wb") as f:
+        np.array([SNAPSHOT_MAGIC, 1, sc.n, sc.W, sc.H, 0, 0, 0], dtype="<u8").tofile(f)
+        for a in (sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius):
+            np.ascontiguousarray(a, dtype="<f4").tofile(f)
+        np.ascontiguousarray(sc.rgba, dtype=np.uint8).tofile(f)
+
+
+def read_snapshot(path: str, name: str = "snapshot") -> Scene:
+    with open(path, "rb") as f:
+        h = np.fromfile(f, dtype="<u8", count=8)
+        if len(h) != 8 or int(h[0]) != SNAPSHOT_MAGIC or int(h[1]) != 1:
+            raise ValueError(f"{path} is not a particle snapshot")
+        n = int(h[2])
+        arrays = [np.fromfile(f, dtype="<f4", count=n) for _ in range(6)]
+        rgba = np.fromfile(f, dtype=np.uint8, count=4 * n).reshape(n, 4)
+        if any(len(a) != n for a in arrays) or rgba.shape[0] != n:
+            raise ValueError(f"{path} is truncated")
+    return Scene(name, int(h[3]), int(h[4]), *arrays, rgba)

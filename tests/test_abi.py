@@ -27,7 +27,7 @@ def declared_symbols():
 
 
 def test_header_and_binding_agree():
-    assert declared_symbols() == sorted(api.REFERENCE_SYMBOLS + api.EXTENSION_SYMBOLS + api.SLAB_SYMBOLS)
+    assert declared_symbols() == sorted(api.REFERENCE_SYMBOLS + api.EXTENSION_SYMBOLS + api.SLAB_SYMBOLS + api.SNAPSHOT_SYMBOLS)
 
 
 def test_library_exports_every_declared_symbol(lib):

@@ -529,3 +529,29 @@ def test_sixteen_million_particles_properties():
     g_kick = 3 * 9.81 * DT * np.sum(st.mass.astype(np.float64))
     assert np.all(np.abs(mom - mom0 - g_kick) < 0.02 * abs(g_kick) + 1e-3 * np.abs(mom0).max())
     p.Free()
+
+
+def test_snapshot_resumes_bit_exactly(oracle, tmp_path):
+    """Save a running field, load it into another store (and through the host-side reader), continue both: same bits."""
+    sc = scenes.polydisperse_pile(30000, seed=117, vmax=4.0)
+    a = gpu_store(state_from_scene(sc))
+    a.run_substeps(sc.W, sc.H, DT, 5)
+    path = str(tmp_path / "running.ppcb")
+    a.snapshot_write(sc.W, sc.H, path)
+    b = api.Particles(sc.n + 100)
+    b.set_sync_policy(api.PPC_SYNC_MANUAL)
+    assert b.snapshot_read(path) == (sc.n, sc.W, sc.H)
+    small = api.Particles(10)
+    with pytest.raises(OSError):
+        small.snapshot_read(path)
+    small.Free()
+    a.run_substeps(sc.W, sc.H, DT, 5)
+    b.run_substeps(sc.W, sc.H, DT, 5)
+    assert_state_bits(gpu_state(a), gpu_state(b), "resumed from snapshot")
+    # the same file, read on the host, continues identically on the oracle
+    ref = state_from_scene(scenes.read_snapshot(path))
+    for _ in range(5):
+        oracle.substep(ref, sc.W, sc.H, DT, 0, False)
+    assert_state_bits(gpu_state(a), ref, "snapshot -> oracle")
+    a.Free()
+    b.Free()

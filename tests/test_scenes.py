@@ -51,3 +51,22 @@ def test_debug_scene_matches_main_c_parameters():
     assert len(frames) == 50
     for x, y, m, r, cnt in frames:
         assert 0 <= x <= 1200 and 0 <= y <= 675 and 5 <= m <= 10 and 2 <= r <= 8 and cnt == 10
+
+
+def test_snapshot_file_round_trip(tmp_path):
+    """The snapshot format (include/ppc_b200.h part 4) written and read by the host-side helpers."""
+    import numpy as np
+    from particlephysicsc_b200 import scenes
+    sc = scenes.polydisperse_pile(5000, seed=9, vmax=3.0)
+    path = str(tmp_path / "pile.ppcb")
+    scenes.write_snapshot(path, sc)
+    assert (tmp_path / "pile.ppcb").stat().st_size == 64 + 28 * sc.n
+    back = scenes.read_snapshot(path)
+    assert (back.W, back.H, back.n) == (sc.W, sc.H, sc.n)
+    for f in ("px", "py", "vx", "vy", "mass", "radius", "rgba"):
+        assert np.array_equal(getattr(back, f), getattr(sc, f))
+    with open(path, "r+b") as f:
+        f.truncate(64 + 10 * sc.n)
+    import pytest
+    with pytest.raises(ValueError):
+        scenes.read_snapshot(path)
