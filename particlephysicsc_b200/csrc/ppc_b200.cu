@@ -64,7 +64,7 @@ struct Store {
     uint32_t    *d_word = nullptr;   // one word for small reductions
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     WaveRecs     recs = {};          // packed records of the event-driven rounds
-    int          events_grid = 0, tasks_grid = 0;
+    int          events_grid = 0;
     size_t       wave_cap = 0;
     int          wave_grid = 0;
     WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
@@ -187,12 +187,6 @@ static void ensure_wave_buffers( Store *st ) {
         abort();
     }
     st->events_grid = per_sm * sms;   // latency bound: as many loads in flight as the SM holds
-    PPC_CK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &per_sm, k_resolve_tasks, EV_THREADS, 0 ) );
-    if ( per_sm < 1 ) {
-        fprintf( stderr, "particlephysicsc_b200: task wavefront kernel cannot be made resident\n" );
-        abort();
-    }
-    st->tasks_grid = per_sm * sms;
 }
 
 static void check_device_flags( Store *st ) {   // after a stream synchronise
@@ -554,18 +548,16 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             size_t n_arg = n;
             // packed records pay off when most particles are in contact; sparse contact sets are cheaper on the polling
             // kernel's compact per-CTA queues (no pack pass).  "wave_mode": 1 = choose by density (default), 2 = always events.
-            if ( ( st->opt_wave_mode == 2 || st->opt_wave_mode == 4 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
+            if ( ( st->opt_wave_mode == 2 || ( st->opt_wave_mode == 1 && dense ) ) && passes == 0 ) {
                 const WaveRecs R = st->recs;
                 st->wave_hops    = 2;   // a thread fires a star of pairs around one particle per round (chain following)
                 PPC_LAUNCH( k_wave_pack, div_up( n, 256 ), 256, 0, st->stream, S, (const float4 *)pv_out, WB, R, n );
-                const bool tasks = st->opt_wave_mode == 4;   // warp-level task queues (experimental) instead of thread-per-item
-                int        grid = tasks ? st->tasks_grid : st->events_grid;
-                const int  want = (int)div_up( n, EV_THREADS );
+                int       grid = st->events_grid;
+                const int want = (int)div_up( n, EV_THREADS );
                 if ( grid > want )
                     grid = want;
                 void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&R };
-                PPC_CK( cudaLaunchCooperativeKernel( tasks ? (const void *)k_resolve_tasks : (const void *)k_resolve_events, dim3( grid ),
-                                                     dim3( EV_THREADS ), args, 0, st->stream ) );
+                PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_events, dim3( grid ), dim3( EV_THREADS ), args, 0, st->stream ) );
                 ++g_launches;
             } else {   // polling rounds (after tile passes, or "wave_mode"=0)
                 int       grid = st->wave_grid;

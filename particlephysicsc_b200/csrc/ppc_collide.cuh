@@ -1353,204 +1353,6 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
     }
 }
 
-// ---- K7b, event-driven rounds with warp-level task queues ---------------------------------------------------------------
-// Same records, firing rule, claims and chain following as k_resolve_events.  There, one thread takes an item through
-// everything -- examine, claim, fire, follow the chain -- so the long firing path (a chain of dependent sector loads) runs
-// with the ~5 lanes of a warp whose item happened to be ready while the others idle (ncu: profiles/README.md).  Here a warp
-// separates the steps and re-packs the work between them in shared memory:
-//   EXAMINE  32 items (from the round's queue, or follow-ups of this warp's own chains): is the head pair ready?  -> task
-//   FIRE     32 ready pairs: claim, impulse, write back; particles with contacts left go to the next round's queue, the
-//            chain particle (the pair's i, as before) becomes a follow-up examination of this same round
-// so every step runs with (nearly) all lanes, each lane waiting on its own loads only.
-constexpr int TQ_CAP = 96;    // ready pairs queued per warp (see the bounds in the loop)
-constexpr int XQ_CAP = 64;    // follow-up examinations queued per warp
-constexpr int OB_CAP = 256;   // pushes to the next round's queue staged per warp
-constexpr uint32_t TM_FOLLOW = 1u << 28, TM_CHAIN_HI = 1u << 27;
-
-struct TaskWarpSmem {
-    uint32_t lo[ TQ_CAP ], hi[ TQ_CAP ], st_lo[ TQ_CAP ], st_hi[ TQ_CAP ], meta[ TQ_CAP ];   // meta: deg_lo | deg_hi << 12 | follows left << 24 | flags
-    uint32_t xq[ XQ_CAP ];   // particle | follows left << 29
-    uint32_t ob[ OB_CAP ];
-};
-
-__global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_tasks( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
-                                                                 const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
-                                                                 const WaveRecs R ) {
-    namespace cg        = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
-    __shared__ TaskWarpSmem smem[ EV_THREADS / 32 ];
-    TaskWarpSmem           &Q = smem[ threadIdx.x >> 5 ];
-    volatile uint32_t      *counters = WB.counters;
-    const unsigned          lane = threadIdx.x & 31u, lt = ( 1u << lane ) - 1u;
-    const size_t            warp_g = ( (size_t)blockIdx.x * EV_THREADS + threadIdx.x ) >> 5, nwarps = ( (size_t)gridDim.x * EV_THREADS ) >> 5;
-
-    for ( uint32_t r = 1;; r++ ) {
-        const uint32_t n_q = r == 1 ? 0u : counters[ ( r - 1 ) % 3 ];
-        if ( r > 1 && n_q == 0 )
-            break;
-        if ( r >= ST_ROUND_LIMIT ) {
-            if ( blockIdx.x == 0 && threadIdx.x == 0 )
-                atomicOr( &WB.counters[ 3 ], 2u );
-            break;
-        }
-        if ( blockIdx.x == 0 && threadIdx.x == 0 )
-            counters[ ( r + 1 ) % 3 ] = 0;
-        const uint32_t *src   = WB.list[ ( r - 1 ) & 1 ];
-        uint32_t       *dst   = WB.list[ r & 1 ];
-        uint32_t       *d_cnt = &WB.counters[ r % 3 ];
-        const size_t    items = r == 1 ? n : (size_t)n_q;
-        size_t          chunk = warp_g;                 // 32 consecutive items; chunks interleave over the warps of the grid
-        uint32_t        nf = 0, nx = 0, nob = 0;        // queue lengths (warp-uniform)
-
-        // queue one examined pair that is ready
-        auto examine = [ & ]( const bool active, const uint32_t p, const uint32_t follows, const bool own ) {
-            bool     ready = false;
-            uint32_t t_lo = 0, t_hi = 0, t_slo = 0, t_shi = 0, t_meta = 0;
-            bool     requeue = false;   // a chain particle whose next pair is not ready goes to the next round
-            if ( active ) {
-                const WaveRec  A   = load_wave_rec( R.wr + p );
-                const uint32_t pcA = A.state & PC_MASK;
-                if ( pcA < A.deg && ( own || st_round( A.state ) != r ) ) {
-                    const uint32_t e = rec_head( S, acc, G, WB, A, p, pcA ), o = e & ~INC_LO_FLAG;
-                    const WaveRec  B = load_wave_rec( R.wr + o );
-                    const uint32_t pcB = B.state & PC_MASK;
-                    if ( pcB < B.deg && st_round( B.state ) != r && ( rec_head( S, acc, G, WB, B, o, pcB ) & ~INC_LO_FLAG ) == p ) {
-                        const bool p_lo = ( e & INC_LO_FLAG ) != 0;
-                        ready = true;
-                        t_lo = p_lo ? p : o, t_hi = p_lo ? o : p;
-                        t_slo = p_lo ? A.state : B.state, t_shi = p_lo ? B.state : A.state;
-                        t_meta = ( p_lo ? A.deg : B.deg ) | ( ( p_lo ? B.deg : A.deg ) << 12 ) | ( follows << 24 );
-                        if ( own )
-                            t_meta |= TM_FOLLOW | ( p_lo ? 0u : TM_CHAIN_HI );
-                    } else
-                        requeue = own;
-                } else
-                    requeue = false;
-            }
-            const unsigned m = __ballot_sync( 0xffffffffu, ready );
-            if ( ready ) {
-                const uint32_t at = nf + (uint32_t)__popc( m & lt );
-                Q.lo[ at ] = t_lo, Q.hi[ at ] = t_hi, Q.st_lo[ at ] = t_slo, Q.st_hi[ at ] = t_shi, Q.meta[ at ] = t_meta;
-            }
-            nf += (uint32_t)__popc( m );
-            const unsigned mq = __ballot_sync( 0xffffffffu, requeue );
-            if ( requeue )
-                Q.ob[ nob + (uint32_t)__popc( mq & lt ) ] = p;
-            nob += (uint32_t)__popc( mq );
-            __syncwarp();
-        };
-
-        for ( ;; ) {
-            if ( nob > (uint32_t)( OB_CAP - 64 ) ) {   // flush the staged pushes: one global atomic per warp and flush
-                uint32_t base = 0;
-                if ( lane == 0 )
-                    base = atomicAdd( d_cnt, nob );
-                base = __shfl_sync( 0xffffffffu, base, 0 );
-                for ( uint32_t t = lane; t < nob; t += 32 )
-                    dst[ base + t ] = Q.ob[ t ];
-                nob = 0;
-                __syncwarp();
-            }
-            const bool have_input = chunk * 32 < items;
-            // bounds: an input batch runs with nf < 32, a follow-up batch with nf <= 63, each adds <= 32: nf <= 95 < TQ_CAP;
-            //         a fire batch runs with nx < 32 and adds <= 32: nx <= 63 < XQ_CAP
-            if ( nx >= 32 || ( nx > 0 && nf < 32 && !have_input ) ) {   // follow-up examinations of this warp's chains
-                const uint32_t cnt = nx < 32 ? nx : 32u;
-                const bool     act = lane < cnt;
-                const uint32_t w   = act ? Q.xq[ nx - cnt + lane ] : 0u;
-                nx -= cnt;
-                __syncwarp();
-                examine( act, w & 0x1fffffffu, w >> 29, true );
-            } else if ( nf >= 32 || ( nf > 0 && !have_input ) ) {        // fire up to 32 ready pairs
-                const uint32_t cnt = nf < 32 ? nf : 32u;
-                const bool     act = lane < cnt;
-                const uint32_t at  = nf - cnt + lane;
-                nf -= cnt;
-                uint32_t push_a = 0xffffffffu, push_b = 0xffffffffu, follow = 0xffffffffu;   // next round's queue (two), follow-up
-                if ( act ) {
-                    const uint32_t lo = Q.lo[ at ], hi = Q.hi[ at ], st_lo = Q.st_lo[ at ], st_hi = Q.st_hi[ at ], meta = Q.meta[ at ];
-                    const uint32_t deg_lo = meta & 0xfffu, deg_hi = ( meta >> 12 ) & 0xfffu, follows = ( meta >> 24 ) & 7u;
-                    const bool     is_follow = ( meta & TM_FOLLOW ) != 0, chain_hi = ( meta & TM_CHAIN_HI ) != 0;
-                    // claim: the pair's i for a pair found through the queue (the other end's examiner may be firing it too);
-                    // the partner for a follow-up (the chain particle already carries this round's stamp and is ours)
-                    const bool     claim_hi = is_follow && !chain_hi;
-                    const uint32_t c = claim_hi ? hi : lo, st_c = claim_hi ? st_hi : st_lo;
-                    if ( atomicCAS( &R.wr[ c ].state, st_c, ( st_c & ST_TAINT ) | ( r << PC_BITS ) | ( st_c & PC_MASK ) ) == st_c ) {
-                        const float4 ga = __ldcg( reinterpret_cast<const float4 *>( R.dr + lo ) );
-                        const float4 gb = __ldcg( reinterpret_cast<const float4 *>( R.dr + hi ) );
-                        float2      *va = reinterpret_cast<float2 *>( R.dr + lo ) + 2, *vb = reinterpret_cast<float2 *>( R.dr + hi ) + 2;
-                        float2       ua = __ldcg( va ), ub = __ldcg( vb );
-                        const ImpulseTerms T = impulse_terms( contact_geom( ga.x, ga.y, ga.z, gb.x, gb.y, gb.z, dt ), ga.w, gb.w, ua.x, ua.y, ub.x, ub.y );
-                        if ( T.impulse ) {
-                            ua.x = __fadd_rn( ua.x, T.dvx_lo ), ua.y = __fadd_rn( ua.y, T.dvy_lo );
-                            ub.x = __fsub_rn( ub.x, T.dvx_hi ), ub.y = __fsub_rn( ub.y, T.dvy_hi );
-                            __stcg( va, ua );
-                            __stcg( vb, ub );
-                        }
-                        const uint32_t taint = ( st_lo | st_hi ) & ST_TAINT;
-                        const uint32_t nlo = ( st_lo & PC_MASK ) + 1, nhi = ( st_hi & PC_MASK ) + 1;
-                        __stcg( &R.wr[ lo ].state, taint | ( r << PC_BITS ) | nlo );
-                        __stcg( &R.wr[ hi ].state, taint | ( r << PC_BITS ) | nhi );
-                        const bool chain_is_lo = !is_follow || !chain_hi;   // the particle whose chain this warp follows
-                        // the pair's i
-                        if ( nlo >= deg_lo )
-                            *( reinterpret_cast<float2 *>( pv_out + lo ) + 1 ) = ua;   // last contact done: final velocity
-                        else if ( chain_is_lo && ( is_follow ? follows > 1 : EV_FOLLOW > 0 ) )   // `follows` counts this fire too
-                            follow = lo | ( ( is_follow ? follows - 1 : (uint32_t)EV_FOLLOW ) << 29 );
-                        else
-                            push_a = lo;
-                        // the pair's j
-                        if ( nhi >= deg_hi )
-                            *( reinterpret_cast<float2 *>( pv_out + hi ) + 1 ) = ub;
-                        else if ( !chain_is_lo && follows > 1 )
-                            follow = hi | ( ( follows - 1 ) << 29 );
-                        else
-                            push_b = hi;
-                    } else if ( is_follow )
-                        push_a = chain_hi ? hi : lo;   // the partner got claimed by someone else: the chain particle waits for the next round
-                }
-                const unsigned mf = __ballot_sync( 0xffffffffu, follow != 0xffffffffu );
-                if ( follow != 0xffffffffu )
-                    Q.xq[ nx + (uint32_t)__popc( mf & lt ) ] = follow;
-                nx += (uint32_t)__popc( mf );
-                const unsigned ma = __ballot_sync( 0xffffffffu, push_a != 0xffffffffu );
-                if ( push_a != 0xffffffffu )
-                    Q.ob[ nob + (uint32_t)__popc( ma & lt ) ] = push_a;
-                nob += (uint32_t)__popc( ma );
-                const unsigned mb = __ballot_sync( 0xffffffffu, push_b != 0xffffffffu );
-                if ( push_b != 0xffffffffu )
-                    Q.ob[ nob + (uint32_t)__popc( mb & lt ) ] = push_b;
-                nob += (uint32_t)__popc( mb );
-                __syncwarp();
-            } else if ( have_input ) {                                   // examine the next 32 items of the round's queue
-                const size_t i   = chunk * 32 + lane;
-                chunk += nwarps;
-                bool         act = i < items;
-                uint32_t     p   = 0;
-                if ( act ) {
-                    p = r == 1 ? (uint32_t)i : src[ i ];
-                    if ( r == 1 && WB.deg[ p ] == 0 )
-                        act = false;
-                }
-                examine( act, p, 0u, false );
-            } else
-                break;
-        }
-        if ( nob ) {
-            uint32_t base = 0;
-            if ( lane == 0 )
-                base = atomicAdd( d_cnt, nob );
-            base = __shfl_sync( 0xffffffffu, base, 0 );
-            for ( uint32_t t = lane; t < nob; t += 32 )
-                dst[ base + t ] = Q.ob[ t ];
-        }
-        if ( threadIdx.x == 0 && blockIdx.x == 0 )
-            WB.counters[ 4 ] = r;
-        grid.sync();
-    }
-}
-
 // ---- K7b, tile passes: the same wavefront, run inside shared memory on one tile of cells at a time ------------------
 // In a dense packing the dependency DAG is ~60 pairs deep and nearly every particle is active, so global rounds
 // stream the whole state ~60 times with scattered access.  A tile pass instead loads the particles of a square tile of

@@ -198,7 +198,7 @@ def test_wavefront_variants_agree(oracle):
     ref = state_from_scene(sc)
     for _ in range(8):
         oracle.substep(ref, sc.W, sc.H, DT, 0, False)
-    for opts in ({}, {"wave_mode": 0}, {"wave_mode": 2}, {"wave_mode": 4}, {"collide": 3}, {"collide": 3, "wave_mode": 4}, {"wave_passes": -1}, {"wave_passes": -4}, {"wave_passes": -7}, {"wave_passes": 4}):
+    for opts in ({}, {"wave_mode": 0}, {"wave_mode": 2}, {"wave_mode": 3}, {"collide": 3}, {"collide": 3, "wave_mode": 3}, {"wave_passes": -1}, {"wave_passes": -4}, {"wave_passes": -7}, {"wave_passes": 4}):
         p = gpu_store(state_from_scene(sc))
         for k, v in opts.items():
             p.set_option(k, v)
