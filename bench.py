@@ -264,7 +264,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stages = {k: (ms / prof_steps, cnt // prof_steps) for k, (ms, cnt) in p.profile_read().items() if cnt}
     peak, peak_src = measured_peak_gbs()
     dom = max(stages, key=lambda k: stages[k][0]) if stages else None
-    algo = {"integrate_walls_keys": 36.0, "collide": 40.0}.get(dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
+    # algorithmic bytes per particle of each kernel: what that kernel cannot avoid moving
+    algo = {"integrate_walls_keys": 36.0, "collide": 40.0, "resolve_wavefront": 16.0, "canonical_gather": 60.0, "cell_sort": 8.0}.get(
+        dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
@@ -477,7 +479,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         dom = max(stages, key=lambda k: stages[k][0]) if stages else None
         roofline = None
         if dom:
-            algo = {"integrate_walls_keys": 36.0, "collide": 40.0}.get(dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
+            algo = {"integrate_walls_keys": 36.0, "collide": 40.0, "resolve_wavefront": 16.0, "canonical_gather": 60.0, "cell_sort": 8.0}.get(
+                dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
             ach = algo * info.n_window / (stages[dom][0] * 1e-3) / 1e9
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "peak_source": peak_src, "algorithmic_bytes_per_particle": algo,
