@@ -672,12 +672,11 @@ constexpr int TILE2_F    = PPC_TILE2_F;           // fine bins per cell
 constexpr int TILE2_MAXC = 64;                    // staged columns (centre + halo)
 constexpr int TILE2_NB   = TILE2_MAXC * TILE2_F;  // fine bins per staged row
 constexpr int TILE2_BINS = ( TILE_R + 2 ) * TILE2_NB;
-constexpr int TILE2_POOL = 512, TILE2_PLIST = 192;
 constexpr int TILE2_TARGET = PPC_TILE2_TARGET;
 
 struct Tile2Smem {
     float4   cand[ TILE2_CAP ];    // x, y, radius, API index (bits), in storage order
-    uint32_t fend[ TILE2_BINS ];   // after the scatter: end (exclusive) of fine bin f = row * nb + bin in perm (nb = bins per staged row of THIS tile); its begin is fend[f - 1]
+    uint32_t fend[ TILE2_BINS ];   // after the scatter: end (exclusive) of fine bin f = row * TILE2_NB + bin in perm; its begin is fend[f - 1]
     uint16_t perm[ TILE2_CAP ];    // staged indices sorted by (staged row, fine bin)
     uint8_t  mass[ TILE2_CAP ];    // mass as the resolve reads it: truncated to uint8_t (:141-142)
     uint8_t  ccol[ TILE2_CAP ];    // cell column relative to the first staged column
@@ -685,74 +684,12 @@ struct Tile2Smem {
     uint32_t run_g0[ TILE_R + 2 ], run_s0[ TILE_R + 3 ], cen_g0[ TILE_R + 1 ], cen_s0[ TILE_R + 1 ];
     uint32_t wsum[ 16 ];
     uint32_t rmax_bits, fallback;
-    // hits handed from the thread that found them to the compacted second phase (see collide_tile2_body)
-    uint32_t pool[ TILE2_POOL ];     // records: self | staged row << 12 | hits << 16, then the hits
-    uint16_t plist[ TILE2_PLIST ];   // offset of each record in pool (0xffff: not written)
-    uint32_t pool_n, plist_n;
 };
 
 __device__ __forceinline__ int fine_bin( const float x, const float x0, const float inv_w, const int nb ) {
     const float q = __fmul_rn( __fsub_rn( x, x0 ), inv_w );
     int         b = ( q >= 0.0f ) ? ( q < 16777216.0f ? __float2int_rz( q ) : nb ) : 0;   // NaN -> 0
     return b < nb ? b : nb - 1;
-}
-
-// The hits of one centre particle (staged indices | row offset << 16) -> the reference's list order, the position pushes summed
-// in that order, the ordered contact list and the particle's outputs.
-__device__ __forceinline__ void tile2_resolve_hits( Tile2Smem &T, const ParticleSet &S, float4 *__restrict__ pv_out, const GridDims &G, const float dt,
-                                                    const WaveBuffers &WB, const int cy0, const int j, const uint32_t self, const uint32_t gk,
-                                                    uint32_t *stash, const uint32_t nh ) {
-    const float4   me4 = T.cand[ self ];
-    const float    x = me4.x, y = me4.y, r = me4.z;
-    const uint32_t gid = __float_as_uint( me4.w );
-    const int      gy  = cy0 - 1 + j;
-    const uint32_t st0 = ( gy == G.taint_lo || gy == G.taint_hi ) ? ST_TAINT : 0u;   // outermost ghost row of a slab window
-    unsigned long long skey[ TILE_STASH ];
-    // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell.
-    //   pairs (i, me), i < me : key = i
-    //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j
-#pragma unroll 1
-    for ( uint32_t a = 0; a < nh; a++ ) {
-        const uint32_t e = stash[ a ], s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
-        skey[ a ] = g < gid ? (unsigned long long)g
-                            : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
-    }
-    float       X = x, Y = y;
-    const float wme = T.inv_lut[ T.mass[ self ] ];
-#pragma unroll 1
-    for ( uint32_t a = 0; a < nh; a++ ) {
-        uint32_t           best = a;
-        unsigned long long bkey = skey[ a ];
-#pragma unroll 1
-        for ( uint32_t b = a + 1; b < nh; b++ )
-            if ( skey[ b ] < bkey ) {
-                bkey = skey[ b ];
-                best = b;
-            }
-        const uint32_t e = stash[ best ];
-        stash[ best ]    = stash[ a ];
-        skey[ best ]     = skey[ a ];
-        stash[ a ]       = e;
-        skey[ a ]        = bkey;
-        const uint32_t s     = e & 0xffffu;
-        const float4   c     = T.cand[ s ];
-        const bool     me_lo = gid < __float_as_uint( c.w );
-        const float    wq    = T.inv_lut[ T.mass[ s ] ];
-        {   // operands selected by role, one evaluation: lo = the pair's i
-            const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
-                                                          me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
-            if ( P.push ) {   // x + t and x - (-t) are the same float operation; the hi side subtracts its own terms (:152-155)
-                X = me_lo ? __fadd_rn( X, P.dpx_lo ) : __fsub_rn( X, P.dpx_hi );
-                Y = me_lo ? __fadd_rn( Y, P.dpy_lo ) : __fsub_rn( Y, P.dpy_hi );
-            }
-        }
-        const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
-        WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
-    }
-    const float4 old = S.pv[ gk ];
-    pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
-    WB.deg[ gk ]     = (uint16_t)nh;
-    WB.state[ gk ]   = st0;
 }
 
 __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const ParticleSet &S, float4 *__restrict__ pv_out,
@@ -778,12 +715,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             T.cen_s0[ j - 1 ] = m1 - m0;   // length for now
         }
     }
-    const int bins = ( TILE_R + 2 ) * nb;   // only the bins this tile uses are zeroed, scanned and indexed
-    if ( threadIdx.x < TILE2_PLIST )
-        T.plist[ threadIdx.x ] = 0xffffu;
-    if ( threadIdx.x == 0 )
-        T.pool_n = T.plist_n = 0;
-    for ( int f = threadIdx.x; f < bins; f += TILE_THREADS )
+    for ( int f = threadIdx.x; f < ( TILE_R + 2 ) * TILE2_NB; f += TILE_THREADS )
         T.fend[ f ] = 0;
     __syncthreads();
     if ( threadIdx.x == 0 ) {
@@ -832,7 +764,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         T.mass[ t ]      = (uint8_t)( (unsigned)__float2int_rz( a.y ) & 0xffu );
         T.ccol[ t ]      = (uint8_t)( S.key[ g ] - (uint32_t)( cy0 - 1 + j ) * (uint32_t)G.cols - (uint32_t)c0 );
         rmax             = fmaxf( rmax, a.x );
-        atomicAdd( &T.fend[ j * nb + fine_bin( p.x, x0, inv_w, nb ) ], 1u );
+        atomicAdd( &T.fend[ j * TILE2_NB + fine_bin( p.x, x0, inv_w, nb ) ], 1u );
     }
     if ( threadIdx.x < 256 )
         T.inv_lut[ threadIdx.x ] = __fdiv_rn( 1.0f, (float)threadIdx.x );
@@ -846,12 +778,11 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
     // ---- exclusive scan of the bin counts (each thread a contiguous chunk; warp scan; block scan) ----
     {
         constexpr int PER = ( TILE2_BINS + TILE_THREADS - 1 ) / TILE_THREADS;
-        const int     per = ( bins + TILE_THREADS - 1 ) / TILE_THREADS;   // <= PER
-        const int     f0  = threadIdx.x * per;
+        const int     f0  = threadIdx.x * PER;
         uint32_t      loc[ PER ], sum = 0;
 #pragma unroll
         for ( int i = 0; i < PER; i++ ) {
-            loc[ i ] = ( i < per && f0 + i < bins ) ? T.fend[ f0 + i ] : 0u;
+            loc[ i ] = ( f0 + i < TILE2_BINS ) ? T.fend[ f0 + i ] : 0u;
             sum += loc[ i ];
         }
         uint32_t inc = sum;
@@ -876,7 +807,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         uint32_t       run  = base + inc - sum;
 #pragma unroll
         for ( int i = 0; i < PER; i++ ) {
-            if ( i < per && f0 + i < bins )
+            if ( f0 + i < TILE2_BINS )
                 T.fend[ f0 + i ] = run;   // begin of the bin; the scatter below advances it to the end
             run += loc[ i ];
         }
@@ -886,7 +817,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         int j = 0;
         while ( j < TILE_R + 1 && t >= T.run_s0[ j + 1 ] )
             j++;
-        T.perm[ atomicAdd( &T.fend[ j * nb + fine_bin( T.cand[ t ].x, x0, inv_w, nb ) ], 1u ) ] = (uint16_t)t;
+        T.perm[ atomicAdd( &T.fend[ j * TILE2_NB + fine_bin( T.cand[ t ].x, x0, inv_w, nb ) ], 1u ) ] = (uint16_t)t;
     }
     __syncthreads();
     const float R = __uint_as_float( T.rmax_bits );
@@ -908,8 +839,9 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
         const uint32_t st0   = ( gy == G.taint_lo || gy == G.taint_hi ) ? ST_TAINT : 0u;   // outermost ghost row of a slab window
 
-        uint32_t stash[ TILE_STASH ];
-        uint32_t nh = 0;
+        uint32_t           stash[ TILE_STASH ];
+        unsigned long long skey[ TILE_STASH ];
+        uint32_t           nh = 0;
 #pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
             const int ry = gy - 1 + d;
@@ -919,7 +851,7 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
                 continue;
             if ( d == 2 && __fadd_rn( y, reach ) < bot )
                 continue;
-            const int      f_lo = ( j - 1 + d ) * nb + b_lo, f_hi = ( j - 1 + d ) * nb + b_hi;
+            const int      f_lo = ( j - 1 + d ) * TILE2_NB + b_lo, f_hi = ( j - 1 + d ) * TILE2_NB + b_hi;
             const uint32_t rb = f_lo > 0 ? T.fend[ f_lo - 1 ] : 0u, re = T.fend[ f_hi ];
             PPC_UNROLL( PPC_TILE_UNROLL )
             for ( uint32_t q = rb; q < re; q++ ) {
@@ -955,30 +887,51 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
             collide_one_generic<COLLIDE_STASH, false>( S, pv_out, cell_start, G, dt, WB, (size_t)gk );
             continue;
         }
-        // Hand the hits to the compacted second phase when there is room (dilute fields: a few particles per warp have hits,
-        // and resolving them where they were found would run that long path with one or two lanes per warp).
-        const uint32_t li = atomicAdd( &T.plist_n, 1u ), off = atomicAdd( &T.pool_n, nh + 1u );
-        if ( li < (uint32_t)TILE2_PLIST && off + nh + 1u <= (uint32_t)TILE2_POOL ) {
-            T.pool[ off ] = self | ( (uint32_t)j << 12 ) | ( nh << 16 );
-            for ( uint32_t a = 0; a < nh; a++ )
-                T.pool[ off + 1 + a ] = stash[ a ];
-            T.plist[ li ] = (uint16_t)off;
-        } else
-            tile2_resolve_hits( T, S, pv_out, G, dt, WB, cy0, j, self, gk, stash, nh );
-    }
-    __syncthreads();
-    // ---- second phase: one thread per particle that has hits, all lanes busy ----
-    const uint32_t listed = min( T.plist_n, (uint32_t)TILE2_PLIST );
-    for ( uint32_t i = threadIdx.x; i < listed; i += TILE_THREADS ) {
-        const uint32_t off = T.plist[ i ];
-        if ( off == 0xffffu )
-            continue;
-        const uint32_t head = T.pool[ off ], self = head & 0xfffu, nh = head >> 16;
-        const int      j    = (int)( ( head >> 12 ) & 0xfu );
-        uint32_t       stash[ TILE_STASH ];
-        for ( uint32_t a = 0; a < nh; a++ )
-            stash[ a ] = T.pool[ off + 1 + a ];
-        tile2_resolve_hits( T, S, pv_out, G, dt, WB, cy0, j, self, T.run_g0[ j ] + ( self - T.run_s0[ j ] ), stash, nh );
+        // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell.
+        //   pairs (i, me), i < me : key = i
+        //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j
+#pragma unroll 1
+        for ( uint32_t a = 0; a < nh; a++ ) {
+            const uint32_t e = stash[ a ], s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
+            skey[ a ] = g < gid ? (unsigned long long)g
+                                : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
+        }
+        float       X = x, Y = y;
+        const float wme = T.inv_lut[ T.mass[ self ] ];
+#pragma unroll 1
+        for ( uint32_t a = 0; a < nh; a++ ) {
+            uint32_t           best = a;
+            unsigned long long bkey = skey[ a ];
+#pragma unroll 1
+            for ( uint32_t b = a + 1; b < nh; b++ )
+                if ( skey[ b ] < bkey ) {
+                    bkey = skey[ b ];
+                    best = b;
+                }
+            const uint32_t e = stash[ best ];
+            stash[ best ]    = stash[ a ];
+            skey[ best ]     = skey[ a ];
+            stash[ a ]       = e;
+            skey[ a ]        = bkey;
+            const uint32_t s     = e & 0xffffu;
+            const float4   c     = T.cand[ s ];
+            const bool     me_lo = gid < __float_as_uint( c.w );
+            const float    wq    = T.inv_lut[ T.mass[ s ] ];
+            {   // operands selected by role, one evaluation: lo = the pair's i
+                const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
+                                                              me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
+                if ( P.push ) {   // x + t and x - (-t) are the same float operation; the hi side subtracts its own terms (:152-155)
+                    X = me_lo ? __fadd_rn( X, P.dpx_lo ) : __fsub_rn( X, P.dpx_hi );
+                    Y = me_lo ? __fadd_rn( Y, P.dpy_lo ) : __fsub_rn( Y, P.dpy_hi );
+                }
+            }
+            const int jj = j - 1 + (int)( e >> 16 );   // staged row of the partner -> its storage slot
+            WB.inc[ (size_t)a * WB.stride + gk ] = ( T.run_g0[ jj ] + ( s - T.run_s0[ jj ] ) ) | ( me_lo ? INC_LO_FLAG : 0u );
+        }
+        const float4 old = S.pv[ gk ];
+        pv_out[ gk ]     = make_float4( X, Y, old.z, old.w );
+        WB.deg[ gk ]     = (uint16_t)nh;
+        WB.state[ gk ]   = st0;
     }
 }
 
