@@ -246,7 +246,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 p.request_colors()
             p.Update(DT)
             p.CollisionsCheck_Grid(W, H, DT)
-        p.download(mask)
+        p.download_async(mask)   # the frame's copy-back overlaps the substeps of the next frame
+    p.download_wait()            # ... and the last one is waited for inside the timed region
     e1.record(ext)
     e1.synchronize()
     barrier()
@@ -328,7 +329,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "cpu_baseline": cpu,
                 "other_configs": others,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step,
-                        "note": "particlesUpdate + particlesCollisionsCheck_Grid x8, then p_x, p_y, colors copied to the host arrays"},
+                        "note": "particlesUpdate + particlesCollisionsCheck_Grid x8, then p_x, p_y, colors copied to the host arrays "
+                                "(ppc_download_async: a frame's copy overlaps the next frame's substeps; the last copy is waited for inside the timed region)"},
                 "resolve_wavefront": None if wave is None else {"rounds_last_substep": wave[0], "particle_visits_last_substep": wave[1]},
                 "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
@@ -433,7 +435,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     n_down = 0
     for _ in range(frames):
         run(me, tr, SUBSTEPS_PER_FRAME, colour_every=SUBSTEPS_PER_FRAME)
-        n_down = me.sync_host()
+        n_down = me.sync_host_async()   # overlaps the next frame's substeps
+    me.sync_host_wait()
     e1.record(me.stream)
     e1.synchronize()
     barrier()
@@ -507,7 +510,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                     "rank 0 in this job; parallel efficiency = value / (n_gpus x this)", "parallel_efficiency": value / (world * ref_value)},
                 "cpu_baseline": None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12.0 * n_down / SUBSTEPS_PER_FRAME,
-                        "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays"},
+                        "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays (asynchronously: a frame's "
+                                "copy overlaps the next frame's substeps; the last copy is waited for inside the timed region)"},
                 "gpu_launches": int(launches), "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             _, _, line["cpu_baseline"] = time_reference_cpu("slab32m", 2, 1)

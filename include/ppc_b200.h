@@ -101,6 +101,11 @@ void ppc_request_colors( struct Particles_t *p );                     /* MANUAL 
 void ppc_host_modified( struct Particles_t *p );                      /* caller wrote the host arrays directly: re-upload at next call */
 void ppc_download( struct Particles_t *p, unsigned mask );            /* make host arrays current now (blocking) */
 void ppc_synchronize( struct Particles_t *p );                        /* wait for all queued device work */
+/* The same copy-back without blocking: the state as of this call is copied to the host arrays while the substeps that
+ * follow run (second CUDA stream); the host arrays are valid after ppc_download_wait().  This is "a frame is drawn"
+ * overlapped with the computation of the next one. */
+void ppc_download_async( struct Particles_t *p, unsigned mask );
+void ppc_download_wait( struct Particles_t *p );
 
 /* n x { particlesUpdate(dt); particlesCollisionsCheck_Grid(W, H, dt); } without touching host memory;
  * colours are computed on the last substep iff color_last. */
@@ -178,6 +183,8 @@ int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *rec
  * (a drawn frame needs PPC_DL_POS | PPC_DL_COLOR only; mass and radius change owner, never value) */
 enum { PPC_DL_IDS = 8, PPC_DL_MASS_RADIUS = 16 };
 int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, unsigned mask );
+/* non-blocking form (see ppc_download_async); ppc_download_wait() completes it; global_ids should be page-locked */
+int ppc_slab_download_async( struct Particles_t *p, uint32_t *global_ids, unsigned mask );
 
 typedef struct ppc_slab_info_t {
     uint64_t n_owned, own_first, n_window; /* owned particles = sorted slots [own_first, own_first + n_owned) of n_window */

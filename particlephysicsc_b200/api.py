@@ -59,11 +59,11 @@ class SlabInfo(C.Structure):
 REFERENCE_SYMBOLS = ["particlesCreate", "particlesFree", "particlesAddParticle", "particlesRemoveParticle", "particlesUpdate",
                      "particlesCollisionsCheck_Grid"]
 EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_mask", "ppc_request_colors", "ppc_host_modified",
-                     "ppc_download", "ppc_synchronize", "ppc_run_substeps", "ppc_set_option", "ppc_debug_grid_info", "ppc_debug_keys",
+                     "ppc_download", "ppc_download_async", "ppc_download_wait", "ppc_synchronize", "ppc_run_substeps", "ppc_set_option", "ppc_debug_grid_info", "ppc_debug_keys",
                      "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
-SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_info",
+SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_download_async", "ppc_slab_info",
                 "ppc_slab_debug_pairs"]
 SNAPSHOT_SYMBOLS = ["ppc_snapshot_write", "ppc_snapshot_read"]
 
@@ -97,6 +97,8 @@ def load_library() -> C.CDLL:
     L.ppc_host_modified.argtypes, L.ppc_host_modified.restype = [PP], None
     L.ppc_download.argtypes, L.ppc_download.restype = [PP, C.c_uint], None
     L.ppc_synchronize.argtypes, L.ppc_synchronize.restype = [PP], None
+    L.ppc_download_async.argtypes, L.ppc_download_async.restype = [PP, C.c_uint], None
+    L.ppc_download_wait.argtypes, L.ppc_download_wait.restype = [PP], None
     L.ppc_run_substeps.argtypes, L.ppc_run_substeps.restype = [PP, C.c_uint16, C.c_uint16, C.c_float, C.c_int, C.c_int], None
     L.ppc_set_option.argtypes, L.ppc_set_option.restype = [PP, C.c_char_p, C.c_longlong], C.c_int
     L.ppc_debug_grid_info.argtypes, L.ppc_debug_grid_info.restype = [PP, C.POINTER(GridInfo)], C.c_int
@@ -125,6 +127,7 @@ def load_library() -> C.CDLL:
     L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.ppc_slab_finish.restype = C.c_int64
     L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p, C.c_uint], C.c_int
+    L.ppc_slab_download_async.argtypes, L.ppc_slab_download_async.restype = [PP, u32p, C.c_uint], C.c_int
     L.ppc_slab_info.argtypes, L.ppc_slab_info.restype = [PP, C.POINTER(SlabInfo)], C.c_int
     L.ppc_slab_debug_pairs.argtypes, L.ppc_slab_debug_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     _lib = L
@@ -215,6 +218,13 @@ class Particles:
 
     def download(self, mask: int = PPC_DL_ALL) -> None:
         self.lib.ppc_download(C.byref(self.s), mask)
+
+    def download_async(self, mask: int = PPC_DL_ALL) -> None:
+        """Start copying the current state to the host arrays; they are valid after download_wait()."""
+        self.lib.ppc_download_async(C.byref(self.s), mask)
+
+    def download_wait(self) -> None:
+        self.lib.ppc_download_wait(C.byref(self.s))
 
     def synchronize(self) -> None:
         self.lib.ppc_synchronize(C.byref(self.s))

@@ -52,10 +52,15 @@ struct Store {
     bool  pending_colour = false;
     // device
     cudaStream_t stream = nullptr;
+    // asynchronous copy-back ("a frame is drawn" while the next one is computed): host copies run on a second stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t  ev_unpacked = nullptr, ev_copied = nullptr;
+    bool         copy_pending = false;
     ParticleSet  set[ 2 ] = {};
     int          cur = 0;
     float       *api_f[ 6 ] = {};   // px, py, vx, vy, mass, radius in API order (staging for upload / download)
     uchar4      *api_col = nullptr;
+    uint32_t    *api_ids = nullptr;   // slab mode: global indices of the copied-back particles
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
     size_t       cells_cap = 0;
@@ -216,18 +221,55 @@ static void free_particle_arrays( Store *st ) {
         st->api_f[ a ] = nullptr;
     }
     cudaFree( st->api_col );
+    cudaFree( st->api_ids );
     cudaFree( st->slot_of );
     cudaFree( st->sort_keys_a );
     cudaFree( st->sort_keys_b );
     cudaFree( st->sort_vals_b );
     cudaFree( st->scratch );
     st->api_col = nullptr;
+    st->api_ids = nullptr;
     st->slot_of = st->sort_keys_a = st->sort_keys_b = st->sort_vals_b = st->scratch = nullptr;
     st->scratch_words = 0;
 }
 
+// ---- asynchronous copy-back -----------------------------------------------------------------------------------------
+// The unpack kernel (storage order -> staging arrays) runs on the compute stream; the device-to-host copies of the staging
+// arrays run on a second stream, so they overlap the substeps that follow.  Anything that touches the staging arrays or
+// the host arrays again waits first.
+static void copy_wait( Store *st ) {
+    if ( st->copy_pending ) {
+        PPC_CK( cudaStreamSynchronize( st->copy_stream ) );
+        st->copy_pending = false;
+    }
+}
+// Call after the unpack kernel was queued on the compute stream: returns the stream the host copies go to.
+static cudaStream_t copy_stream_after_unpack( Store *st, bool async ) {
+    if ( !async )
+        return st->stream;
+    PPC_CK( cudaEventRecord( st->ev_unpacked, st->stream ) );
+    PPC_CK( cudaStreamWaitEvent( st->copy_stream, st->ev_unpacked, 0 ) );
+    return st->copy_stream;
+}
+static void copy_started( Store *st, bool async ) {
+    if ( async ) {
+        PPC_CK( cudaEventRecord( st->ev_copied, st->copy_stream ) );
+        st->copy_pending = true;
+    }
+}
+// Before the staging arrays are overwritten by a new unpack: the previous copies must have read them.
+static void staging_reuse( Store *st, bool async ) {
+    if ( !st->copy_pending )
+        return;
+    if ( async )
+        PPC_CK( cudaStreamWaitEvent( st->stream, st->ev_copied, 0 ) );   // device-side wait; the host does not block
+    else
+        copy_wait( st );
+}
+
 // (Re)allocate the per-particle device arrays for `cap` particles, keeping the first `keep` storage slots.
 static void resize_particle_arrays( Store *st, size_t cap, size_t keep ) {
+    copy_wait( st );
     ParticleSet old[ 2 ] = { st->set[ 0 ], st->set[ 1 ] };
     for ( int s = 0; s < 2; s++ ) {
         st->set[ s ].pv  = dev_alloc<float4>( cap );
@@ -257,11 +299,13 @@ static void resize_particle_arrays( Store *st, size_t cap, size_t keep ) {
         st->api_f[ a ] = dev_alloc<float>( cap );
     }
     cudaFree( st->api_col );
+    cudaFree( st->api_ids );
     cudaFree( st->slot_of );
     cudaFree( st->sort_keys_a );
     cudaFree( st->sort_keys_b );
     cudaFree( st->sort_vals_b );
     st->api_col     = dev_alloc<uchar4>( cap );
+    st->api_ids     = dev_alloc<uint32_t>( cap );
     st->slot_of     = dev_alloc<uint32_t>( cap );
     st->sort_keys_a = dev_alloc<uint32_t>( cap );
     st->sort_keys_b = dev_alloc<uint32_t>( cap );
@@ -297,6 +341,9 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     st->host_key  = p->mass;
     st->owns_host = owns_host;
     PPC_CK( cudaStreamCreateWithFlags( &st->stream, cudaStreamNonBlocking ) );
+    PPC_CK( cudaStreamCreateWithFlags( &st->copy_stream, cudaStreamNonBlocking ) );
+    PPC_CK( cudaEventCreateWithFlags( &st->ev_unpacked, cudaEventDisableTiming ) );
+    PPC_CK( cudaEventCreateWithFlags( &st->ev_copied, cudaEventDisableTiming ) );
     PPC_CK( cudaEventCreate( &st->ev0 ) );
     PPC_CK( cudaEventCreate( &st->ev1 ) );
     st->d_word = dev_alloc<uint32_t>( 4 );
@@ -328,6 +375,7 @@ static float *const *host_float_arrays( struct Particles_t *p, float *out[ 6 ] )
 static void upload_range( Store *st, struct Particles_t *p, size_t first, size_t count ) {
     if ( count == 0 )
         return;
+    copy_wait( st );   // the staging arrays are shared with the copy-back
     StageTimer T( st, ST_UPLOAD );
     float     *h[ 6 ];
     host_float_arrays( p, h );
@@ -619,24 +667,29 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     st->pre_valid = true;
 }
 
-static void download( Store *st, struct Particles_t *p, unsigned mask ) {
+static void download( Store *st, struct Particles_t *p, unsigned mask, bool async = false ) {
     flush_pending_update( st );
     const size_t n = st->n < p->length ? st->n : p->length;
     if ( n && mask ) {
         StageTimer T( st, ST_DOWNLOAD );
+        staging_reuse( st, async );
         PPC_LAUNCH( k_unpack_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->api_f[ 0 ],
                     st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_col, n, mask );
+        const cudaStream_t cs = copy_stream_after_unpack( st, async );
         if ( mask & PPC_DL_POS ) {
-            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], n * sizeof( float ), cudaMemcpyDeviceToHost, cs ) );
+            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], n * sizeof( float ), cudaMemcpyDeviceToHost, cs ) );
         }
         if ( mask & PPC_DL_VEL ) {
-            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], n * sizeof( float ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], n * sizeof( float ), cudaMemcpyDeviceToHost, cs ) );
+            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], n * sizeof( float ), cudaMemcpyDeviceToHost, cs ) );
         }
         if ( mask & PPC_DL_COLOR )
-            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, cs ) );
+        copy_started( st, async );
     }
+    if ( async )
+        return;
     PPC_CK( cudaStreamSynchronize( st->stream ) );
     check_device_flags( st );
 }
@@ -681,6 +734,10 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         if ( st->host_key != particles->mass )
             continue;
         PPC_CK( cudaStreamSynchronize( st->stream ) );
+        copy_wait( st );
+        cudaStreamDestroy( st->copy_stream );
+        cudaEventDestroy( st->ev_unpacked );
+        cudaEventDestroy( st->ev_copied );
         free_particle_arrays( st );
         cudaFree( st->cell_count );
         cudaFree( st->cell_start );
@@ -813,11 +870,19 @@ extern "C" void ppc_request_colors( struct Particles_t *p ) { store_of( p )->col
 extern "C" void ppc_host_modified( struct Particles_t *p ) { store_of( p )->dirty_all = true; }
 extern "C" void ppc_download( struct Particles_t *p, unsigned mask ) {
     Store *st = store_of( p );
+    copy_wait( st );
     absorb_host_changes( st, p );
     download( st, p, mask );
 }
+extern "C" void ppc_download_async( struct Particles_t *p, unsigned mask ) {
+    Store *st = store_of( p );
+    absorb_host_changes( st, p );
+    download( st, p, mask, true );
+}
+extern "C" void ppc_download_wait( struct Particles_t *p ) { copy_wait( store_of( p ) ); }
 extern "C" void ppc_synchronize( struct Particles_t *p ) {
     Store *st = store_of( p );
+    copy_wait( st );
     PPC_CK( cudaStreamSynchronize( st->stream ) );
     check_device_flags( st );
 }
@@ -997,6 +1062,7 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
     if ( !st->h_slab )
         PPC_CK( cudaHostAlloc( (void **)&st->h_slab, 16 * sizeof( uint32_t ), cudaHostAllocDefault ) );
     const size_t n = p->length;
+    copy_wait( st );
     if ( n ) {
         StageTimer T( st, ST_UPLOAD );
         float     *h[ 6 ];
@@ -1178,38 +1244,58 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     return (int64_t)st->n_own;
 }
 
-extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, unsigned mask ) {
-    Store *st = store_of( p );
-    if ( !st->slab )
-        return -1;
+static int slab_download( Store *st, struct Particles_t *p, uint32_t *global_ids, unsigned mask, bool async ) {
     const size_t n = st->n_own;
     if ( n > p->size )
         return -3;
     if ( n && mask ) {
         StageTimer T( st, ST_DOWNLOAD );
+        staging_reuse( st, async );
         PPC_LAUNCH( k_slab_download, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->own_first, n, st->api_f[ 0 ],
-                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, st->sort_keys_a );
-        const size_t fb = n * sizeof( float );
+                    st->api_f[ 1 ], st->api_f[ 2 ], st->api_f[ 3 ], st->api_f[ 4 ], st->api_f[ 5 ], st->api_col, st->api_ids );
+        const cudaStream_t cs = copy_stream_after_unpack( st, async );
+        const size_t       fb = n * sizeof( float );
         if ( mask & PPC_DL_POS ) {
-            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->p_x, st->api_f[ 0 ], fb, cudaMemcpyDeviceToHost, cs ) );
+            PPC_CK( cudaMemcpyAsync( p->p_y, st->api_f[ 1 ], fb, cudaMemcpyDeviceToHost, cs ) );
         }
         if ( mask & PPC_DL_VEL ) {
-            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->v_x, st->api_f[ 2 ], fb, cudaMemcpyDeviceToHost, cs ) );
+            PPC_CK( cudaMemcpyAsync( p->v_y, st->api_f[ 3 ], fb, cudaMemcpyDeviceToHost, cs ) );
         }
         if ( mask & PPC_DL_MASS_RADIUS ) {
-            PPC_CK( cudaMemcpyAsync( p->mass, st->api_f[ 4 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
-            PPC_CK( cudaMemcpyAsync( p->radius, st->api_f[ 5 ], fb, cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->mass, st->api_f[ 4 ], fb, cudaMemcpyDeviceToHost, cs ) );
+            PPC_CK( cudaMemcpyAsync( p->radius, st->api_f[ 5 ], fb, cudaMemcpyDeviceToHost, cs ) );
         }
         if ( mask & PPC_DL_COLOR )
-            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( p->colors, st->api_col, n * sizeof( uchar4 ), cudaMemcpyDeviceToHost, cs ) );
         if ( ( mask & PPC_DL_IDS ) && global_ids )
-            PPC_CK( cudaMemcpyAsync( global_ids, st->sort_keys_a, n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( global_ids, st->api_ids, n * sizeof( uint32_t ), cudaMemcpyDeviceToHost, cs ) );
+        copy_started( st, async );
     }
-    PPC_CK( cudaStreamSynchronize( st->stream ) );
     p->length = n;
+    return 0;
+}
+
+extern "C" int ppc_slab_download( struct Particles_t *p, uint32_t *global_ids, unsigned mask ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    copy_wait( st );
+    const int rc = slab_download( st, p, global_ids, mask, false );
+    if ( rc != 0 )
+        return rc;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
     return slab_halo_ok( st ) ? 0 : -2;
+}
+
+// The same, without waiting: the copies overlap the substeps that follow; ppc_download_wait() makes the host arrays valid.
+// (global_ids must be page-locked memory, or the copy of the indices blocks.)
+extern "C" int ppc_slab_download_async( struct Particles_t *p, uint32_t *global_ids, unsigned mask ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    return slab_download( st, p, global_ids, mask, true );
 }
 
 extern "C" int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out ) {

@@ -188,6 +188,17 @@ class DeviceSlab:
             raise RuntimeError(f"ppc_slab_download failed ({rc})")
         return self.p.length
 
+    def sync_host_async(self, mask: int = api.PPC_DL_POS | api.PPC_DL_COLOR) -> int:
+        """Start the copy-back of the owned particles and return at once (it overlaps the substeps that follow);
+        sync_host_wait() completes it.  Returns the number of particles being copied."""
+        rc = self.p.lib.ppc_slab_download_async(C.byref(self.p.s), None, mask & ~api.PPC_DL_IDS)
+        if rc != 0:
+            raise RuntimeError(f"ppc_slab_download_async failed ({rc})")
+        return self.p.length
+
+    def sync_host_wait(self) -> None:
+        self.p.lib.ppc_download_wait(C.byref(self.p.s))
+
     def debug_pairs(self) -> np.ndarray:
         n = self.p.lib.ppc_slab_debug_pairs(C.byref(self.p.s), None, 0)
         if n < 0:

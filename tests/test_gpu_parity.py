@@ -555,3 +555,25 @@ def test_snapshot_resumes_bit_exactly(oracle, tmp_path):
     assert_state_bits(gpu_state(a), ref, "snapshot -> oracle")
     a.Free()
     b.Free()
+
+
+def test_async_copy_back_is_a_snapshot(oracle):
+    """ppc_download_async copies the state as of the call, while later substeps run; ppc_download_wait completes it."""
+    sc = scenes.uniform_random(200000, 2.0, 0.4, seed=118, vmax=50.0)
+    a, b = gpu_store(state_from_scene(sc)), gpu_store(state_from_scene(sc))
+    for p in (a, b):
+        p.run_substeps(sc.W, sc.H, DT, 4, True)
+    want = gpu_state(b)                       # blocking copy of the same moment
+    a.download_async(api.PPC_DL_ALL)
+    a.run_substeps(sc.W, sc.H, DT, 4, True)   # overlaps the copy
+    a.download_wait()
+    got = State(*(a.array(n).copy() for n in ("p_x", "p_y", "v_x", "v_y", "mass", "radius", "colors")))
+    assert_state_bits(got, want, "async snapshot")
+    assert np.array_equal(got.rgba, want.rgba)
+    a.download_async(api.PPC_DL_POS)          # a second one re-uses the staging arrays: must wait for the first on the device
+    a.download_async(api.PPC_DL_POS)
+    a.download_wait()
+    b.run_substeps(sc.W, sc.H, DT, 4, True)
+    assert_state_bits(gpu_state(a), gpu_state(b), "state after the overlapped substeps", fields=("px", "py", "vx", "vy"))
+    a.Free()
+    b.Free()
