@@ -100,6 +100,22 @@ def test_slabs_on_one_gpu_equal_the_whole_field(name, make, world, steps, by_loa
     assert travelled >= 1
 
 
+def test_empty_slabs_are_fine():
+    """Slabs that own nothing (the field fills only the upper half of the box) take part in the exchange like any other."""
+    sc = scenes.uniform_random(60000, 2.0, 0.35, seed=407, vmax=200.0)
+    sc.H *= 2
+    want, grid, pairs, rounds = single_gpu(sc, 4)
+    ranks = slab.make_device_slabs(sc, 4, 6)
+    assert ranks[3].info().n_owned == 0 and ranks[2].info().n_owned < 1000
+    for _ in range(4):
+        slab.local_step(ranks, DT)
+    got = gather(ranks, sc.n)
+    for k in want:
+        assert_bits_equal(got[k], want[k], f"empty slabs {k}")
+    for r in ranks:
+        r.free()
+
+
 def test_shallow_halo_is_reported():
     """A halo thinner than the dependency depth cannot guarantee exact velocities: the library says so instead of going on."""
     sc = scenes.uniform_random(100000, 2.0, 0.60, seed=405, vmax=100.0)
