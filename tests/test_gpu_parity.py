@@ -577,3 +577,36 @@ def test_async_copy_back_is_a_snapshot(oracle):
     assert_state_bits(gpu_state(a), gpu_state(b), "state after the overlapped substeps", fields=("px", "py", "vx", "vy"))
     a.Free()
     b.Free()
+
+
+def test_largest_world_of_the_api(oracle):
+    """uint16_t window arguments cap the world at 65,535 px: 5,462 x 5,462 = 29.8M cells of 12 px (25-bit keys) for a sparse
+    field whose particles sit in clumps, on the walls and in the far corner."""
+    n, W, H = 120000, 65535, 65535
+    rng = scenes.Stream(119)
+    s = State.empty(n)
+    cx, cy = rng.unit(300) * (W - 400) + 200, rng.unit(300) * (H - 400) + 200      # 300 clumps of 400 particles
+    k = np.arange(n) % 300
+    s.px[:] = cx[k] + (rng.unit(n) - 0.5) * 260
+    s.py[:] = cy[k] + (rng.unit(n) - 0.5) * 260
+    s.px[:200], s.py[:200] = W - rng.unit(200) * 120, H - rng.unit(200) * 120       # far corner, partly beyond the walls
+    s.px[500:700] = rng.unit(200) * 8                                              # on the left wall
+    s.vx[:] = (rng.unit(n) - 0.5) * 400
+    s.vy[:] = (rng.unit(n) - 0.5) * 400
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 1.5 + rng.unit(n) * 4.5
+    ref = s.copy()
+    p = gpu_store(s)
+    for step in range(3):
+        oracle.update(ref, DT, False)
+        p.Update(DT)
+        want = oracle.collisions_check_grid(ref, W, H, DT, 0, want_grid=True)
+        p.CollisionsCheck_Grid(W, H, DT)
+        got = p.debug_grid()
+        assert (got["cols"], got["rows"]) == (5462, 5462)
+        assert np.array_equal(got["keys"], want["keys"]) and np.array_equal(got["order"], want["order"])
+        assert np.array_equal(got["cell_start"], want["cell_start"])
+        assert np.array_equal(p.debug_pairs(), want["pairs"])
+        assert_state_bits(gpu_state(p), ref, f"largest world step {step}")
+    assert got["keys"].max() >= 5461 * 5462 and len(want["pairs"]) > 5000
+    p.Free()
