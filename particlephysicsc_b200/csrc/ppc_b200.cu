@@ -40,6 +40,7 @@ struct Store {
     bool        dirty_all  = true;
     float       max_radius = 6.0f;   // reference src/particles_solver.c:231
     bool        max_radius_dirty = true;
+    bool        lists_unverified = true;   // particles were uploaded since the contact-list length was last checked synchronously
     // policy
     int      sync_policy   = PPC_SYNC_FRAME;
     unsigned dl_mask       = PPC_DL_ALL;
@@ -75,7 +76,7 @@ struct Store {
     WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
     uint32_t    *wave_n_items = nullptr;
     size_t       wave_items_stride = 0;
-    uint32_t    *h_active = nullptr;   // pinned [2]: particles with contacts, densest tile (per 1024 cells), as of a recent substep
+    uint32_t    *h_active = nullptr;   // pinned [5]: particles with contacts, densest tile (per 1024 cells), -, -, longest unstored contact list, as of a recent substep
     // slab mode (multi-GPU decomposition): this store holds the particles of one slab of cell rows
     bool      slab = false;
     SlabRows  slab_rows = {};
@@ -157,9 +158,34 @@ static void free_wave_buffers( Store *st ) {
     st->wave_cap = 0;
 }
 
-static void ensure_wave_buffers( Store *st ) {
-    if ( st->wave_cap >= st->cap && st->wave.deg )
+// Contact lists are stored with a fixed number of positions per particle (16, or 64 for stores up to 4M particles).  A particle
+// with more contacts than that still resolves correctly -- its list entries are recomputed on demand -- but very slowly, so
+// when a substep reports such lists (heavily overlapping fields: many particles spawned on one spot) the lists are
+// lengthened for the following substeps, as far as 4 GB of list storage go.
+static void grow_contact_lists( Store *st ) {
+    const uint32_t seen = st->h_active[ 4 ];   // a substep or two old
+    if ( !st->wave.deg || seen <= st->wave.maxdeg )
         return;
+    uint32_t want = st->wave.maxdeg;
+    while ( want < seen && want < 4096u )
+        want *= 2;
+    const size_t limit = ( (size_t)4 << 30 ) / ( sizeof( uint32_t ) * ( st->wave_cap ? st->wave_cap : 1 ) );
+    if ( want > limit )
+        want = (uint32_t)limit;
+    if ( want <= st->wave.maxdeg )
+        return;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    cudaFree( st->wave.inc );
+    st->wave.maxdeg   = want;
+    st->wave.inc      = dev_alloc<uint32_t>( st->wave_cap * (size_t)want );
+    st->h_active[ 4 ] = 0;
+}
+
+static void ensure_wave_buffers( Store *st ) {
+    if ( st->wave_cap >= st->cap && st->wave.deg ) {
+        grow_contact_lists( st );
+        return;
+    }
     PPC_CK( cudaStreamSynchronize( st->stream ) );
     free_wave_buffers( st );
     const size_t cap    = st->cap ? st->cap : 1;
@@ -347,9 +373,9 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     PPC_CK( cudaEventCreate( &st->ev0 ) );
     PPC_CK( cudaEventCreate( &st->ev1 ) );
     st->d_word = dev_alloc<uint32_t>( 4 );
-    PPC_CK( cudaHostAlloc( (void **)&st->h_active, 2 * sizeof( uint32_t ), cudaHostAllocDefault ) );
+    PPC_CK( cudaHostAlloc( (void **)&st->h_active, 5 * sizeof( uint32_t ), cudaHostAllocDefault ) );
     st->h_active[ 0 ] = 0xffffffffu;   // unknown yet: assume dense
-    st->h_active[ 1 ] = 0;
+    st->h_active[ 1 ] = st->h_active[ 2 ] = st->h_active[ 3 ] = st->h_active[ 4 ] = 0;
     resize_particle_arrays( st, p->size, 0 );
     g_stores.push_back( st );
     return st;
@@ -376,6 +402,7 @@ static void upload_range( Store *st, struct Particles_t *p, size_t first, size_t
     if ( count == 0 )
         return;
     copy_wait( st );   // the staging arrays are shared with the copy-back
+    st->lists_unverified = true;
     StageTimer T( st, ST_UPLOAD );
     float     *h[ 6 ];
     host_float_arrays( p, h );
@@ -519,10 +546,10 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
-            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 8 * sizeof( uint32_t ), st->stream ) );
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 4, 0, 9 * sizeof( uint32_t ), st->stream ) );
         }
-        const WaveBuffers WB = st->wave;
-        {
+        WaveBuffers WB = st->wave;
+        for ( int attempt = 0; attempt < 2; attempt++ ) {
             StageTimer T( st, ST_COLLIDE );                                            // K7: narrow phase + position pushes
             const unsigned blocks = div_up( n, COLLIDE_THREADS );
             if ( jacobi && st->opt_stash )
@@ -552,6 +579,24 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
                 PPC_LAUNCH( ( k_collide_global<COLLIDE_STASH, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else
                 PPC_LAUNCH( ( k_collide_global<0, false> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
+            // First grid build after particles were uploaded: look at once whether some contact list did not fit the stored
+            // positions (many particles spawned on one spot); if so lengthen the lists and redo the narrow phase now rather
+            // than resolve this substep through the slow on-demand path.  (Later on the same check runs a substep late, async.)
+            if ( jacobi || attempt == 1 || !st->lists_unverified )
+                break;
+            st->lists_unverified = false;
+            uint32_t seen = 0;
+            PPC_CK( cudaMemcpyAsync( &seen, st->wave.counters + 12, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaStreamSynchronize( st->stream ) );
+            if ( seen <= st->wave.maxdeg )
+                break;
+            const uint32_t before = st->wave.maxdeg;
+            st->h_active[ 4 ]     = seen;
+            grow_contact_lists( st );
+            if ( st->wave.maxdeg == before )
+                break;   // no room to lengthen them
+            WB = st->wave;
+            PPC_CK( cudaMemsetAsync( st->wave.counters + 8, 0, 5 * sizeof( uint32_t ), st->stream ) );
         }
         if ( !jacobi ) {
             StageTimer T( st, ST_WAVEFRONT );                                          // K7b: velocities, in the reference's pair order
@@ -561,7 +606,7 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             // are cheaper on the compact queues of the global rounds.  The count is a few substeps old.
             const bool      dense  = *st->h_active == 0xffffffffu || (double)*st->h_active > 0.25 * (double)n;
             const int       passes = ( st->opt_wave_passes < 0 ) ? -st->opt_wave_passes : ( dense ? st->opt_wave_passes : 0 );
-            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 2 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 5 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
             st->wave_hops = passes > 0 ? 0 : 1;
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
                 static bool configured = false;

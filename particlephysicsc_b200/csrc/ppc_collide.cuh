@@ -313,7 +313,8 @@ struct WaveBuffers {
     uint32_t *counters;  // [0..2] rotating totals of still-active particles, [3] error flags, [4] rounds of the last resolve,
                          // [5] tiles with work left after the tile passes, [6..7] particle visits of the last resolve (64-bit),
                          // [8] particles with at least one contact in this substep, [9] densest tile in particles per 1024 cells (from k_collide_tile),
-                         // [10] slab mode: the taint reached an owned particle, [11] rows the taint travelled into the window
+                         // [10] slab mode: the taint reached an owned particle, [11] rows the taint travelled into the window,
+                         // [12] longest contact list that did not fit the stored lists (0: all fit)
 };
 
 // ---- K7, global-memory form: one thread per sorted particle --------------------------------------------------
@@ -343,6 +344,8 @@ __device__ __noinline__ void collide_one_generic( const ParticleSet &S, float4 *
             atomicOr( &WB.counters[ 3 ], 1u );
             cnt = PC_MASK;
         }
+        if ( cnt > WB.maxdeg )   // list longer than what is stored: tell the host, which lengthens the lists for the next substeps
+            atomicMax( &WB.counters[ 12 ], cnt );
         WB.deg[ k ]   = (uint16_t)cnt;
         WB.state[ k ] = initial_state( G, S.key[ k ] );
     }

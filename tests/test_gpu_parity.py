@@ -610,3 +610,37 @@ def test_largest_world_of_the_api(oracle):
         assert_state_bits(gpu_state(p), ref, f"largest world step {step}")
     assert got["keys"].max() >= 5461 * 5462 and len(want["pairs"]) > 5000
     p.Free()
+
+
+def test_heavily_overlapping_clumps(oracle):
+    """Hundreds of contacts per particle (many particles spawned on nearly the same spot): lists longer than the stored
+    positions are recomputed on demand at first, then the library lengthens the stored lists; results stay the reference's."""
+    import time
+    n, W, H = 12000, 3000, 3000
+    rng = scenes.Stream(120)
+    s = State.empty(n)
+    cx, cy = rng.unit(30) * (W - 400) + 200, rng.unit(30) * (H - 400) + 200      # 30 clumps of 400 particles within 90 px
+    k = np.arange(n) % 30
+    s.px[:] = cx[k] + (rng.unit(n) - 0.5) * 90
+    s.py[:] = cy[k] + (rng.unit(n) - 0.5) * 90
+    s.px[:160], s.py[:160] = 1500 + rng.unit(160) * 14, 1500 + rng.unit(160) * 14   # and 160 particles on one spot
+    s.vx[:] = (rng.unit(n) - 0.5) * 100
+    s.vy[:] = (rng.unit(n) - 0.5) * 100
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 1.5 + rng.unit(n) * 4.5
+    ref = s.copy()
+    p = gpu_store(s)
+    times = []
+    for step in range(5):
+        oracle.substep(ref, W, H, DT, 0, False)
+        t0 = time.perf_counter()
+        p.run_substeps(W, H, DT, 1)
+        p.synchronize()
+        times.append(time.perf_counter() - t0)
+        if step == 0:
+            deg = np.bincount(p.debug_pairs().ravel(), minlength=n)
+    assert_state_bits(gpu_state(p), ref, "overlapping clumps")
+    print(f"clumps: up to {deg.max()} contacts per particle in the first substep; seconds per substep {[round(t, 3) for t in times]}")
+    assert deg.max() > 64
+    assert times[-1] < 0.5 * times[0] or times[0] < 0.05   # stored lists took over from the on-demand path
+    p.Free()
