@@ -29,7 +29,7 @@ def single_gpu(sc, steps, options=None):
     rounds = 0
     for _ in range(steps):
         p.run_substeps(sc.W, sc.H, DT, 1)
-        rounds = max(rounds, p.wave_stats()[0])
+        rounds = max(rounds, (p.wave_stats() or (0, 0))[0])
     grid = p.debug_grid()
     pairs = p.debug_pairs()
     p.download(api.PPC_DL_ALL)
@@ -56,6 +56,8 @@ CASES = [
     ("lattice_phi50_w3", lambda: scenes.jittered_lattice(200000, 2.0, 0.50, seed=402, vmax=500.0), 3, 10, False, {}),
     ("pile_w2_by_load", lambda: scenes.polydisperse_pile(150000, seed=403, vmax=20.0), 2, 6, True, {"wave_mode": 0}),
     ("uniform_polling_w2", lambda: scenes.uniform_random(100000, 2.0, 0.30, seed=404, vmax=300.0), 2, 6, False, {"wave_mode": 0}),
+    ("uniform_radix_sort_w3", lambda: scenes.uniform_random(100000, 2.0, 0.30, seed=408, vmax=300.0), 3, 5, False, {"sort": 1}),
+    ("lattice_jacobi_w2", lambda: scenes.jittered_lattice(100000, 2.0, 0.40, seed=409, vmax=300.0), 2, 5, False, {"resolve": 2}),
 ]
 
 
@@ -97,7 +99,7 @@ def test_slabs_on_one_gpu_equal_the_whole_field(name, make, world, steps, by_loa
         for r in ranks:
             r.free()
     print(f"{name}: {rounds} dependency rounds, inexactness mark travelled {travelled} rows")
-    assert travelled >= 1
+    assert travelled >= 1 or options.get("resolve") == 2   # Jacobi needs one ghost row and nothing travels
 
 
 def test_empty_slabs_are_fine():
@@ -189,3 +191,25 @@ def test_two_ranks_over_nccl():
     assert (count == 1).all()
     for k in have:
         assert_bits_equal(have[k], want[k], f"nccl world 2 {k}")
+
+
+def test_colours_travel_with_migrants():
+    """A drawn substep: colours come back per particle exactly as from the single-GPU run, whichever rank owns the particle."""
+    sc = scenes.uniform_random(80000, 2.0, 0.30, seed=410, vmax=400.0)
+    p = api.Particles(sc.n)
+    p.set_sync_policy(api.PPC_SYNC_MANUAL)
+    p.fill(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba)
+    p.run_substeps(sc.W, sc.H, DT, 8, True)
+    p.download(api.PPC_DL_ALL)
+    want = p.array("colors").copy()
+    p.Free()
+    ranks = slab.make_device_slabs(sc, 3, 8)
+    for s in range(8):
+        slab.local_step(ranks, DT, colour=(s == 7))
+    got = np.zeros((sc.n, 4), np.uint8)
+    for r in ranks:
+        d = r.download()
+        got[d["ids"]] = d["colors"]
+        r.free()
+    assert np.array_equal(got, want)
+    assert len(np.unique(want, axis=0)) > 100   # the field is moving: colours are not all alike
