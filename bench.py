@@ -414,17 +414,28 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         return int(t.item())
 
     me, H = make_rank(rank, world, args.settle_halo)
+    me.p.set_option("slab_strict", 0)   # a halo that turns out too thin is counted, then the phase is redone with a wider one
     tr = slab.DistTransport(dist, dev) if dist is not None else None
     halo, rounds, travelled = settle_and_choose_halo(me, tr, group_max)
-    run(me, tr, args.warmup)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    launches0 = api.kernel_launches()
-    ms_total = max_over_ranks(timed(me, tr, args.steps), dist, "cuda")
-    launches = api.kernel_launches() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    halo_retries = 0
+    while True:
+        run(me, tr, args.warmup)
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = api.kernel_launches()
+        ms_total = max_over_ranks(timed(me, tr, args.steps), dist, "cuda")
+        launches = api.kernel_launches() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        if group_max(int(me.info().violations)) == 0 or halo_retries >= 3:
+            break
+        halo_retries += 1   # every rank takes this branch together: widen the halo, restart from the current state, measure again
+        halo += 4
+        me.reinit(halo)
+        me.p.set_option("slab_strict", 0)
+        if tr is not None:
+            tr.reset()
+    exact = group_max(int(me.info().violations)) == 0
     value = whole_job_value(n_per, world, args.steps, ms_total)
 
     # e2e: owned particles copied back to the host arrays every 8th substep (colours computed on that substep)
@@ -494,7 +505,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                 "data": "synthetic",
                 "config": {"workload": descr, "particles_per_gpu": n_per, "particles": n_per * world, "box": [SLAB_W, H],
                            "grid": [info.cols, info.rows], "rows_per_gpu": rows_per, "halo_rows": halo, "dependency_rounds": rounds,
-                           "inexactness_travel_rows": travelled, "dt": DT,
+                           "inexactness_travel_rows": travelled, "halo_retries": halo_retries,
+                           "owned_particles_exact_in_timed_region": exact, "dt": DT,
                            "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
                            "resolve": "sequential-equivalent wavefront (bit-exact)",
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n_per / 1e6),
@@ -536,7 +548,7 @@ def main():
                     help="default: pile16m on one GPU (the configuration the roofline target is stated on), slab32m on several")
     ap.add_argument("--particles-per-gpu", type=int, default=0, help="slab32m only: override 2**25")
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
-    ap.add_argument("--halo-margin", type=int, default=2, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
+    ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -118,6 +118,8 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
  *   "collide"  0 = auto (shared-memory tile kernel with fine x-bins), 1 = global-memory thread-per-particle kernel,
  *              3 = shared-memory tile kernel scanning the whole 3x3 neighbourhood
+ *   "slab_strict"  slab mode: 1 = ppc_slab_begin fails (-2) when the substep just finished was not exact (default); 0 = it only
+ *              counts such substeps (ppc_slab_info), for a harness that prefers to widen the halo and redo a phase
  *   "wave_mode"    global rounds of the wavefront: 1 = event driven on packed records while more than a quarter of the
  *              particles are in contact, else polling (default); 2 = always event driven; 0 = always polling
  *   "wave_passes"  shared-memory tile passes ahead of the (polling) global rounds: 0 = none (default); k = k passes while
@@ -192,6 +194,7 @@ typedef struct ppc_slab_info_t {
     int      own_row_begin, own_row_end, halo_rows, cols, rows;
     uint32_t rounds;                       /* dependency rounds of the last resolve */
     uint32_t taint_rows;                   /* rows the inexactness of the window's outermost rows travelled inwards in the last resolve */
+    uint32_t violations;                   /* substeps since ppc_slab_init in which it reached an owned particle ("slab_strict" 0 counts instead of failing) */
 } ppc_slab_info_t;
 int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out );
 /* candidate pairs (i, j) whose i (lower global index) this rank owns; every pair of the field appears on exactly one rank */

@@ -52,7 +52,7 @@ class GridInfo(C.Structure):
 class SlabInfo(C.Structure):
     _fields_ = [("n_owned", C.c_uint64), ("own_first", C.c_uint64), ("n_window", C.c_uint64), ("row_lo", C.c_int), ("row_hi", C.c_int),
                 ("own_row_begin", C.c_int), ("own_row_end", C.c_int), ("halo_rows", C.c_int), ("cols", C.c_int), ("rows", C.c_int),
-                ("rounds", C.c_uint32), ("taint_rows", C.c_uint32)]
+                ("rounds", C.c_uint32), ("taint_rows", C.c_uint32), ("violations", C.c_uint32)]
 
 
 # every symbol include/ppc_b200.h declares (tests check the library exports all of them)

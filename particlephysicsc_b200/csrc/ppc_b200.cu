@@ -46,7 +46,7 @@ struct Store {
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
-    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -86,7 +86,7 @@ struct Store {
     int       row_lo = 0, row_hi = 0;        // window of the last grid build
     uint32_t *slab_counts = nullptr;         // device [8]: send counts lo/hi, lost, -, pack cursors lo/hi
     uint32_t *h_slab = nullptr;              // pinned [8]
-    uint32_t  slab_own_first = 0, slab_own_end = 0, slab_taint_rows = 0;
+    uint32_t  slab_own_first = 0, slab_own_end = 0, slab_taint_rows = 0, slab_violations = 0;
     int       wave_hops = 1;                 // contacts an error can travel per wavefront round of the engine last used (0: unbounded)
     // last grid
     bool     grid_valid = false, pre_valid = false;
@@ -961,6 +961,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_wave_passes = (int)value;
     else if ( !strcmp( name, "wave_mode" ) )
         st->opt_wave_mode = (int)value;
+    else if ( !strcmp( name, "slab_strict" ) )
+        st->opt_slab_strict = (int)value;
     else
         return -1;
     return 0;
@@ -1123,6 +1125,7 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
     st->own_first  = 0;
     st->n_own      = n;
     st->n          = n;
+    st->slab_violations = 0;
     st->dirty_all  = false;
     st->pending    = false;
     st->col_valid  = true;
@@ -1155,8 +1158,11 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     if ( !st->slab )
         return -1;
     PPC_CK( cudaStreamSynchronize( st->stream ) );
-    if ( st->grid_valid && !slab_halo_ok( st ) )
-        return -2;   // the previous substep's dependency depth exceeded what the halo guarantees: results may be inexact
+    if ( st->grid_valid && !slab_halo_ok( st ) ) {   // the inexactness mark reached an owned particle in the substep just finished
+        st->slab_violations++;
+        if ( st->opt_slab_strict )
+            return -2;
+    }
     const size_t n = st->n_own;
     const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
     StepParams   P = {};
@@ -1357,6 +1363,7 @@ extern "C" int ppc_slab_info( struct Particles_t *p, ppc_slab_info_t *out ) {
     out->rounds = rounds;
     slab_halo_ok( st );
     out->taint_rows = st->slab_taint_rows;
+    out->violations = st->slab_violations;
     return 0;
 }
 
