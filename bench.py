@@ -351,11 +351,21 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    n_per, descr = WORKLOADS["slab32m"]
+    # weak scaling: BASELINE configs[3], every rank generates its own slab; strong scaling: one of the single-GPU fields
+    # (e.g. the 16M pile), generated identically on every rank and cut into slabs of equal particle count
+    split = args.workload != "slab32m"
+    n_per, descr = WORKLOADS[args.workload]
     n_per = args.particles_per_gpu or n_per
     rows_per = max(8, int(round(SLAB_ROWS_PER_GPU * n_per / float(1 << 25))))
+    n_total = n_per if split else n_per * world
+    opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
+    whole = make_scene(args.workload, n_per) if split else None
+    box_w = whole.W if split else SLAB_W
 
     def make_rank(k: int, nranks: int, halo: int):
+        if split:
+            r = slab.make_device_slabs(whole, nranks, halo, device_of=lambda _: local_rank, only_rank=k, options=opts, by_load=True)[0]
+            return r, whole.H
         H = rows_per * SLAB_CELL * nranks
         sc = scenes.uniform_slab(n_per, SLAB_RADIUS, SLAB_W, H, k * rows_per * SLAB_CELL, (k + 1) * rows_per * SLAB_CELL,
                                  seed=0x5EED0004 + 0x100 * k)
@@ -363,7 +373,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         ghosts = int(2.2 * halo * n_per / rows_per)
         cap = int(1.15 * (n_per + 3 * ghosts)) + 65536
         r = slab.DeviceSlab(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba, ids, SLAB_W, H, 6.0, (k * rows_per, (k + 1) * rows_per), halo,
-                            capacity=cap, device=local_rank, options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt})
+                            capacity=cap, device=local_rank, options=opts)
         return r, H
 
     def barrier():
@@ -436,7 +446,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         if tr is not None:
             tr.reset()
     exact = group_max(int(me.info().violations)) == 0
-    value = whole_job_value(n_per, world, args.steps, ms_total)
+    value = n_total * args.steps / (ms_total * 1e-3)
 
     # e2e: owned particles copied back to the host arrays every 8th substep (colours computed on that substep)
     frames = max(1, args.steps // SUBSTEPS_PER_FRAME)
@@ -452,7 +462,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     e1.synchronize()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), dist, "cuda")
-    e2e_value = n_per * world * frames * SUBSTEPS_PER_FRAME / (e2e_ms * 1e-3)
+    e2e_value = n_total * frames * SUBSTEPS_PER_FRAME / (e2e_ms * 1e-3)
 
     # per-stage times of this rank (serialised) and exchange volume
     prof_steps = min(args.steps, 8)
@@ -484,7 +494,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         run(solo, None, args.steps)
         e1.record(solo.stream)
         e1.synchronize()
-        ref_value = n_per * args.steps / (e0.elapsed_time(e1) * 1e-3)
+        ref_value = ( n_total if split else n_per ) * args.steps / (e0.elapsed_time(e1) * 1e-3)
         solo.free()
     if dist is not None:
         dist.barrier()
@@ -499,11 +509,11 @@ def run_slab(args, rank: int, world: int, local_rank: int):
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                         "peak_source": peak_src, "algorithmic_bytes_per_particle": algo,
                         "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
-        substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * n_per * args.steps / (ms_total * 1e-3) / 1e9
+        substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * (n_total / world) * args.steps / (ms_total * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic",
-                "config": {"workload": descr, "particles_per_gpu": n_per, "particles": n_per * world, "box": [SLAB_W, H],
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if split else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": descr, "particles_per_gpu": n_total // world, "particles": n_total, "box": [box_w, H],
                            "grid": [info.cols, info.rows], "rows_per_gpu": rows_per, "halo_rows": halo, "dependency_rounds": rounds,
                            "inexactness_travel_rows": travelled, "halo_retries": halo_retries,
                            "owned_particles_exact_in_timed_region": exact, "dt": DT,
@@ -518,8 +528,11 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                 "roofline_substep": {"bound": "hbm", "achieved": substep_gbs, "peak": peak, "unit": "GB/s", "frac": substep_gbs / peak,
                                      "note": "40 B x owned particles x substeps / time, whole substep, per GPU"},
                 "scaling_reference": None if ref_value is None else {
-                    "n_gpus": 1, "value": ref_value, "unit": UNIT, "note": "the same per-GPU workload as one slab on one GPU, measured by "
-                    "rank 0 in this job; parallel efficiency = value / (n_gpus x this)", "parallel_efficiency": value / (world * ref_value)},
+                    "n_gpus": 1, "value": ref_value, "unit": UNIT,
+                    "note": ("the whole field as one slab on one GPU, measured by rank 0 in this job; parallel efficiency = value / (n_gpus x this)"
+                             if split else "the same per-GPU workload as one slab on one GPU, measured by rank 0 in this job; "
+                             "parallel efficiency = value / (n_gpus x this)"),
+                    "parallel_efficiency": value / (world * ref_value)},
                 "cpu_baseline": None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12.0 * n_down / SUBSTEPS_PER_FRAME,
                         "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays (asynchronously: a frame's "
@@ -550,6 +563,7 @@ def main():
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
     ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--replicas", action="store_true", help="with --gpus N and a single-GPU workload: N independent copies instead of N slabs of one field")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -569,7 +583,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
-    if args.workload == "slab32m":
+    if args.workload == "slab32m" or (world > 1 and not args.replicas):
         run_slab(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
