@@ -506,7 +506,13 @@ def run_slab(args, rank: int, world: int, local_rank: int):
             algo = {"integrate_walls_keys": 36.0, "collide": 40.0, "resolve_wavefront": 16.0, "canonical_gather": 60.0, "cell_sort": 8.0}.get(
                 dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
             ach = algo * info.n_window / (stages[dom][0] * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            traffic = None
+            try:   # bytes per launch from the ncu --set full capture of one 2**25-particle slab (profiles/)
+                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                    traffic = json.load(f).get("slab32m", {}).get(dom) if (not split and n_per == 1 << 25) else None
+            except Exception:
+                traffic = None
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                         "peak_source": peak_src, "algorithmic_bytes_per_particle": algo,
                         "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
         substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * (n_total / world) * args.steps / (ms_total * 1e-3) / 1e9
