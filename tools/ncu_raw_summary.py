@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""One CSV line per profiled kernel of an ncu report (time, DRAM bytes, instructions, lane occupancy, issue activity, L2 hit
+rate ...): the summaries committed under profiles/.
+
+    python tools/ncu_raw_summary.py gpurun_out/prof.ncu-rep > profiles/<name>.csv
+"""
 import csv,sys,subprocess,io
 rep=sys.argv[1]
 out=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
