@@ -34,6 +34,7 @@ static const char *k_stage_names[ ST_COUNT ] = { "integrate_walls_keys", "cell_s
 struct Store {
     // identity / host side
     const void *host_key   = nullptr;   // particles->mass
+    int         device     = 0;         // the CUDA device this store lives on (ppc_set_device at creation time)
     bool        owns_host  = false;
     size_t      cap        = 0;   // capacity of host and device arrays (particles->size)
     size_t      n          = 0;   // particles resident on the device: API indices [0, n)
@@ -99,7 +100,7 @@ struct Store {
 };
 
 static std::vector<Store *> g_stores;
-static int                  g_device = -1;
+static int                  g_device = -1;   // device of the stores created next (ppc_set_device / $PPC_DEVICE / 0)
 
 static void select_device() {
     if ( g_device < 0 ) {
@@ -364,6 +365,7 @@ static void ensure_cells( Store *st, size_t cells ) {
 static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     select_device();
     Store *st     = new Store();
+    st->device    = g_device;
     st->host_key  = p->mass;
     st->owns_host = owns_host;
     PPC_CK( cudaStreamCreateWithFlags( &st->stream, cudaStreamNonBlocking ) );
@@ -384,8 +386,10 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
 // Find the device mirror of a caller's struct; adopt arrays we did not allocate (a harness that filled its own).
 static Store *store_of( struct Particles_t *p ) {
     for ( Store *st : g_stores )
-        if ( st->host_key == p->mass )
-            return st;
+        if ( st->host_key == p->mass ) {
+            PPC_CK( cudaSetDevice( st->device ) );   // several stores on several GPUs in one process (or a host framework that
+            return st;                               // switches devices between calls): always work on this store's device
+        }
     Store *st     = new_store( p, false );
     st->dirty_all = true;
     return st;
@@ -778,6 +782,7 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         Store *st = g_stores[ k ];
         if ( st->host_key != particles->mass )
             continue;
+        PPC_CK( cudaSetDevice( st->device ) );
         PPC_CK( cudaStreamSynchronize( st->stream ) );
         copy_wait( st );
         cudaStreamDestroy( st->copy_stream );

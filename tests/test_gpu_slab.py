@@ -213,3 +213,20 @@ def test_colours_travel_with_migrants():
         r.free()
     assert np.array_equal(got, want)
     assert len(np.unique(want, axis=0)) > 100   # the field is moving: colours are not all alike
+
+
+def test_slabs_on_two_gpus_in_one_process():
+    """Stores on different devices in one process: every entry point works on its own store's device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = scenes.uniform_random(200000, 2.0, 0.30, seed=411, vmax=300.0)
+    want, _, _, rounds = single_gpu(sc, 6)
+    ranks = slab.make_device_slabs(sc, 2, 2 * rounds + 4, device_of=lambda k: k)
+    for _ in range(6):
+        slab.local_step(ranks, DT)
+    got = gather(ranks, sc.n)
+    for k in want:
+        assert_bits_equal(got[k], want[k], f"two devices, one process: {k}")
+    for r in ranks:
+        r.free()
