@@ -35,6 +35,7 @@ struct Store {
     // identity / host side
     const void *host_key   = nullptr;   // particles->mass
     int         device     = 0;         // the CUDA device this store lives on (ppc_set_device at creation time)
+    bool        tile_attr_set = false, wtile_attr_set = false;   // dynamic shared-memory limits of the tile kernels set on that device
     bool        owns_host  = false;
     size_t      cap        = 0;   // capacity of host and device arrays (particles->size)
     size_t      n          = 0;   // particles resident on the device: API indices [0, n)
@@ -561,11 +562,10 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             else if ( jacobi )
                 PPC_LAUNCH( ( k_collide_global<0, true> ), blocks, COLLIDE_THREADS, 0, st->stream, S, O.pv, st->cell_start, n, G, dt, WB );
             else if ( st->opt_collide != 1 && st->opt_stash ) {   // shared-memory tile kernels
-                static bool configured = false;
-                if ( !configured ) {
+                if ( !st->tile_attr_set ) {   // function attributes are per device: once per store
                     PPC_CK( cudaFuncSetAttribute( k_collide_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( TileSmem ) ) );
                     PPC_CK( cudaFuncSetAttribute( k_collide_tile2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( Tile2Smem ) ) );
-                    configured = true;
+                    st->tile_attr_set = true;
                 }
                 const bool   bins     = st->opt_collide != 3;   // fine x-bins (default) or the plain 3x3 scan
                 const double per_cell = (double)n / (double)G.cells;
@@ -613,10 +613,9 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 5 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
             st->wave_hops = passes > 0 ? 0 : 1;
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
-                static bool configured = false;
-                if ( !configured ) {
+                if ( !st->wtile_attr_set ) {
                     PPC_CK( cudaFuncSetAttribute( k_wave_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( WaveTileSmem ) ) );
-                    configured = true;
+                    st->wtile_attr_set = true;
                 }
                 const int    tw  = WTILE_TW;   // fixed; dense tiles subdivide themselves (see k_wave_plan)
                 const int    txn = ( G.cols + tw / 2 + tw - 1 ) / tw, tyn = ( G.rows + tw / 2 + tw - 1 ) / tw;
