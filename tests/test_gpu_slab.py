@@ -230,3 +230,18 @@ def test_slabs_on_two_gpus_in_one_process():
         assert_bits_equal(got[k], want[k], f"two devices, one process: {k}")
     for r in ranks:
         r.free()
+
+
+def test_cpp_host_drives_the_slabs_through_the_c_abi():
+    """examples/slab_multi_gpu.cu: no Python, no torch in the loop -- a C++ host cuts a field into slabs (spread over the GPUs
+    there are), moves the exchange buffers with cudaMemcpyPeer, and compares every particle with the single-GPU run."""
+    import subprocess
+    exe = os.path.join(ROOT, "examples", "_bin", "slab_multi_gpu")
+    if not os.path.exists(exe):
+        sys.path.insert(0, ROOT)
+        import __graft_entry__ as g
+        g.build_examples()
+    out = subprocess.run([exe, "4", "300000", "6"], capture_output=True, text=True, timeout=600)
+    print(out.stdout[-600:], out.stderr[-300:])
+    assert out.returncode == 0, out.stdout[-400:] + out.stderr[-400:]
+    assert "0 differ from the single-GPU run" in out.stdout
