@@ -1,7 +1,7 @@
 /*
  * slab_multi_gpu.cu -- the slab decomposition driven from C++ through the C ABI alone (no Python, no torch, no NCCL):
  * one process, one slab store per slab, slab k on GPU k % (number of GPUs); the exchange buffers move with
- * cudaMemcpyPeerAsync.  (bench.py does the same with one PROCESS per GPU and NCCL send/recv; the C calls are identical.)
+ * cudaMemcpyPeerAsync on the receiving store's stream.  (bench.py does the same with one PROCESS per GPU and NCCL send/recv; the C calls are identical.)
  *
  * The field is also run whole on GPU 0 through the reference's own entry points, and the two results are compared
  * particle by particle: the program exits 0 only if every position and velocity is bit-identical.
@@ -133,10 +133,13 @@ int main( int argc, char **argv ) {
             Slab          &sl = S[ k ];
             const uint64_t from_lo = k > 0 ? S[ k - 1 ].counts[ 1 ] : 0, from_hi = k + 1 < slabs ? S[ k + 1 ].counts[ 0 ] : 0;
             ensure( sl, &sl.recv[ 0 ], sl.cap[ 2 ], from_lo ), ensure( sl, &sl.recv[ 1 ], sl.cap[ 3 ], from_hi );
+            // on the receiving store's own stream (ppc_stream), so that ppc_slab_finish is ordered behind the copies; the senders
+            // were synchronised above
+            cudaStream_t stream = (cudaStream_t)ppc_stream( &sl.p );
             if ( from_lo )
-                CK( cudaMemcpyPeer( sl.recv[ 0 ], sl.device, S[ k - 1 ].send[ 1 ], S[ k - 1 ].device, from_lo * PPC_SLAB_RECORD_BYTES ) );
+                CK( cudaMemcpyPeerAsync( sl.recv[ 0 ], sl.device, S[ k - 1 ].send[ 1 ], S[ k - 1 ].device, from_lo * PPC_SLAB_RECORD_BYTES, stream ) );
             if ( from_hi )
-                CK( cudaMemcpyPeer( sl.recv[ 1 ], sl.device, S[ k + 1 ].send[ 0 ], S[ k + 1 ].device, from_hi * PPC_SLAB_RECORD_BYTES ) );
+                CK( cudaMemcpyPeerAsync( sl.recv[ 1 ], sl.device, S[ k + 1 ].send[ 0 ], S[ k + 1 ].device, from_hi * PPC_SLAB_RECORD_BYTES, stream ) );
             ppc_slab_finish( &sl.p, dt, sl.recv[ 0 ], from_lo, sl.recv[ 1 ], from_hi, 0, nullptr );
         }
     }
