@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU acceptance check: the slab-decomposed run equals the single-GPU run of the whole field.
 
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/slab_equivalence.py [--n 16777216] [--steps 8]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/slab_equivalence.py [--particles 16777216] [--steps 8]
 
 Every rank runs its slab over NCCL neighbour exchange; rank 0 also runs the whole field on its GPU through the ordinary entry
 points.  Compared: an order-independent 64-bit digest of (global index, p_x, p_y, v_x, v_y bit patterns) over all particles,
@@ -33,7 +33,7 @@ def main():
     import torch
     import torch.distributed as dist
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=1 << 24)
+    ap.add_argument("--particles", dest="n", type=int, default=1 << 24)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--phi", type=float, default=0.30)
     ap.add_argument("--halo", type=int, default=8)
