@@ -49,8 +49,6 @@ def main():
         slab.slab_step(me, tr, DT)
         travelled = max(travelled, int(me.info().taint_rows))
     d = me.download()
-    mine = torch.tensor([digest(d["ids"], d["p_x"], d["p_y"], d["v_x"], d["v_y"]) & 0x7FFFFFFFFFFFFFFF, len(d["ids"]), travelled, int(d["halo_ok"])],
-                        dtype=torch.int64, device="cuda")
     # digests are sums modulo 2^64; add them as two 32-bit halves so that int64 all_reduce cannot overflow
     full = digest(d["ids"], d["p_x"], d["p_y"], d["v_x"], d["v_y"])
     parts = torch.tensor([full & 0xFFFFFFFF, full >> 32, len(d["ids"]), int(d["halo_ok"])], dtype=torch.int64, device="cuda")
