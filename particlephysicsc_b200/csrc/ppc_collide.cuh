@@ -842,9 +842,8 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
         const uint32_t st0   = ( gy == G.taint_lo || gy == G.taint_hi ) ? ST_TAINT : 0u;   // outermost ghost row of a slab window
 
-        uint32_t           stash[ TILE_STASH ];
-        unsigned long long skey[ TILE_STASH ];
-        uint32_t           nh = 0;
+        uint32_t stash[ TILE_STASH ];
+        uint32_t nh = 0;
 #pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
             const int ry = gy - 1 + d;
@@ -893,29 +892,33 @@ __device__ __forceinline__ void collide_tile2_body( Tile2Smem &T, const Particle
         // list order: pairs (i, me) by ascending i, then pairs (me, j) by scan cell, descending index inside a cell.
         //   pairs (i, me), i < me : key = i
         //   pairs (me, j), j > me : key = 2^48 | scan cell << 32 | ~j
-#pragma unroll 1
-        for ( uint32_t a = 0; a < nh; a++ ) {
-            const uint32_t e = stash[ a ], s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
-            skey[ a ] = g < gid ? (unsigned long long)g
-                                : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
-        }
+        // The keys are recomputed from the staged data when two hits are compared (a particle has a handful of hits), rather than
+        // kept in a per-thread array: thread-local arrays live in local memory, which is most of this kernel's memory traffic.
+        auto sort_key = [ & ]( const uint32_t e ) -> unsigned long long {
+            const uint32_t s = e & 0xffffu, g = __float_as_uint( T.cand[ s ].w );
+            return g < gid ? (unsigned long long)g
+                           : ( 1ull << 48 ) | ( (unsigned long long)( ( e >> 16 ) * 128u + T.ccol[ s ] ) << 32 ) | ( 0xffffffffu - g );
+        };
         float       X = x, Y = y;
         const float wme = T.inv_lut[ T.mass[ self ] ];
 #pragma unroll 1
         for ( uint32_t a = 0; a < nh; a++ ) {
-            uint32_t           best = a;
-            unsigned long long bkey = skey[ a ];
+            uint32_t           best = a, e = stash[ a ];
+            unsigned long long bkey = sort_key( e );
 #pragma unroll 1
-            for ( uint32_t b = a + 1; b < nh; b++ )
-                if ( skey[ b ] < bkey ) {
-                    bkey = skey[ b ];
+            for ( uint32_t b = a + 1; b < nh; b++ ) {
+                const uint32_t           eb = stash[ b ];
+                const unsigned long long kb = sort_key( eb );
+                if ( kb < bkey ) {
+                    bkey = kb;
                     best = b;
+                    e    = eb;
                 }
-            const uint32_t e = stash[ best ];
-            stash[ best ]    = stash[ a ];
-            skey[ best ]     = skey[ a ];
-            stash[ a ]       = e;
-            skey[ a ]        = bkey;
+            }
+            if ( best != a ) {
+                stash[ best ] = stash[ a ];
+                stash[ a ]    = e;
+            }
             const uint32_t s     = e & 0xffffu;
             const float4   c     = T.cand[ s ];
             const bool     me_lo = gid < __float_as_uint( c.w );
