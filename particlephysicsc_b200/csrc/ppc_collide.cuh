@@ -322,8 +322,10 @@ struct WaveBuffers {
 // JACOBI = false: positions only; the contact list and the contact count go to the wavefront buffers.
 // One particle, generic path: candidates straight from global memory, one thread does everything.
 template <int STASH, bool JACOBI>
-__device__ __noinline__ void collide_one_generic( const ParticleSet &S, float4 *__restrict__ pv_out, const uint32_t *__restrict__ cell_start,
-                                                     const GridDims &G, const float dt, const WaveBuffers &WB, const size_t k ) {
+// (Arguments by value: this function is not inlined, and references would force the callers' copies of the kernel parameters
+// into local memory for the whole kernel, not just around the rare calls.)
+__device__ __noinline__ void collide_one_generic( const ParticleSet S, float4 *__restrict__ pv_out, const uint32_t *__restrict__ cell_start,
+                                                     const GridDims G, const float dt, const WaveBuffers WB, const size_t k ) {
     uint32_t             cnt = 0;
     const Self           me  = load_self( S, k );
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
