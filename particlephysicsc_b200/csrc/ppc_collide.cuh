@@ -1159,8 +1159,15 @@ __global__ void __launch_bounds__( 256 ) k_wave_pack( const ParticleSet S, const
 
 __device__ __forceinline__ uint32_t rec_head( const ParticleSet &S, const GlobalAccessor &acc, const GridDims &G, const WaveBuffers &WB,
                                               const WaveRec &w, const uint32_t k, const uint32_t pc ) {
-    if ( pc < (uint32_t)WREC_INLINE )
-        return w.c[ pc ];
+    if ( pc < (uint32_t)WREC_INLINE ) {   // selects, not w.c[ pc ]: a dynamically indexed member would put every loaded record into local memory
+        uint32_t v = w.c[ 0 ];
+        v          = pc == 1 ? w.c[ 1 ] : v;
+        v          = pc == 2 ? w.c[ 2 ] : v;
+        v          = pc == 3 ? w.c[ 3 ] : v;
+        v          = pc == 4 ? w.c[ 4 ] : v;
+        v          = pc == 5 ? w.c[ 5 ] : v;
+        return v;
+    }
     if ( w.deg <= WB.maxdeg )
         return WB.inc[ (size_t)pc * WB.stride + k ];
     return nth_contact( acc, G, load_self( S, k ), S.key[ k ], pc );
