@@ -1276,7 +1276,12 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                 // pair (cur, x) may fire right away iff x has not advanced in this round (its velocity was last
                                 // written before the previous grid barrier, so it is visible) and x's head is that same pair --
                                 // then no other thread can fire it: an examiner of x sees cur's stamp and backs off.
-                                const WaveRec &C   = p_lo ? A : B;   // contacts of the cursor particle
+                                WaveRec C;   // contacts of the cursor particle, selected field by field: a reference chosen at run time
+                                             // between A and B would force both records into local memory
+                                C.state = 0u, C.deg = deg_lo;
+#pragma unroll
+                                for ( int ci = 0; ci < WREC_INLINE; ci++ )
+                                    C.c[ ci ] = p_lo ? A.c[ ci ] : B.c[ ci ];
                                 const uint32_t cur = lo, cdeg = deg_lo;
                                 uint32_t       cpc = ( st_lo & PC_MASK ) + 1;
                                 float2         uc  = ua;
