@@ -1181,7 +1181,7 @@ __device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
 }
 
 #ifndef PPC_EV_MINBLOCKS
-#define PPC_EV_MINBLOCKS 6
+#define PPC_EV_MINBLOCKS 4   // 64 registers: measured on the 16M pile 9.3 / 7.8 / 7.4 / 7.1 / 8.1 / 10.5 ms with 8 / 6 / 5 / 4 / 3 / 2 CTAs per SM (spills vs loads in flight)
 #endif
 constexpr int EV_THREADS = 256;
 #ifndef PPC_EV_FOLLOW
