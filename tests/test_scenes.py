@@ -70,3 +70,27 @@ def test_snapshot_file_round_trip(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         scenes.read_snapshot(path)
+
+
+def test_uniform_slab_stays_inside_its_rows():
+    """One rank's share of the configs[3] field: every particle lies in the rank's own cell rows and inside the walls."""
+    import numpy as np
+    from particlephysicsc_b200 import scenes
+    W, H, cell = 45916, 478 * 12 * 4, 12.0
+    for k in range(4):
+        sc = scenes.uniform_slab(50000, 1.0, W, H, k * 478 * cell, (k + 1) * 478 * cell, seed=0x5EED0004 + 0x100 * k)
+        rows = np.floor(sc.py / np.float32(cell)).astype(int)
+        assert rows.min() >= k * 478 and rows.max() < (k + 1) * 478
+        assert sc.px.min() >= 1.0 and sc.px.max() <= W - 1.0 and sc.py.min() >= 1.0 and sc.py.max() <= H - 1.0
+        assert (sc.W, sc.H) == (W, H) and sc.n == 50000
+
+
+def test_bench_workloads_build_small():
+    """bench.make_scene for every workload name, at a small size (the generators behind the benchmark lines)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    for name in bench.WORKLOADS:
+        sc = bench.make_scene(name, 1 << 14)
+        assert sc.n == 1 << 14 and sc.W <= 65535 and sc.H <= 65535 and sc.radius.min() > 0
