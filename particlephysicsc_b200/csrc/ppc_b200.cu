@@ -652,7 +652,11 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
                 const int want = (int)div_up( n, EV_THREADS );
                 if ( grid > want )
                     grid = want;
-                void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&R };
+                // Chain following trades rounds for divergence: on large fields a round is throughput bound and short chains win
+                // (16M pile: 7.9 / 6.6 / 6.5 / 6.9 / 7.2 ms with 0 / 1 / 2 / 4 / 6 pairs followed); a small, deeply dependent field
+                // (the reference's debug scene: 1,500 rounds of ~18 us) is bound by the number of rounds and wants long ones.
+                int   follow = n > ( (size_t)1 << 21 ) ? 2 : EV_FOLLOW;
+                void *args[] = { (void *)&S, (void *)&pv_out, (void *)&cs, (void *)&n_arg, (void *)&G, (void *)&dt, (void *)&WB, (void *)&R, (void *)&follow };
                 PPC_CK( cudaLaunchCooperativeKernel( (const void *)k_resolve_events, dim3( grid ), dim3( EV_THREADS ), args, 0, st->stream ) );
                 ++g_launches;
             } else {   // polling rounds (after tile passes, or "wave_mode"=0)

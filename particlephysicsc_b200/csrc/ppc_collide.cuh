@@ -1183,16 +1183,19 @@ __device__ __forceinline__ WaveRec load_wave_rec( const WaveRec *p ) {
 #ifndef PPC_EV_MINBLOCKS
 #define PPC_EV_MINBLOCKS 4   // 64 registers: measured on the 16M pile 9.3 / 7.8 / 7.4 / 7.1 / 8.1 / 10.5 ms with 8 / 6 / 5 / 4 / 3 / 2 CTAs per SM (spills vs loads in flight)
 #endif
-constexpr int EV_THREADS = 256;
+#ifndef PPC_EV_THREADS
+#define PPC_EV_THREADS 256
+#endif
+constexpr int EV_THREADS = PPC_EV_THREADS;
 #ifndef PPC_EV_FOLLOW
 #define PPC_EV_FOLLOW 6
 #endif
-constexpr int EV_FOLLOW  = PPC_EV_FOLLOW;   // pairs one thread may fire in a row along a chain
+constexpr int EV_FOLLOW  = PPC_EV_FOLLOW;   // most pairs one thread may fire in a row along a chain (the launch passes the actual limit)
 constexpr int EV_BUF     = ( EV_FOLLOW + 2 ) * EV_THREADS * 2;   // per-CTA staging of queue pushes: one global atomic per flush
 
 __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_events( const ParticleSet S, float4 *pv_out, const uint32_t *__restrict__ cell_start,
                                                                   const size_t n, const GridDims G, const float dt, const WaveBuffers WB,
-                                                                  const WaveRecs R ) {
+                                                                  const WaveRecs R, const int follow_max ) {
     namespace cg        = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const GlobalAccessor acc{ S.pv, S.rm, S.gid, cell_start };
@@ -1285,7 +1288,7 @@ __global__ void __launch_bounds__( EV_THREADS, PPC_EV_MINBLOCKS ) k_resolve_even
                                 const uint32_t cur = lo, cdeg = deg_lo;
                                 uint32_t       cpc = ( st_lo & PC_MASK ) + 1;
                                 float2         uc  = ua;
-                                for ( int follow = 0; follow < EV_FOLLOW && cpc < cdeg; follow++ ) {
+                                for ( int follow = 0; follow < follow_max && cpc < cdeg; follow++ ) {
                                     const uint32_t e2 = rec_head( S, acc, G, WB, C, cur, cpc ), x = e2 & ~INC_LO_FLAG;
                                     const WaveRec  X   = load_wave_rec( R.wr + x );
                                     const uint32_t pcx = X.state & PC_MASK;
