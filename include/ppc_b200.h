@@ -115,7 +115,14 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *   "sort"     0 = counting sort on the cell key (default), 1 = LSD radix sort
  *   "stash"    per-thread contact stash: 1 = on (default), 0 = off (streaming path only; test hook)
  *   "resolve"  1 = sequential-equivalent wavefront: replays the reference's pair order, bit-exact (default),
+ *              3 = tile Gauss-Seidel: the reference's sequential pass 2 (src/particles_solver.c:131-191) with the pair
+ *                  list in a different, deterministic order (by shared-memory tile, then by cell pair); positions stay
+ *                  bit-exact, velocities agree with the reference as well as the reference agrees with itself under a
+ *                  reordering of its list; one fused kernel, no dependency rounds,
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
+ *   "gs_wc"    "resolve"=3: tile width in cells (0 = from the particle density, default).  Part of the pair order: the
+ *              ranks of a multi-GPU field must all use the same value
+ *   "gs_dump"  "resolve"=3: 1 = every substep also dumps the pairs it resolves (ppc_debug_hot_pairs); test hook
  *   "collide"  0 = auto (shared-memory tile kernel with fine x-bins), 1 = global-memory thread-per-particle kernel,
  *              3 = shared-memory tile kernel scanning the whole 3x3 neighbourhood
  *   "slab_strict"  slab mode: 1 = ppc_slab_begin fails (-2) when the substep just finished was not exact (default); 0 = it only
@@ -139,6 +146,12 @@ int     ppc_debug_sorted_order( struct Particles_t *p, uint32_t *order /* n */ )
 int     ppc_debug_cell_start( struct Particles_t *p, uint32_t *cell_start /* cells+1 */ );
 /* candidate pairs (i, j) in the reference's list order (:311-383); returns the count, writes min(count, max_pairs) */
 int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
+/* The pair set exactly as the HOT narrow-phase kernel of the last substep found it, (i, j) with i < j, unordered: rebuilt from
+ * the contact lists k_collide_tile2 wrote ("resolve"=1) or dumped by k_collide_gs while it resolved them ("resolve"=3 with
+ * "gs_dump").  Returns the count; -1 nothing to report; -2 a contact list exceeded the stored lists (pairs incomplete). */
+int64_t ppc_debug_hot_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
+/* tile geometry of the last "resolve"=3 substep: {tile width, tile height (cells), strip threshold, strip capacity (particles)} */
+int     ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] );
 /* last sequential-equivalent resolve: rounds = depth of the reference's pair dependency graph, visits = particle visits */
 int     ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *rounds, unsigned long long *visits );
 

@@ -107,6 +107,9 @@ class Oracle:
         L.ppc_oracle_substep.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, u8p, C.c_size_t, C.c_uint16, C.c_uint16, C.c_float,
                                          C.c_int, C.c_int]
         L.ppc_oracle_stats.argtypes = [f32p, f32p, f32p, f32p, f32p, f32p, C.c_size_t, C.c_uint16, C.c_uint16, C.POINTER(C.c_double)]
+        L.ppc_oracle_set_tilegs.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.ppc_oracle_tilegs_order.argtypes = [i32p, C.c_size_t, C.c_size_t, u32p, u32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u32p]
+        L.ppc_oracle_resolve_permuted.argtypes = rs + [u32p]
 
     # -- pieces ---------------------------------------------------------------------------------
     def update(self, s: State, dt: float, colour: bool = True) -> None:
@@ -144,9 +147,22 @@ class Oracle:
         fn = self.lib.ppc_oracle_resolve_jacobi if jacobi else self.lib.ppc_oracle_resolve_sequential
         fn(_fp(s.px), _fp(s.py), _fp(s.vx), _fp(s.vy), _fp(s.mass), _fp(s.radius), s.n, pairs.ctypes.data_as(i32p), len(pairs), dt)
 
+    def set_tilegs(self, wc: int, tile_r: int = 8, strip_limit: int = 921) -> None:
+        """Tile geometry of the mode-3 model (the device's: ppc_debug_gs_params)."""
+        self.lib.ppc_oracle_set_tilegs(wc, tile_r, strip_limit)
+
+    def tilegs_order(self, pairs: np.ndarray, grid, n: int, wc: int, tile_r: int = 8, strip_limit: int = 921, row0: int = 0) -> np.ndarray:
+        """The order in which the device's tile Gauss-Seidel resolve applies the velocity impulses of `pairs`."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+        perm = np.zeros(len(pairs), np.uint32)
+        self.lib.ppc_oracle_tilegs_order(pairs.ctypes.data_as(i32p), len(pairs), n, grid["keys"].ctypes.data_as(u32p),
+                                         grid["cell_start"].ctypes.data_as(u32p), grid["cols"], grid["rows"], row0, wc, tile_r, strip_limit,
+                                         perm.ctypes.data_as(u32p))
+        return perm
+
     # -- whole entry points ---------------------------------------------------------------------
     def collisions_check_grid(self, s: State, W: int, H: int, dt: float, mode: int = 0, want_grid: bool = False):
-        """mode 0 = sequential (reference), 1 = Jacobi model of the device, 2 = walls + grid only."""
+        """mode 0 = sequential (reference), 1 = Jacobi model of the device, 2 = walls + grid only, 3 = tile Gauss-Seidel model."""
         keys = order = start = None
         kp = op = sp = None
         if want_grid and s.n >= 2:

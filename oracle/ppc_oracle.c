@@ -371,8 +371,199 @@ void ppc_oracle_resolve_jacobi( float *px, float *py, float *vx, float *vy, cons
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Tile Gauss-Seidel model of the B200 "resolve"=3 path -- NOT reference behaviour.
+ *
+ * It is the reference's pass 2 (src/particles_solver.c:131-191) with the velocity impulses applied in a DIFFERENT,
+ * deterministic pair order; everything else is the reference's: the same candidate pairs, the same frozen contact
+ * geometry (pass 1, :84-127), position pushes summed in the reference's list order (so positions equal the
+ * sequential ones bit for bit), and every impulse computed by the same formulas from the CURRENT velocities of its
+ * two particles (:159-190).  The order is the one the device kernel (csrc/ppc_gs.cuh) executes:
+ *
+ *   1. The grid is cut into tiles of tile_r cell rows x wc cell columns, coloured (tx & 1) + 2 (ty & 1).  A tile
+ *      whose staged particle count (tile + one-cell halo) exceeds strip_limit is cut into column strips
+ *      (strips = ceil(count / strip_limit), width = ceil(wc / strips)), which its CTA runs one after the other.
+ *   2. A pair belongs to ONE sub-tile (tile, strip): the one holding both particles, else the earlier of the two
+ *      in the order (colour of the tile; inside a tile the strip index).  Sub-tiles run in that order; tiles of one
+ *      colour touch disjoint particles, so their mutual order is immaterial.
+ *   3. Inside a sub-tile pairs are grouped by the pair of cells they connect.  Nine phases: same cell; east
+ *      neighbour, base column even / odd; south, south-east, south-west neighbour, base row even / odd (base =
+ *      the smaller cell in (row, column) order; parities of the grid-global coordinates).  The groups of a phase
+ *      share no particle.
+ *   4. Inside a group pairs are ordered by their ANCHOR particle (the one inside the sub-tile if the other is in
+ *      its halo, else the one in the base cell, else -- same cell -- the lower index), ascending index, and then by
+ *      the pair's position in the anchor's contact list (the order the reference's pair list touches that particle:
+ *      pairs in which it is j by ascending i, then pairs in which it is i in list order).
+ *
+ * tests/test_gpu_gs.py checks the device against this model bit for bit, and this model against the reference
+ * statistically (the north-star's 1 % bar, with the reference's own reordering spread beside it).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    uint32_t sub;    /* colour << 28 | strip (the tile itself is immaterial: see 2. above, but kept for locality) */
+    uint32_t tile;
+    uint32_t phase;
+    uint32_t base;   /* global key of the base cell */
+    uint32_t anchor; /* index of the anchor particle */
+    uint32_t rank;   /* position in the anchor's contact list */
+    uint32_t k;      /* index into the pair list */
+} gs_key_t;
+
+static int gs_key_cmp( const void *pa, const void *pb ) {
+    const gs_key_t *a = (const gs_key_t *)pa, *b = (const gs_key_t *)pb;
+#define GS_CMP( f )                                                                                                  \
+    if ( a->f != b->f )                                                                                              \
+        return a->f < b->f ? -1 : 1;
+    GS_CMP( sub ) GS_CMP( tile ) GS_CMP( phase ) GS_CMP( base ) GS_CMP( anchor ) GS_CMP( rank )
+#undef GS_CMP
+    return 0;
+}
+
+void ppc_oracle_tilegs_order( const int32_t *pairs, size_t npairs, size_t n, const uint32_t *keys, const uint32_t *cell_start, int cols,
+                              int rows, int row0, int wc, int tile_r, int strip_limit, uint32_t *perm_out ) {
+    if ( npairs == 0 )
+        return;
+    const int tiles_x = ( cols + wc - 1 ) / wc;
+    const int ty0 = row0 / tile_r, tiles_y = ( row0 + rows + tile_r - 1 ) / tile_r - ty0;
+    /* strip width of every tile (1. above) */
+    int *strip_w = (int *)malloc( (size_t)tiles_x * tiles_y * sizeof( int ) );
+    for ( int ty = 0; ty < tiles_y; ty++ )
+        for ( int tx = 0; tx < tiles_x; tx++ ) {
+            const int cx0 = tx * wc, cx1 = cx0 + wc < cols ? cx0 + wc : cols;
+            const int c0 = cx0 > 0 ? cx0 - 1 : 0, c1 = cx1 + 1 < cols ? cx1 + 1 : cols;
+            const int cy0 = ( ty0 + ty ) * tile_r - row0;
+            uint32_t  total = 0;
+            for ( int gy = cy0 - 1; gy <= cy0 + tile_r; gy++ )
+                if ( gy >= 0 && gy < rows )
+                    total += cell_start[ (size_t)gy * cols + c1 ] - cell_start[ (size_t)gy * cols + c0 ];
+            const int strips = total ? (int)( ( total + (uint32_t)strip_limit - 1 ) / (uint32_t)strip_limit ) : 1;
+            int       sw     = ( cx1 - cx0 + strips - 1 ) / strips;
+            strip_w[ ty * tiles_x + tx ] = sw > 1 ? sw : 1;
+        }
+    /* contact-list ranks (4. above) */
+    uint32_t *cnt_j = (uint32_t *)calloc( n ? n : 1, sizeof( uint32_t ) ), *first_i = (uint32_t *)malloc( ( n ? n : 1 ) * sizeof( uint32_t ) );
+    uint32_t *rank_i = (uint32_t *)malloc( npairs * sizeof( uint32_t ) ), *rank_j = (uint32_t *)malloc( npairs * sizeof( uint32_t ) );
+    for ( size_t k = 0; k < npairs; k++ )
+        rank_j[ k ] = cnt_j[ pairs[ 2 * k + 1 ] ]++; /* the list is ascending in i, so this counts the pairs (i' < i, j) */
+    for ( size_t k = 0; k < npairs; k++ ) {
+        const int i = pairs[ 2 * k ];
+        if ( k == 0 || pairs[ 2 * ( k - 1 ) ] != i )
+            first_i[ i ] = (uint32_t)k;
+        rank_i[ k ] = cnt_j[ i ] + ( (uint32_t)k - first_i[ i ] );
+    }
+    gs_key_t *K = (gs_key_t *)malloc( npairs * sizeof( gs_key_t ) );
+    for ( size_t k = 0; k < npairs; k++ ) {
+        const int      i = pairs[ 2 * k ], j = pairs[ 2 * k + 1 ];
+        const int      cxi = (int)( keys[ i ] % (uint32_t)cols ), cyi = (int)( keys[ i ] / (uint32_t)cols );
+        const int      cxj = (int)( keys[ j ] % (uint32_t)cols ), cyj = (int)( keys[ j ] / (uint32_t)cols );
+        const int      txi = cxi / wc, tyi = ( cyi + row0 ) / tile_r - ty0, txj = cxj / wc, tyj = ( cyj + row0 ) / tile_r - ty0;
+        const uint32_t ti = (uint32_t)( tyi * tiles_x + txi ), tj = (uint32_t)( tyj * tiles_x + txj );
+        const uint32_t si = (uint32_t)( ( cxi - txi * wc ) / strip_w[ ti ] ), sj = (uint32_t)( ( cxj - txj * wc ) / strip_w[ tj ] );
+        const uint32_t ci = (uint32_t)( ( txi & 1 ) + 2 * ( ( tyi + ty0 ) & 1 ) ), cj = (uint32_t)( ( txj & 1 ) + 2 * ( ( tyj + ty0 ) & 1 ) );
+        /* owner sub-tile (2.) and whether each particle lies inside it */
+        int owner_is_i;
+        if ( ti == tj )
+            owner_is_i = si <= sj;
+        else
+            owner_is_i = ci < cj;
+        const uint32_t ot = owner_is_i ? ti : tj, os = owner_is_i ? si : sj, oc = owner_is_i ? ci : cj;
+        const int      i_in = ( ti == ot && si == os ), j_in = ( tj == ot && sj == os );
+        /* cells, base cell, phase (3.) */
+        const int gyi = cyi + row0, gyj = cyj + row0;
+        const int i_base = ( gyi < gyj ) || ( gyi == gyj && cxi <= cxj );
+        const int by = i_base ? gyi : gyj, bx = i_base ? cxi : cxj, oy = i_base ? gyj : gyi, ox = i_base ? cxj : cxi;
+        uint32_t  phase;
+        if ( oy == by && ox == bx )
+            phase = 0;
+        else if ( oy == by )
+            phase = 1 + (uint32_t)( bx & 1 );
+        else if ( ox == bx )
+            phase = 3 + (uint32_t)( by & 1 );
+        else if ( ox == bx + 1 )
+            phase = 5 + (uint32_t)( by & 1 );
+        else
+            phase = 7 + (uint32_t)( by & 1 );
+        /* anchor (4.) */
+        int anchor_is_i;
+        if ( i_in && j_in ) {
+            if ( gyi == gyj && cxi == cxj )
+                anchor_is_i = 1; /* same cell: the lower index, and i < j */
+            else
+                anchor_is_i = i_base;
+        } else
+            anchor_is_i = i_in;
+        K[ k ].sub    = ( oc << 28 ) | os;
+        K[ k ].tile   = ot;
+        K[ k ].phase  = phase;
+        K[ k ].base   = (uint32_t)( by - row0 ) * (uint32_t)cols + (uint32_t)bx;
+        K[ k ].anchor = (uint32_t)( anchor_is_i ? i : j );
+        K[ k ].rank   = anchor_is_i ? rank_i[ k ] : rank_j[ k ];
+        K[ k ].k      = (uint32_t)k;
+    }
+    qsort( K, npairs, sizeof( gs_key_t ), gs_key_cmp );
+    for ( size_t k = 0; k < npairs; k++ )
+        perm_out[ k ] = K[ k ].k;
+    free( K );
+    free( rank_i );
+    free( rank_j );
+    free( cnt_j );
+    free( first_i );
+    free( strip_w );
+}
+
+/* Positions in the reference's list order, velocities in the order perm[] (a permutation of the pair list). */
+void ppc_oracle_resolve_permuted( float *px, float *py, float *vx, float *vy, const float *mass, const float *radius, size_t n,
+                                  const int32_t *pairs, size_t npairs, float dt, const uint32_t *perm ) {
+    if ( npairs == 0 || n < 2 )
+        return;
+    contact_t *ct = (contact_t *)malloc( npairs * sizeof( contact_t ) );
+    for ( size_t k = 0; k < npairs; k++ ) {
+        const int i = pairs[ 2 * k ], j = pairs[ 2 * k + 1 ];
+        ct[ k ] = contact_of( px[ i ], py[ i ], radius[ i ], px[ j ], py[ j ], radius[ j ], dt );
+    }
+    for ( size_t k = 0; k < npairs; k++ ) { /* :145-156 in list order */
+        const int   i = pairs[ 2 * k ], j = pairs[ 2 * k + 1 ];
+        const float wi = inv_mass_u8( mass[ i ] ), wj = inv_mass_u8( mass[ j ] );
+        const float wsum = wi + wj;
+        if ( ct[ k ].raw > 0.0f ) {
+            const float fi = ( wi / wsum ) * ct[ k ].corrected;
+            const float fj = ( wj / wsum ) * ct[ k ].corrected;
+            px[ i ] += fi * ct[ k ].nx;
+            py[ i ] += fi * ct[ k ].ny;
+            px[ j ] -= fj * ct[ k ].nx;
+            py[ j ] -= fj * ct[ k ].ny;
+        }
+    }
+    for ( size_t q = 0; q < npairs; q++ ) { /* :158-190 in the permuted order */
+        const size_t k = perm[ q ];
+        const int    i = pairs[ 2 * k ], j = pairs[ 2 * k + 1 ];
+        const float  wi = inv_mass_u8( mass[ i ] ), wj = inv_mass_u8( mass[ j ] );
+        const float  wsum = wi + wj;
+        const float  nx = ct[ k ].nx, ny = ct[ k ].ny;
+        const float  rx = vx[ i ] - vx[ j ], ry = vy[ i ] - vy[ j ];
+        const float  vn = rx * nx + ry * ny;
+        if ( vn > 0.0f && ct[ k ].vbias == 0.0f )
+            continue;
+        const float want = (float)( -K_RESTITUTION * (double)vn + (double)ct[ k ].vbias );
+        const float jmag = ( want - vn ) / wsum;
+        const float ix = jmag * nx, iy = jmag * ny;
+        vx[ i ] += wi * ix;
+        vy[ i ] += wi * iy;
+        vx[ j ] -= wj * ix;
+        vy[ j ] -= wj * iy;
+    }
+    free( ct );
+}
+
+static int g_gs_wc = 16, g_gs_tile_r = 8, g_gs_strip_limit = 921;
+void       ppc_oracle_set_tilegs( int wc, int tile_r, int strip_limit ) {
+    g_gs_wc          = wc;
+    g_gs_tile_r      = tile_r;
+    g_gs_strip_limit = strip_limit;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * particlesCollisionsCheck_Grid: src/particles_solver.c:197-393, composed from the pieces above.
- * mode 0 = sequential resolve (reference), 1 = Jacobi model, 2 = no resolve (walls + grid only).
+ * mode 0 = sequential resolve (reference), 1 = Jacobi model, 2 = no resolve (walls + grid only),
+ * 3 = tile Gauss-Seidel model (parameters from ppc_oracle_set_tilegs).
  * Optional outputs (may be NULL): keys[n], order[n], cell_start[cells+1] (caller sizes it with
  * ppc_oracle_grid_dims first), *pairs_out / *npairs_out.
  * ---------------------------------------------------------------------------------------------- */
@@ -400,6 +591,12 @@ void ppc_oracle_collisions_check_grid( float *px, float *py, float *vx, float *v
         ppc_oracle_resolve_sequential( px, py, vx, vy, mass, radius, n, pairs, npairs, dt );
     else if ( mode == 1 )
         ppc_oracle_resolve_jacobi( px, py, vx, vy, mass, radius, n, pairs, npairs, dt );
+    else if ( mode == 3 && npairs ) {
+        uint32_t *perm = (uint32_t *)malloc( npairs * sizeof( uint32_t ) );
+        ppc_oracle_tilegs_order( pairs, npairs, n, keys, start, cols, rows, 0, g_gs_wc, g_gs_tile_r, g_gs_strip_limit, perm );
+        ppc_oracle_resolve_permuted( px, py, vx, vy, mass, radius, n, pairs, npairs, dt, perm );
+        free( perm );
+    }
     if ( npairs_out )
         *npairs_out = npairs;
     if ( pairs_out )

@@ -18,6 +18,11 @@ void   ppc_oracle_resolve_sequential( float *px, float *py, float *vx, float *vy
                                       const int32_t *pairs, size_t npairs, float dt );
 void   ppc_oracle_resolve_jacobi( float *px, float *py, float *vx, float *vy, const float *mass, const float *radius, size_t n,
                                   const int32_t *pairs, size_t npairs, float dt );
+void   ppc_oracle_tilegs_order( const int32_t *pairs, size_t npairs, size_t n, const uint32_t *keys, const uint32_t *cell_start, int cols,
+                                int rows, int row0, int wc, int tile_r, int strip_limit, uint32_t *perm_out );
+void   ppc_oracle_resolve_permuted( float *px, float *py, float *vx, float *vy, const float *mass, const float *radius, size_t n,
+                                    const int32_t *pairs, size_t npairs, float dt, const uint32_t *perm );
+void   ppc_oracle_set_tilegs( int wc, int tile_r, int strip_limit );
 void   ppc_oracle_collisions_check_grid( float *px, float *py, float *vx, float *vy, const float *mass, const float *radius, size_t n,
                                          uint16_t W, uint16_t H, float dt, int mode, uint32_t *keys_out, uint32_t *order_out,
                                          uint32_t *cell_start_out, int32_t **pairs_out, size_t *npairs_out );

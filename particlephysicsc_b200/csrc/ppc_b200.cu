@@ -16,6 +16,7 @@
 #include "ppc_collide.cuh"
 #include "ppc_common.cuh"
 #include "ppc_grid.cuh"
+#include "ppc_gs.cuh"
 #include "ppc_radix.cuh"
 #include "ppc_scan.cuh"
 #include "ppc_slab.cuh"
@@ -48,7 +49,8 @@ struct Store {
     unsigned dl_mask       = PPC_DL_ALL;
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
-    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi
+    int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi, 3 tile Gauss-Seidel
+    int      opt_gs_wc = 0, opt_gs_dump = 0;   // tile width of the "resolve"=3 kernel (0: from the particle density); dump the pairs it resolves
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -70,6 +72,12 @@ struct Store {
     uint32_t    *scratch = nullptr;
     size_t       scratch_words = 0;
     uint32_t    *d_word = nullptr;   // one word for small reductions
+    // "resolve"=3 (tile Gauss-Seidel, ppc_gs.cuh): the staged records, error flags, tile width of the last substep, pair dump
+    float4      *rec_a = nullptr, *rec_b = nullptr;
+    uint32_t    *gs_flags = nullptr, *gs_dump = nullptr;   // gs_flags[0] error bits, [1] pairs dumped
+    uint32_t     gs_dump_cap = 0;
+    int          gs_wc = 0;
+    bool         gs_attr_set = false;
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     WaveRecs     recs = {};          // packed records of the event-driven rounds
     int          events_grid = 0;
@@ -223,19 +231,55 @@ static void ensure_wave_buffers( Store *st ) {
 }
 
 static void check_device_flags( Store *st ) {   // after a stream synchronise
+    if ( st->gs_flags ) {
+        uint32_t flags = 0;
+        PPC_CK( cudaMemcpy( &flags, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
+        if ( flags ) {
+            fprintf( stderr, "particlephysicsc_b200: \"resolve\"=3 cannot run this field (%s%s); use the default resolve\n",
+                     ( flags & GS_ERR_CAP ) ? "a one-column strip of a tile holds more particles than shared memory takes " : "",
+                     ( flags & GS_ERR_POOL ) ? "more contacts in one tile than its contact pool holds" : "" );
+            abort();
+        }
+    }
     if ( !st->wave.counters )
         return;
     uint32_t flags = 0;
     PPC_CK( cudaMemcpy( &flags, st->wave.counters + 3, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
     if ( flags ) {
         fprintf( stderr, "particlephysicsc_b200: resolve failed (%s%s)\n", ( flags & 1u ) ? "a particle has more than 4095 simultaneous contacts " : "",
-                 ( flags & 2u ) ? "pair dependency chain longer than 2^20 rounds" : "" );
+                 ( flags & 2u ) ? "pair dependency chain longer than 2^19 - 1 rounds" : "" );
         abort();
+    }
+}
+
+static void free_gs_buffers( Store *st ) {
+    cudaFree( st->rec_a );
+    cudaFree( st->rec_b );
+    cudaFree( st->gs_dump );
+    st->rec_a = st->rec_b = nullptr;
+    st->gs_dump     = nullptr;
+    st->gs_dump_cap = 0;
+}
+
+// Buffers of the tile Gauss-Seidel path, on first use: 32 bytes of staged records per particle.
+static void ensure_gs_buffers( Store *st ) {
+    if ( !st->gs_flags ) {
+        st->gs_flags = dev_alloc<uint32_t>( 4 );
+        PPC_CK( cudaMemsetAsync( st->gs_flags, 0, 4 * sizeof( uint32_t ), st->stream ) );
+    }
+    if ( !st->rec_a ) {
+        st->rec_a = dev_alloc<float4>( st->cap );
+        st->rec_b = dev_alloc<float4>( st->cap );
+    }
+    if ( st->opt_gs_dump && !st->gs_dump ) {
+        st->gs_dump_cap = (uint32_t)( st->cap * 8 < 0x7fffffffu ? st->cap * 8 : 0x7fffffffu );
+        st->gs_dump     = dev_alloc<uint32_t>( 2 * (size_t)st->gs_dump_cap );
     }
 }
 
 static void free_particle_arrays( Store *st ) {
     free_wave_buffers( st );
+    free_gs_buffers( st );
     for ( int s = 0; s < 2; s++ ) {
         cudaFree( st->set[ s ].pv );
         cudaFree( st->set[ s ].rm );
@@ -341,6 +385,7 @@ static void resize_particle_arrays( Store *st, size_t cap, size_t keep ) {
     st->cap         = cap;
     st->pre_valid   = false;
     free_wave_buffers( st );
+    free_gs_buffers( st );
 }
 
 static void ensure_scratch( Store *st, size_t words ) {
@@ -514,7 +559,7 @@ static ParticleSet offset_view( const ParticleSet &S, const size_t first ) {
     return ParticleSet{ S.pv + first, S.rm + first, S.gid + first, S.key + first, S.col + first };
 }
 
-static void grid_stage( Store *st, const size_t n, const size_t bins, const size_t first = 0, const uint32_t unranked_cell = 0xffffffffu ) {
+static void grid_stage( Store *st, const size_t n, const size_t bins, const int cols, const size_t first = 0, const uint32_t unranked_cell = 0xffffffffu ) {
     const ParticleSet  A = offset_view( st->set[ st->cur ], first );   // input: n slots starting at `first`
     const ParticleSet &B = st->set[ st->cur ^ 1 ];
     {
@@ -537,14 +582,59 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const size
     }
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
+        const bool gs = st->opt_resolve == 3;   // the moving state goes into the tile kernel's staged records
         PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
-                    st->col_valid ? 1 : 0, unranked_cell );
+                    st->col_valid ? 1 : 0, unranked_cell, gs ? st->rec_a : (float4 *)nullptr, gs ? st->rec_b : (float4 *)nullptr,
+                    (uint32_t)cols );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
 }
 
 // Narrow phase + contact resolution over the first n slots of the (sorted) current set on grid G (K7, K7b).
+// "resolve"=3: narrow phase, position pushes and the tile Gauss-Seidel velocity resolve in one kernel (ppc_gs.cuh), one launch
+// per tile colour.  Reads the staged records the gather wrote, writes the final state into the sorted set's pv array.
+static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
+    int wc = st->opt_gs_wc;
+    if ( wc <= 0 ) {
+        const double per_cell = (double)n / (double)G.cells;
+        wc = (int)( (double)GS_TARGET / ( GS_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
+    }
+    return wc < 2 ? 2 : ( wc > GS_MAXC - 2 ? GS_MAXC - 2 : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
+}
+
+static void resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
+    StageTimer T( st, ST_COLLIDE );
+    if ( !st->gs_attr_set ) {
+        PPC_CK( cudaFuncSetAttribute( k_collide_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( GsSmem ) ) );
+        st->gs_attr_set = true;
+    }
+    GsLaunch L;
+    L.wc       = st->gs_wc = gs_tile_width( st, n, G );
+    L.tiles_x  = ( G.cols + L.wc - 1 ) / L.wc;
+    L.ty_first = G.row0 / GS_R;
+    const int tiles_y = ( G.row0 + G.rows + GS_R - 1 ) / GS_R - L.ty_first;
+    GsDump    D{ nullptr, nullptr, 0u };
+    if ( st->opt_gs_dump ) {
+        PPC_CK( cudaMemsetAsync( st->gs_flags + 1, 0, sizeof( uint32_t ), st->stream ) );
+        D = GsDump{ st->gs_dump, st->gs_flags + 1, st->gs_dump_cap };
+    }
+    for ( int colour = 0; colour < 4; colour++ ) {
+        L.colour   = colour;
+        L.ntx      = ( L.tiles_x - ( colour & 1 ) + 1 ) / 2;
+        L.ty_start = ( ( colour >> 1 ) - L.ty_first ) & 1;
+        const int nty = ( tiles_y - L.ty_start + 1 ) / 2;
+        if ( L.ntx <= 0 || nty <= 0 )
+            continue;
+        PPC_LAUNCH( k_collide_gs, (unsigned)( L.ntx * nty ), GS_THREADS, sizeof( GsSmem ), st->stream, st->rec_a, st->rec_b, st->set[ st->cur ].pv,
+                    st->cell_start, G, dt, L, st->gs_flags, D );
+    }
+}
+
 static void resolve_stage( Store *st, const size_t n, const GridDims &G, const float dt ) {
+    if ( st->opt_resolve == 3 ) {
+        resolve_gs( st, n, G, dt );
+        return;
+    }
     ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
     if ( st->opt_resolve ) {
         const bool jacobi = st->opt_resolve == 2;
@@ -712,7 +802,9 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     st->pending     = false;
 
     launch_integrate( st, P );                                                         // K1 (+K3 histogram)
-    grid_stage( st, n, G.cells );
+    if ( st->opt_resolve == 3 )
+        ensure_gs_buffers( st );
+    grid_stage( st, n, G.cells, G.cols );
     st->grid       = G;
     st->grid_valid = true;
     resolve_stage( st, n, G, dt );
@@ -801,6 +893,7 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFreeHost( st->h_active );
         cudaFree( st->wave_items );
         cudaFree( st->wave_n_items );
+        cudaFree( st->gs_flags );
         cudaEventDestroy( st->ev0 );
         cudaEventDestroy( st->ev1 );
         cudaStreamDestroy( st->stream );
@@ -971,6 +1064,10 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_wave_mode = (int)value;
     else if ( !strcmp( name, "slab_strict" ) )
         st->opt_slab_strict = (int)value;
+    else if ( !strcmp( name, "gs_wc" ) )
+        st->opt_gs_wc = (int)value;
+    else if ( !strcmp( name, "gs_dump" ) )
+        st->opt_gs_dump = (int)value;
     else
         return -1;
     return 0;
@@ -1026,6 +1123,8 @@ extern "C" int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_
     ParticleSet  pre = st->set[ st->cur ];
     if ( st->opt_resolve )
         pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw (before the resolve moved anything)
+    if ( st->opt_resolve == 3 )               // ... which in this mode live in the staged records
+        PPC_LAUNCH( k_rec_to_pv, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, (const float4 *)st->rec_b, pre.pv, n );
     uint32_t *count  = st->sort_keys_a;       // n + 1 words needed; sort_keys_a has cap >= n, use scratch when tight
     uint32_t *offset = st->sort_keys_b;
     uint32_t *tmp    = nullptr;
@@ -1063,6 +1162,56 @@ extern "C" int ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *
     PPC_CK( cudaMemcpy( w, st->wave.counters, sizeof( w ), cudaMemcpyDeviceToHost ) );
     *rounds = w[ 4 ];
     *visits = ( (unsigned long long)w[ 7 ] << 32 ) | w[ 6 ];
+    return 0;
+}
+
+// The pairs the HOT narrow-phase kernel of the last substep found, as (i, j) API indices with i < j, in no particular order:
+// "resolve"=1 rebuilds them from the contact lists k_collide_tile2 wrote for the wavefront; "resolve"=3 returns what
+// k_collide_gs dumped while resolving (option "gs_dump" must be on during that substep).  Returns the number of pairs,
+// -1 when there is nothing to report, -2 when a contact list was longer than the stored lists (pairs incomplete).
+extern "C" int64_t ppc_debug_hot_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs ) {
+    Store *st = store_of( p );
+    if ( !st->grid_valid || !st->pre_valid )
+        return -1;
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    if ( st->opt_resolve == 3 ) {
+        if ( !st->gs_dump )
+            return -1;
+        uint32_t total = 0;
+        PPC_CK( cudaMemcpy( &total, st->gs_flags + 1, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
+        if ( total > st->gs_dump_cap )
+            return -2;
+        const size_t keep = total < max_pairs ? total : max_pairs;
+        if ( pairs && keep )
+            PPC_CK( cudaMemcpy( pairs, st->gs_dump, 2 * keep * sizeof( int32_t ), cudaMemcpyDeviceToHost ) );
+        return (int64_t)total;
+    }
+    if ( st->opt_resolve != 1 || !st->wave.deg )
+        return -1;
+    const size_t n = st->n;
+    uint32_t    *d_cnt = dev_alloc<uint32_t>( 2 );
+    int32_t     *d_out = dev_alloc<int32_t>( 2 * ( max_pairs ? max_pairs : 1 ) );
+    PPC_CK( cudaMemsetAsync( d_cnt, 0, 2 * sizeof( uint32_t ), st->stream ) );
+    PPC_LAUNCH( k_pairs_from_lists, div_up( n, COLLIDE_THREADS ), COLLIDE_THREADS, 0, st->stream, st->set[ st->cur ].gid, st->wave, n, d_out,
+                (uint32_t)( max_pairs < 0xffffffffu ? max_pairs : 0xffffffffu ), d_cnt );
+    uint32_t h[ 2 ] = { 0, 0 };
+    PPC_CK( cudaMemcpyAsync( h, d_cnt, sizeof( h ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
+    const size_t keep = h[ 0 ] < max_pairs ? h[ 0 ] : max_pairs;
+    if ( pairs && keep )
+        PPC_CK( cudaMemcpy( pairs, d_out, 2 * keep * sizeof( int32_t ), cudaMemcpyDeviceToHost ) );
+    cudaFree( d_cnt );
+    cudaFree( d_out );
+    return h[ 1 ] ? -2 : (int64_t)h[ 0 ];
+}
+
+// Tile geometry of the last "resolve"=3 substep: out = {tile width in cells, tile height in cells, staged particles above which
+// a tile is cut into strips, staged-particle capacity of a strip} -- the parameters of the oracle's model of that order.
+extern "C" int ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] ) {
+    Store *st = store_of( p );
+    if ( st->opt_resolve != 3 || st->gs_wc == 0 )
+        return -1;
+    out[ 0 ] = st->gs_wc, out[ 1 ] = GS_R, out[ 2 ] = GS_STRIP_LIMIT, out[ 3 ] = GS_CAP;
     return 0;
 }
 
@@ -1241,6 +1390,8 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     const size_t bins = (size_t)G.cells + 1;   // + the drop bin
     ensure_cells( st, bins );
     ensure_scratch( st, radix_scratch_words( n_loc ) + scan_scratch_words( bins + 1 ) + scan_scratch_words( n_loc + 1 ) + 64 );
+    if ( st->opt_resolve == 3 )
+        ensure_gs_buffers( st );
     const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
     {
         StageTimer T( st, ST_SLAB );
@@ -1261,7 +1412,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
                         st->cell_count );
     }
     if ( n_loc )
-        grid_stage( st, n_loc, bins, st->own_first, G.cells );
+        grid_stage( st, n_loc, bins, G.cols, st->own_first, G.cells );
     else {
         PPC_CK( cudaMemsetAsync( st->cell_start, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
         st->cur ^= 1;
@@ -1385,6 +1536,9 @@ extern "C" int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, 
     ParticleSet pre = st->set[ st->cur ];
     if ( st->opt_resolve )
         pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw
+    if ( st->opt_resolve == 3 )
+        PPC_LAUNCH( k_rec_to_pv, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, (const float4 *)st->rec_b, pre.pv,
+                    st->n );
     const size_t padded = ( n + 1 + 63 ) & ~(size_t)63;
     uint32_t    *tmp    = dev_alloc<uint32_t>( 2 * padded );
     uint32_t    *count = tmp, *offset = tmp + padded;

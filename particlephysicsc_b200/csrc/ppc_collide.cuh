@@ -1683,4 +1683,28 @@ __global__ void __launch_bounds__( COLLIDE_THREADS ) k_pairs_emit( const Particl
     } );
 }
 
+// The pair set as the HOT kernel found it: every contact-list entry in which the particle is the pair's i (k_collide_tile2 /
+// k_collide_tile / k_collide_global wrote them for the wavefront).  out_count[0] = pairs, [1] = particles whose list was
+// longer than the stored positions (their pairs are incomplete here).
+__global__ void __launch_bounds__( COLLIDE_THREADS ) k_pairs_from_lists( const uint32_t *__restrict__ gid, const WaveBuffers WB, const size_t n,
+                                                                         int32_t *__restrict__ pairs, const uint32_t max_pairs,
+                                                                         uint32_t *__restrict__ out_count ) {
+    const size_t k = (size_t)blockIdx.x * COLLIDE_THREADS + threadIdx.x;
+    if ( k >= n )
+        return;
+    const uint32_t deg = WB.deg[ k ];
+    if ( deg > WB.maxdeg )
+        atomicAdd( &out_count[ 1 ], 1u );
+    for ( uint32_t c = 0; c < deg && c < WB.maxdeg; c++ ) {
+        const uint32_t e = WB.inc[ (size_t)c * WB.stride + k ];
+        if ( !( e & INC_LO_FLAG ) )
+            continue;
+        const uint32_t at = atomicAdd( &out_count[ 0 ], 1u );
+        if ( at < max_pairs ) {
+            pairs[ 2 * at ]     = (int32_t)gid[ k ];
+            pairs[ 2 * at + 1 ] = (int32_t)gid[ e & ~INC_LO_FLAG ];
+        }
+    }
+}
+
 }   // namespace ppc

@@ -102,10 +102,14 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
 // particles of the same cell with a smaller API index).  That makes storage the stable ascending (key, index)
 // order -- the canonical form of the reference's chains (:293-294) -- whatever order the scatter or the radix
 // sort left inside the cell.  Then the whole particle record moves from the old set to the new one.
+// With rec_a / rec_b given ("resolve"=3) the moving state goes into the two 16-byte records the tile kernel stages with
+// bulk copies (ppc_gs.cuh) instead of Out.pv, which that kernel then writes itself:
+//   rec_a = {x, y, radius, API index}   rec_b = {v_x, v_y, mass byte (:141-142) | cell column byte << 8, empty list head}
 __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const ParticleSet In, const ParticleSet Out,
                                                                         const uint32_t *__restrict__ slot_of,
                                                                         const uint32_t *__restrict__ cell_start, const size_t n,
-                                                                        const int move_colour, const uint32_t unranked_cell ) {
+                                                                        const int move_colour, const uint32_t unranked_cell,
+                                                                        float4 *__restrict__ rec_a, float4 *__restrict__ rec_b, const uint32_t cols ) {
     const size_t pos = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( pos >= n )
         return;
@@ -120,8 +124,16 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
         for ( uint32_t q = b; q < e; q++ )
             rank += ( In.gid[ slot_of[ q ] ] < g ) ? 1u : 0u;
     const uint32_t dst = b + rank;
-    Out.pv[ dst ]  = In.pv[ src ];
-    Out.rm[ dst ]  = In.rm[ src ];
+    const float4   s4  = In.pv[ src ];
+    const float2   a2  = In.rm[ src ];
+    if ( rec_a ) {
+        const uint32_t cx = c - ( c / cols ) * cols;
+        rec_a[ dst ] = make_float4( s4.x, s4.y, a2.x, __uint_as_float( g ) );
+        rec_b[ dst ] = make_float4( s4.z, s4.w, __uint_as_float( ( (unsigned)__float2int_rz( a2.y ) & 0xffu ) | ( ( cx & 0xffu ) << 8 ) ),
+                                    __uint_as_float( 0xffffu ) );
+    } else
+        Out.pv[ dst ] = s4;
+    Out.rm[ dst ]  = a2;
     Out.gid[ dst ] = g;
     Out.key[ dst ] = c;
     if ( move_colour )
@@ -165,6 +177,16 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_unpack_download( const Par
     }
     if ( mask & PPC_COLOR )
         col[ g ] = S.col[ k ];
+}
+
+// "resolve"=3 keeps the pre-resolve positions in the tile kernel's staged records; the pair exporter wants them as pv
+__global__ void __launch_bounds__( STREAM_THREADS ) k_rec_to_pv( const float4 *__restrict__ rec_a, const float4 *__restrict__ rec_b,
+                                                                 float4 *__restrict__ pv, const size_t n ) {
+    const size_t k = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    if ( k >= n )
+        return;
+    const float4 a = rec_a[ k ], b = rec_b[ k ];
+    pv[ k ] = make_float4( a.x, a.y, b.x, b.y );
 }
 
 // keys by API index / sorted order, for the parity exporters
