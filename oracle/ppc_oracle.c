@@ -380,8 +380,8 @@ void ppc_oracle_resolve_jacobi( float *px, float *py, float *vx, float *vy, cons
  * two particles (:159-190).  The order is the one the device kernel (csrc/ppc_gs.cuh) executes:
  *
  *   1. The grid is cut into tiles of tile_r cell rows x wc cell columns, coloured (tx & 1) + 2 (ty & 1).  A tile
- *      whose staged particle count (tile + one-cell halo) exceeds strip_limit is cut into column strips
- *      (strips = ceil(count / strip_limit), width = ceil(wc / strips)), which its CTA runs one after the other.
+ *      whose staged particle count (tile + one-cell halo) exceeds strip_limit is cut into column strips, greedily from
+ *      the left, each as wide as keeps its own staged count within strip_limit; its CTA runs them one after the other.
  *   2. A pair belongs to ONE sub-tile (tile, strip): the one holding both particles, else the earlier of the two
  *      in the order (colour of the tile; inside a tile the strip index).  Sub-tiles run in that order; tiles of one
  *      colour touch disjoint particles, so their mutual order is immaterial.
@@ -423,20 +423,35 @@ void ppc_oracle_tilegs_order( const int32_t *pairs, size_t npairs, size_t n, con
         return;
     const int tiles_x = ( cols + wc - 1 ) / wc;
     const int ty0 = row0 / tile_r, tiles_y = ( row0 + rows + tile_r - 1 ) / tile_r - ty0;
-    /* strip width of every tile (1. above) */
-    int *strip_w = (int *)malloc( (size_t)tiles_x * tiles_y * sizeof( int ) );
+    /* strip of every tile column (1. above): greedily from the left, each strip as wide as keeps its staged particle count
+     * (strip + one halo column either side, tile rows + one halo row either side) within strip_limit, at least one column */
+    uint8_t *strip_of = (uint8_t *)calloc( (size_t)tiles_x * tiles_y * wc, 1 );
     for ( int ty = 0; ty < tiles_y; ty++ )
         for ( int tx = 0; tx < tiles_x; tx++ ) {
             const int cx0 = tx * wc, cx1 = cx0 + wc < cols ? cx0 + wc : cols;
             const int c0 = cx0 > 0 ? cx0 - 1 : 0, c1 = cx1 + 1 < cols ? cx1 + 1 : cols;
             const int cy0 = ( ty0 + ty ) * tile_r - row0;
-            uint32_t  total = 0;
-            for ( int gy = cy0 - 1; gy <= cy0 + tile_r; gy++ )
-                if ( gy >= 0 && gy < rows )
-                    total += cell_start[ (size_t)gy * cols + c1 ] - cell_start[ (size_t)gy * cols + c0 ];
-            const int strips = total ? (int)( ( total + (uint32_t)strip_limit - 1 ) / (uint32_t)strip_limit ) : 1;
-            int       sw     = ( cx1 - cx0 + strips - 1 ) / strips;
-            strip_w[ ty * tiles_x + tx ] = sw > 1 ? sw : 1;
+            uint32_t  P[ 70 ]; /* wc + 3 <= 67 */
+            for ( int c = 0; c <= c1 - c0; c++ ) {
+                P[ c ] = 0;
+                for ( int gy = cy0 - 1; gy <= cy0 + tile_r; gy++ )
+                    if ( gy >= 0 && gy < rows )
+                        P[ c ] += cell_start[ (size_t)gy * cols + c0 + c ];
+            }
+            const uint32_t total = P[ c1 - c0 ] - P[ 0 ];
+            uint8_t       *so    = strip_of + ( (size_t)ty * tiles_x + tx ) * wc;
+            int            strip = 0;
+            for ( int sx = cx0; sx < cx1; strip++ ) {
+                int ex = cx1;
+                if ( total > (uint32_t)strip_limit ) {
+                    ex = sx + 1;
+                    while ( ex < cx1 && P[ ( ex + 2 < c1 ? ex + 2 : c1 ) - c0 ] - P[ ( sx - 1 > c0 ? sx - 1 : c0 ) - c0 ] <= (uint32_t)strip_limit )
+                        ex++;
+                }
+                for ( int c = sx; c < ex; c++ )
+                    so[ c - cx0 ] = (uint8_t)strip;
+                sx = ex;
+            }
         }
     /* contact-list ranks (4. above) */
     uint32_t *cnt_j = (uint32_t *)calloc( n ? n : 1, sizeof( uint32_t ) ), *first_i = (uint32_t *)malloc( ( n ? n : 1 ) * sizeof( uint32_t ) );
@@ -456,7 +471,7 @@ void ppc_oracle_tilegs_order( const int32_t *pairs, size_t npairs, size_t n, con
         const int      cxj = (int)( keys[ j ] % (uint32_t)cols ), cyj = (int)( keys[ j ] / (uint32_t)cols );
         const int      txi = cxi / wc, tyi = ( cyi + row0 ) / tile_r - ty0, txj = cxj / wc, tyj = ( cyj + row0 ) / tile_r - ty0;
         const uint32_t ti = (uint32_t)( tyi * tiles_x + txi ), tj = (uint32_t)( tyj * tiles_x + txj );
-        const uint32_t si = (uint32_t)( ( cxi - txi * wc ) / strip_w[ ti ] ), sj = (uint32_t)( ( cxj - txj * wc ) / strip_w[ tj ] );
+        const uint32_t si = strip_of[ (size_t)ti * wc + ( cxi - txi * wc ) ], sj = strip_of[ (size_t)tj * wc + ( cxj - txj * wc ) ];
         const uint32_t ci = (uint32_t)( ( txi & 1 ) + 2 * ( ( tyi + ty0 ) & 1 ) ), cj = (uint32_t)( ( txj & 1 ) + 2 * ( ( tyj + ty0 ) & 1 ) );
         /* owner sub-tile (2.) and whether each particle lies inside it */
         int owner_is_i;
@@ -506,7 +521,7 @@ void ppc_oracle_tilegs_order( const int32_t *pairs, size_t npairs, size_t n, con
     free( rank_j );
     free( cnt_j );
     free( first_i );
-    free( strip_w );
+    free( strip_of );
 }
 
 /* Positions in the reference's list order, velocities in the order perm[] (a permutation of the pair list). */

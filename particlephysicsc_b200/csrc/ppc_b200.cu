@@ -235,9 +235,10 @@ static void check_device_flags( Store *st ) {   // after a stream synchronise
         uint32_t flags = 0;
         PPC_CK( cudaMemcpy( &flags, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
         if ( flags ) {
-            fprintf( stderr, "particlephysicsc_b200: \"resolve\"=3 cannot run this field (%s%s); use the default resolve\n",
+            fprintf( stderr, "particlephysicsc_b200: \"resolve\"=3 cannot run this field (%s%s%s); use the default resolve\n",
                      ( flags & GS_ERR_CAP ) ? "a one-column strip of a tile holds more particles than shared memory takes " : "",
-                     ( flags & GS_ERR_POOL ) ? "more contacts in one tile than its contact pool holds" : "" );
+                     ( flags & GS_ERR_POOL ) ? "more contacts in one tile than its contact pool holds " : "",
+                     ( flags & GS_ERR_DEPTH ) ? "a chain of more than 255 dependent pairs inside one tile" : "" );
             abort();
         }
     }
@@ -599,7 +600,8 @@ static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
         const double per_cell = (double)n / (double)G.cells;
         wc = (int)( (double)GS_TARGET / ( GS_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
     }
-    return wc < 2 ? 2 : ( wc > GS_MAXC - 2 ? GS_MAXC - 2 : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
+    const int wc_max = GS_THREADS / ( GS_R + 2 ) - 2 < GS_MAXC - 2 ? GS_THREADS / ( GS_R + 2 ) - 2 : GS_MAXC - 2;   // one thread per staged cell
+    return wc < 2 ? 2 : ( wc > wc_max ? wc_max : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
 }
 
 static void resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
@@ -1174,6 +1176,7 @@ extern "C" int64_t ppc_debug_hot_pairs( struct Particles_t *p, int32_t *pairs, s
     if ( !st->grid_valid || !st->pre_valid )
         return -1;
     PPC_CK( cudaStreamSynchronize( st->stream ) );
+    check_device_flags( st );
     if ( st->opt_resolve == 3 ) {
         if ( !st->gs_dump )
             return -1;

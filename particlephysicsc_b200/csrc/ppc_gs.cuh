@@ -17,7 +17,7 @@
 //  1. Tiles of GS_R cell rows x wc cell columns, anchored at the whole field's cell (0, 0), coloured
 //     (tx & 1) + 2 (ty & 1).  One launch per colour; tiles of one colour touch disjoint particles (a tile touches its
 //     cells and a one-cell halo; tiles are >= 2 cells wide).  A tile whose staged particles would overflow shared memory
-//     is cut into column strips, which its CTA runs one after the other.
+//     is cut into column strips (greedily from the left, as wide as fits), which its CTA runs one after the other.
 //  2. A pair belongs to the sub-tile (tile, strip) holding both particles, else to the EARLIER of the two sub-tiles
 //     (lower colour; inside a tile the lower strip).  The owner applies the impulse to both particles; what it did to a
 //     halo particle is written back to global memory, where that particle's own sub-tile picks it up later.  After a
@@ -44,13 +44,13 @@ namespace ppc {
 #define PPC_GS_MINBLOCKS 3
 #endif
 #ifndef PPC_GS_CAP
-#define PPC_GS_CAP 1408    // staged particles (centre + halo) per sub-tile
+#define PPC_GS_CAP 1152    // staged particles (centre + halo) per sub-tile
 #endif
 #ifndef PPC_GS_POOL
-#define PPC_GS_POOL 4096   // contact entries per sub-tile (a centre-centre pair takes two)
+#define PPC_GS_POOL 6144   // contact entries per sub-tile (a centre-centre pair takes two)
 #endif
 #ifndef PPC_GS_TARGET
-#define PPC_GS_TARGET 520  // centre particles per tile the host aims for
+#define PPC_GS_TARGET 430  // centre particles per tile the host aims for
 #endif
 #ifndef PPC_GS_TMA
 #define PPC_GS_TMA 1       // 0: stage with ordinary loads (debugging aid)
@@ -64,10 +64,10 @@ constexpr int      GS_F       = 4;                   // fine bins per cell
 constexpr int      GS_MAXC    = 64;                  // staged columns (centre + halo)
 constexpr int      GS_NB      = GS_MAXC * GS_F;      // fine bins per staged row
 constexpr int      GS_BINS    = ( GS_R + 2 ) * GS_NB;
-constexpr int      GS_STRIP_LIMIT = GS_CAP * 6 / 10; // staged particles above which a tile is cut into strips
+constexpr int      GS_STRIP_LIMIT = GS_CAP;          // staged particles (strip + halo) a strip may hold
 constexpr uint32_t GS_NONE    = 0xffffu;
 constexpr uint32_t GS_TOUCHED = 0x10000u;            // rec_b.aux: a sub-tile that owns a pair with this halo particle changed its velocity
-constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u;
+constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u;
 static_assert( GS_CAP <= 2048, "contact entries hold the partner in 11 bits" );
 static_assert( GS_BINS * 4 <= GS_POOL * 4, "the bin counters alias the contact pool" );
 static_assert( GS_BINS % GS_THREADS == 0, "bins per thread" );
@@ -83,6 +83,8 @@ struct GsSmem {
     float    inv_lut[ 256 ];        // 1 / (float)k, the inverse masses of :146-147
     uint32_t run_g0[ GS_R + 2 ], run_s0[ GS_R + 3 ], cen_g0[ GS_R + 1 ], cen_s0[ GS_R + 1 ];
     uint32_t wsum[ 32 ];
+    uint32_t colp[ GS_MAXC + 2 ];   // column sums of cell_start over the staged rows (strip planning)
+    uint32_t lcount[ 256 ];         // pairs per level, then running begin / end of each level in the level-sorted entry list
     uint32_t rmax_bits, pool_n, err;
     unsigned long long mbar;
 };
@@ -437,42 +439,174 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
         return;
     }
 
-    // ---- Gauss-Seidel over the pairs of this sub-tile: nine phases of disjoint cell pairs ----
-    const int ncell = ( GS_R + 2 ) * ncol;
-    const int row_g0 = G.row0 + cy0 - 1;   // whole-field row of staged row 0
+    // ---- Gauss-Seidel over the pairs of this sub-tile ----
+    // The ORDER is the nine phases of disjoint cell pairs described in the header; the EXECUTION is levelled: every pair gets
+    // level = 1 + max(level of the previous pair of either particle in that order), a cheap integer pass; pairs of one level
+    // share no particle and fire together, one thread per pair, all lanes busy.  Each particle still receives its impulses
+    // in exactly the order of the phases, so the result is the sequential one.
+    const int ncell  = ( GS_R + 2 ) * ncol;   // <= GS_THREADS (the host bounds the tile width): one thread per staged cell
+    const int row_g0 = G.row0 + cy0 - 1;      // whole-field row of staged row 0
+    uint16_t *seg    = T.fend;                // fend + perm are dead: entry numbers, first by (cell, direction), later by level
+    static_assert( sizeof( T.fend ) + sizeof( T.perm ) >= GS_POOL / 2 * sizeof( uint16_t ), "an anchored entry per pair" );
+    const int  xj = (int)threadIdx.x / ncol, xc = (int)threadIdx.x - xj * ncol;                       // this thread's cell
+    const bool x_in = (int)threadIdx.x < ncell && xj >= 1 && xj <= GS_R && c0 + xc >= cx0 && c0 + xc < cx1;   // anchors are centre particles
+    const uint32_t x_pb = x_in ? T.cstart[ xj * ( GS_MAXC + 1 ) + xc ] : 0u, x_pe = x_in ? T.cstart[ xj * ( GS_MAXC + 1 ) + xc + 1 ] : 0u;
+    // (a) anchored entries of this cell per direction code d * 3 + dc (nine 7-bit counters in one word)
+    unsigned long long cnt = 0ull;
+    uint32_t           mine = 0;
+#pragma unroll 1
+    for ( uint32_t a = x_pb; a < x_pe; a++ )
+#pragma unroll 1
+        for ( uint32_t e = __float_as_uint( T.b[ a ].w ) & 0xffffu; e != GS_NONE; e = T.pool_next[ e ] ) {
+            const uint32_t v = T.pool_val[ e ];
+            if ( v & 0x8000u ) {
+                cnt += 1ull << ( 7u * ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) );
+                mine++;
+            }
+        }
+    if ( threadIdx.x < 256 )
+        T.lcount[ threadIdx.x ] = 0u;
+    uint32_t seg_base;   // exclusive scan of `mine` over the CTA
+    {
+        uint32_t inc = mine;
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, inc, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d )
+                inc += o;
+        }
+        if ( ( threadIdx.x & 31u ) == 31u )
+            T.wsum[ threadIdx.x >> 5 ] = inc;
+        __syncthreads();
+        uint32_t ws = ( threadIdx.x & 31u ) < (unsigned)( GS_THREADS / 32 ) ? T.wsum[ threadIdx.x & 31u ] : 0u;
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, ws, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d )
+                ws += o;
+        }
+        const unsigned wid = threadIdx.x >> 5;
+        seg_base           = ( wid ? __shfl_sync( 0xffffffffu, ws, wid - 1 ) : 0u ) + inc - mine;
+        if ( __shfl_sync( 0xffffffffu, ws, GS_THREADS / 32 - 1 ) > (uint32_t)( ( sizeof( T.fend ) + sizeof( T.perm ) ) / sizeof( uint16_t ) ) )
+            T.err = GS_ERR_POOL;   // more pairs than the entry list takes (same value in every thread)
+    }
+    if ( mine > 127u )   // a 7-bit counter may have wrapped (dozens of particles on one spot): not a field for this mode
+        T.err = GS_ERR_POOL;
+    __syncthreads();
+    if ( T.err ) {
+        if ( threadIdx.x == 0 )
+            atomicOr( err_flags, T.err );
+        return;
+    }
+    // (b) entry numbers of this cell, grouped by direction code; the entry remembers its anchor where its link was
+    {
+        unsigned long long cur = 0ull;
+#pragma unroll 1
+        for ( uint32_t a = x_pb; a < x_pe; a++ )
+#pragma unroll 1
+            for ( uint32_t e = __float_as_uint( T.b[ a ].w ) & 0xffffu; e != GS_NONE; ) {
+                const uint32_t nxt = T.pool_next[ e ], v = T.pool_val[ e ];
+                if ( v & 0x8000u ) {
+                    const uint32_t code = ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u );
+                    uint32_t       pre  = 0;
+#pragma unroll
+                    for ( uint32_t k = 0; k < 8; k++ )
+                        pre += k < code ? (uint32_t)( cnt >> ( 7u * k ) ) & 127u : 0u;
+                    seg[ seg_base + pre + ( (uint32_t)( cur >> ( 7u * code ) ) & 127u ) ] = (uint16_t)e;
+                    cur += 1ull << ( 7u * code );
+                    T.pool_next[ e ] = (uint16_t)a;   // bits [10:0] anchor; [15:11] and pool_val [14:11] will hold the level
+                    T.pool_val[ e ]  = (uint16_t)( v & 0x87ffu );
+                }
+                e = nxt;
+            }
+    }
+    __syncthreads();
+    // (c) levels, phase by phase: in a phase a cell's thread walks the pairs of ONE direction code (towards the phase's other
+    //     cell when this cell is the base, i.e. has the phase's parity; backwards to a halo base cell otherwise)
 #pragma unroll 1
     for ( int phase = 0; phase < 9; phase++ ) {
         const int cls = phase == 0 ? 0 : ( phase + 1 ) >> 1;   // 0 same cell, 1 east, 2 south, 3 south-east, 4 south-west
         const int par = phase == 0 ? 0 : ( phase + 1 ) & 1;
-        const int dj = cls >= 2 ? 1 : 0, dcl = cls == 1 || cls == 3 ? 1 : ( cls == 4 ? -1 : 0 );
-        for ( int cell = threadIdx.x; cell < ncell; cell += GS_THREADS ) {
-            const int j = cell / ncol, c = cell - j * ncol;
-            if ( cls == 1 && ( ( c0 + c ) & 1 ) != par )
-                continue;
-            if ( cls >= 2 && ( ( row_g0 + j ) & 1 ) != par )
-                continue;
-            const int tj = j + dj, tc = c + dcl;
-            if ( tj > GS_R + 1 || tc < 0 || tc >= ncol )
-                continue;
-            const bool a_in = j >= 1 && j <= GS_R && c0 + c >= cx0 && c0 + c < cx1;
-            const bool b_in = tj >= 1 && tj <= GS_R && c0 + tc >= cx0 && c0 + tc < cx1;
-            if ( !a_in && !b_in )
-                continue;
-            // anchors sit in the base cell when it is inside the sub-tile, else in the other cell; the entry's direction is
-            // as seen from the anchor
-            const int      aj = a_in ? j : tj, ac = a_in ? c : tc;
-            const uint32_t want = 0x8000u | ( (uint32_t)( ( a_in ? dj : -dj ) + 1 ) << 11 ) | ( (uint32_t)( ( a_in ? dcl : -dcl ) + 1 ) << 13 );
-            const uint32_t pb = T.cstart[ aj * ( GS_MAXC + 1 ) + ac ], pe = T.cstart[ aj * ( GS_MAXC + 1 ) + ac + 1 ];
+        if ( x_in && mine ) {
+            const bool     base = cls == 0 || ( ( cls == 1 ? c0 + xc : row_g0 + xj ) & 1 ) == par;
+            const int      dj = cls >= 2 ? 1 : 0, dcl = cls == 1 || cls == 3 ? 1 : ( cls == 4 ? -1 : 0 );
+            const uint32_t code = (uint32_t)( ( ( base ? dj : -dj ) + 1 ) * 3 + ( base ? dcl : -dcl ) + 1 );
+            uint32_t       pre  = 0;
+#pragma unroll
+            for ( uint32_t k = 0; k < 8; k++ )
+                pre += k < code ? (uint32_t)( cnt >> ( 7u * k ) ) & 127u : 0u;
+            const uint32_t kb = seg_base + pre, ke = kb + ( (uint32_t)( cnt >> ( 7u * code ) ) & 127u );
 #pragma unroll 1
-            for ( uint32_t a = pb; a < pe; a++ )
-#pragma unroll 1
-                for ( uint32_t e = __float_as_uint( T.b[ a ].w ) & 0xffffu; e != GS_NONE; e = T.pool_next[ e ] ) {
-                    const uint32_t v = T.pool_val[ e ];
-                    if ( ( v & 0xf800u ) == want )
-                        gs_fire( T, a, v & 0x7ffu, dt );
+            for ( uint32_t k = kb; k < ke; k++ ) {
+                const uint32_t e = seg[ k ];
+                const uint32_t a = T.pool_next[ e ] & 0x7ffu, q = T.pool_val[ e ] & 0x7ffu;
+                uint32_t      *wa = reinterpret_cast<uint32_t *>( &T.b[ a ].w ), *wq = reinterpret_cast<uint32_t *>( &T.b[ q ].w );
+                const uint32_t ua = *wa, uq = *wq;
+                uint32_t       lv = max( ( ua >> 17 ) & 0x3ffu, ( uq >> 17 ) & 0x3ffu ) + 1u;
+                if ( lv > 255u ) {
+                    T.err = GS_ERR_DEPTH;
+                    lv    = 255u;
                 }
+                *wa = ( ua & 0x1ffffu ) | ( lv << 17 );
+                *wq = ( uq & 0x1ffffu ) | ( lv << 17 );
+                T.pool_val[ e ]  = (uint16_t)( 0x8000u | q | ( ( lv & 15u ) << 11 ) );
+                T.pool_next[ e ] = (uint16_t)( a | ( ( lv >> 4 ) << 11 ) );
+                atomicAdd( &T.lcount[ lv ], 1u );
+            }
         }
         __syncthreads();
+    }
+    if ( T.err ) {
+        if ( threadIdx.x == 0 )
+            atomicOr( err_flags, T.err );
+        return;
+    }
+    // (d) entries by level: scan of the level counts, scatter (the order inside a level is immaterial)
+    const uint32_t n_entries = min( T.pool_n, (uint32_t)GS_POOL );
+    if ( threadIdx.x < 32 ) {
+        uint32_t loc[ 8 ], sum = 0;
+#pragma unroll
+        for ( int i = 0; i < 8; i++ ) {
+            loc[ i ] = T.lcount[ threadIdx.x * 8 + i ];
+            sum += loc[ i ];
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, inc, d );
+            if ( threadIdx.x >= (unsigned)d )
+                inc += o;
+        }
+        uint32_t run = inc - sum;
+#pragma unroll
+        for ( int i = 0; i < 8; i++ ) {
+            T.lcount[ threadIdx.x * 8 + i ] = run;   // begin of the level; the scatter advances it to the end
+            run += loc[ i ];
+        }
+        if ( threadIdx.x == 31 )
+            T.wsum[ 0 ] = run;   // pairs of this sub-tile
+    }
+    __syncthreads();
+    const uint32_t n_pairs = T.wsum[ 0 ];
+    for ( uint32_t e = threadIdx.x; e < n_entries; e += GS_THREADS ) {
+        const uint32_t v = T.pool_val[ e ];
+        if ( v & 0x8000u )
+            seg[ atomicAdd( &T.lcount[ ( ( v >> 11 ) & 15u ) | ( ( (uint32_t)T.pool_next[ e ] >> 11 ) << 4 ) ], 1u ) ] = (uint16_t)e;
+    }
+    __syncthreads();
+    // (e) fire, level by level
+    {
+        uint32_t kb = 0;
+#pragma unroll 1
+        for ( uint32_t lv = 1; kb < n_pairs; lv++ ) {
+            const uint32_t ke = T.lcount[ lv ];
+            for ( uint32_t k = kb + threadIdx.x; k < ke; k += GS_THREADS ) {
+                const uint32_t e = seg[ k ];
+                gs_fire( T, T.pool_next[ e ] & 0x7ffu, T.pool_val[ e ] & 0x7ffu, dt );
+            }
+            kb = ke;
+            __syncthreads();
+        }
     }
 
     // ---- final velocities of this sub-tile's particles; velocities of halo particles it changed go back in place ----
@@ -505,27 +639,35 @@ __global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_collide_gs( 
     const int cy0 = tyg * GS_R - G.row0;                                   // may be negative for a slab window's first tile row
     if ( threadIdx.x == 0 )
         mbar_init( reinterpret_cast<uint64_t *>( &T.mbar ), 1u );
-    // staged particle count of the whole tile; a tile that would overflow shared memory is cut into column strips that fit
+    // Column sums of the tile and its halo: cell_start is a running sum along a grid row, so P[c] = sum over the staged rows of
+    // cell_start[row][c0 + c] makes the staged particle count of the columns [a, b) equal to P[b] - P[a].
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );
-    if ( threadIdx.x < GS_R + 2 ) {
-        const int gy = cy0 - 1 + (int)threadIdx.x;
-        uint32_t  len = 0;
-        if ( gy >= 0 && gy < G.rows )
-            len = cell_start[ (size_t)gy * G.cols + c1 ] - cell_start[ (size_t)gy * G.cols + c0 ];
-        T.run_s0[ threadIdx.x ] = len;
+    for ( int c = threadIdx.x; c <= c1 - c0; c += GS_THREADS ) {
+        uint32_t sum = 0;
+        for ( int j = 0; j < GS_R + 2; j++ ) {
+            const int gy = cy0 - 1 + j;
+            if ( gy >= 0 && gy < G.rows )
+                sum += cell_start[ (size_t)gy * G.cols + c0 + c ];
+        }
+        T.colp[ c ] = sum;
     }
     __syncthreads();
-    uint32_t total = 0;
-#pragma unroll
-    for ( int j = 0; j < GS_R + 2; j++ )
-        total += T.run_s0[ j ];
+    const uint32_t total = T.colp[ c1 - c0 ] - T.colp[ 0 ];
     if ( total == 0 )
         return;
-    const int strips = (int)( ( total + GS_STRIP_LIMIT - 1 ) / GS_STRIP_LIMIT );
-    const int sw     = max( ( cx1 - cx0 + strips - 1 ) / strips, 1 );
-    uint32_t  parity = 0;
-    for ( int sx = cx0; sx < cx1; sx += sw )
-        gs_subtile( T, rec_a, rec_b, pv_out, cell_start, G, dt, sx, min( sx + sw, cx1 ), cx0, cx1, cy0, tx, tyg, L.colour, parity, sx != cx0, err_flags, D );
+    // A tile that would overflow shared memory is cut into column strips, greedily from the left: each strip takes as many
+    // columns as keep its staged particles (strip + one halo column either side) within GS_STRIP_LIMIT, and at least one.
+    uint32_t parity = 0;
+    for ( int sx = cx0; sx < cx1; ) {
+        int ex = cx1;
+        if ( total > (uint32_t)GS_STRIP_LIMIT ) {
+            ex = sx + 1;
+            while ( ex < cx1 && T.colp[ min( ex + 2, c1 ) - c0 ] - T.colp[ max( sx - 1, c0 ) - c0 ] <= (uint32_t)GS_STRIP_LIMIT )
+                ex++;
+        }
+        gs_subtile( T, rec_a, rec_b, pv_out, cell_start, G, dt, sx, ex, cx0, cx1, cy0, tx, tyg, L.colour, parity, sx != cx0, err_flags, D );
+        sx = ex;
+    }
 }
 
 }   // namespace ppc
