@@ -73,8 +73,13 @@ struct Store {
     size_t       scratch_words = 0;
     uint32_t    *d_word = nullptr;   // one word for small reductions
     // "resolve"=3 (tile Gauss-Seidel, ppc_gs.cuh): the staged records, error flags, tile width of the last substep, pair dump
-    float4      *rec_a = nullptr, *rec_b = nullptr;
-    uint32_t    *gs_flags = nullptr, *gs_dump = nullptr;   // gs_flags[0] error bits, [1] pairs dumped
+    float4      *rec_a = nullptr;
+    uint16_t    *gs_mcol = nullptr;
+    uint4       *gs_chunks = nullptr;                       // pair records of the current substep, one chunk per sub-tile
+    uint32_t     gs_chunk_cap = 0;                          // 16-byte units
+    uint2       *gs_desc = nullptr;                         // chunk of every (tile, strip)
+    size_t       gs_desc_cap = 0;
+    uint32_t    *gs_flags = nullptr, *gs_dump = nullptr;   // gs_flags[0] error bits, [1] pairs dumped, [2] chunk units handed out
     uint32_t     gs_dump_cap = 0;
     int          gs_wc = 0;
     bool         gs_attr_set = false;
@@ -235,10 +240,11 @@ static void check_device_flags( Store *st ) {   // after a stream synchronise
         uint32_t flags = 0;
         PPC_CK( cudaMemcpy( &flags, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
         if ( flags ) {
-            fprintf( stderr, "particlephysicsc_b200: \"resolve\"=3 cannot run this field (%s%s%s); use the default resolve\n",
+            fprintf( stderr, "particlephysicsc_b200: \"resolve\"=3 cannot run this field (%s%s%s%s); use the default resolve\n",
                      ( flags & GS_ERR_CAP ) ? "a one-column strip of a tile holds more particles than shared memory takes " : "",
                      ( flags & GS_ERR_POOL ) ? "more contacts in one tile than its contact pool holds " : "",
-                     ( flags & GS_ERR_DEPTH ) ? "a chain of more than 255 dependent pairs inside one tile" : "" );
+                     ( flags & GS_ERR_DEPTH ) ? "more than 127 owned contacts in one cell, or a chain of more than 255 dependent pairs inside one tile " : "",
+                     ( flags & GS_ERR_CHUNK ) ? "pair-record buffer full" : "" );
             abort();
         }
     }
@@ -255,22 +261,32 @@ static void check_device_flags( Store *st ) {   // after a stream synchronise
 
 static void free_gs_buffers( Store *st ) {
     cudaFree( st->rec_a );
-    cudaFree( st->rec_b );
+    cudaFree( st->gs_mcol );
+    cudaFree( st->gs_chunks );
+    cudaFree( st->gs_desc );
     cudaFree( st->gs_dump );
-    st->rec_a = st->rec_b = nullptr;
+    st->rec_a       = nullptr;
+    st->gs_mcol     = nullptr;
+    st->gs_chunks   = nullptr;
+    st->gs_desc     = nullptr;
+    st->gs_desc_cap = 0;
     st->gs_dump     = nullptr;
     st->gs_dump_cap = 0;
 }
 
-// Buffers of the tile Gauss-Seidel path, on first use: 32 bytes of staged records per particle.
+// Buffers of the tile Gauss-Seidel path, on first use: 18 bytes of staged records per particle plus the pair records.
 static void ensure_gs_buffers( Store *st ) {
     if ( !st->gs_flags ) {
         st->gs_flags = dev_alloc<uint32_t>( 4 );
         PPC_CK( cudaMemsetAsync( st->gs_flags, 0, 4 * sizeof( uint32_t ), st->stream ) );
     }
     if ( !st->rec_a ) {
-        st->rec_a = dev_alloc<float4>( st->cap );
-        st->rec_b = dev_alloc<float4>( st->cap );
+        st->rec_a   = dev_alloc<float4>( st->cap );
+        st->gs_mcol = dev_alloc<uint16_t>( st->cap + 16 );   // bulk copies of the 16-bit words round their ends up to 16 bytes
+        // pair records: 16 bytes per pair plus a small header per sub-tile; a dense pile has ~3 pairs per particle
+        const size_t units = st->cap * 6 + ( (size_t)1 << 20 );
+        st->gs_chunk_cap   = (uint32_t)( units < 0xfffffff0u ? units : 0xfffffff0u );
+        st->gs_chunks      = dev_alloc<uint4>( st->gs_chunk_cap );
     }
     if ( st->opt_gs_dump && !st->gs_dump ) {
         st->gs_dump_cap = (uint32_t)( st->cap * 8 < 0x7fffffffu ? st->cap * 8 : 0x7fffffffu );
@@ -583,9 +599,9 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
     }
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
-        const bool gs = st->opt_resolve == 3;   // the moving state goes into the tile kernel's staged records
+        const bool gs = st->opt_resolve == 3;   // also leave the records the tile kernel stages
         PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
-                    st->col_valid ? 1 : 0, unranked_cell, gs ? st->rec_a : (float4 *)nullptr, gs ? st->rec_b : (float4 *)nullptr,
+                    st->col_valid ? 1 : 0, unranked_cell, gs ? st->rec_a : (float4 *)nullptr, gs ? st->gs_mcol : (uint16_t *)nullptr,
                     (uint32_t)cols );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
@@ -605,21 +621,33 @@ static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
 }
 
 static void resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
-    StageTimer T( st, ST_COLLIDE );
     if ( !st->gs_attr_set ) {
-        PPC_CK( cudaFuncSetAttribute( k_collide_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( GsSmem ) ) );
+        PPC_CK( cudaFuncSetAttribute( k_gs_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( GsSmem ) ) );
         st->gs_attr_set = true;
     }
-    GsLaunch L;
+    GsLaunch L = {};
     L.wc       = st->gs_wc = gs_tile_width( st, n, G );
     L.tiles_x  = ( G.cols + L.wc - 1 ) / L.wc;
     L.ty_first = G.row0 / GS_R;
-    const int tiles_y = ( G.row0 + G.rows + GS_R - 1 ) / GS_R - L.ty_first;
-    GsDump    D{ nullptr, nullptr, 0u };
-    if ( st->opt_gs_dump ) {
-        PPC_CK( cudaMemsetAsync( st->gs_flags + 1, 0, sizeof( uint32_t ), st->stream ) );
-        D = GsDump{ st->gs_dump, st->gs_flags + 1, st->gs_dump_cap };
+    const int    tiles_y = ( G.row0 + G.rows + GS_R - 1 ) / GS_R - L.ty_first;
+    const size_t tiles   = (size_t)L.tiles_x * tiles_y;
+    if ( tiles * GS_MAXSTRIPS > st->gs_desc_cap ) {
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        cudaFree( st->gs_desc );
+        st->gs_desc_cap = tiles * GS_MAXSTRIPS + tiles * GS_MAXSTRIPS / 8;
+        st->gs_desc     = dev_alloc<uint2>( st->gs_desc_cap );
     }
+    const GsPairs PR{ st->gs_chunks, st->gs_flags + 2, st->gs_chunk_cap, st->gs_desc };
+    GsDump        D{ nullptr, nullptr, 0u };
+    PPC_CK( cudaMemsetAsync( st->gs_flags + 1, 0, 2 * sizeof( uint32_t ), st->stream ) );
+    if ( st->opt_gs_dump )
+        D = GsDump{ st->gs_dump, st->gs_flags + 1, st->gs_dump_cap };
+    {
+        StageTimer T( st, ST_COLLIDE );   // narrow phase, position pushes, pair records: all tiles at once
+        PPC_LAUNCH( k_gs_pairs, (unsigned)tiles, GS_THREADS, sizeof( GsSmem ), st->stream, (const float4 *)st->rec_a, (const uint16_t *)st->gs_mcol,
+                    st->set[ st->cur ].pv, st->cell_start, G, dt, L, PR, st->gs_flags, D );
+    }
+    StageTimer T( st, ST_WAVEFRONT );     // velocity impulses: tiles of one colour at a time
     for ( int colour = 0; colour < 4; colour++ ) {
         L.colour   = colour;
         L.ntx      = ( L.tiles_x - ( colour & 1 ) + 1 ) / 2;
@@ -627,8 +655,7 @@ static void resolve_gs( Store *st, const size_t n, const GridDims &G, const floa
         const int nty = ( tiles_y - L.ty_start + 1 ) / 2;
         if ( L.ntx <= 0 || nty <= 0 )
             continue;
-        PPC_LAUNCH( k_collide_gs, (unsigned)( L.ntx * nty ), GS_THREADS, sizeof( GsSmem ), st->stream, st->rec_a, st->rec_b, st->set[ st->cur ].pv,
-                    st->cell_start, G, dt, L, st->gs_flags, D );
+        PPC_LAUNCH( k_gs_resolve, (unsigned)( L.ntx * nty ), GSB_THREADS, 0, st->stream, (const uint16_t *)st->gs_mcol, st->set[ st->cur ].pv, L, PR );
     }
 }
 
@@ -1126,7 +1153,7 @@ extern "C" int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_
     if ( st->opt_resolve )
         pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw (before the resolve moved anything)
     if ( st->opt_resolve == 3 )               // ... which in this mode live in the staged records
-        PPC_LAUNCH( k_rec_to_pv, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, (const float4 *)st->rec_b, pre.pv, n );
+        PPC_LAUNCH( k_rec_to_pv, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, pre.pv, n );
     uint32_t *count  = st->sort_keys_a;       // n + 1 words needed; sort_keys_a has cap >= n, use scratch when tight
     uint32_t *offset = st->sort_keys_b;
     uint32_t *tmp    = nullptr;
@@ -1540,8 +1567,7 @@ extern "C" int64_t ppc_slab_debug_pairs( struct Particles_t *p, int32_t *pairs, 
     if ( st->opt_resolve )
         pre.pv = st->set[ st->cur ^ 1 ].pv;   // positions the pair search saw
     if ( st->opt_resolve == 3 )
-        PPC_LAUNCH( k_rec_to_pv, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, (const float4 *)st->rec_b, pre.pv,
-                    st->n );
+        PPC_LAUNCH( k_rec_to_pv, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, pre.pv, st->n );
     const size_t padded = ( n + 1 + 63 ) & ~(size_t)63;
     uint32_t    *tmp    = dev_alloc<uint32_t>( 2 * padded );
     uint32_t    *count = tmp, *offset = tmp + padded;

@@ -102,14 +102,13 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
 // particles of the same cell with a smaller API index).  That makes storage the stable ascending (key, index)
 // order -- the canonical form of the reference's chains (:293-294) -- whatever order the scatter or the radix
 // sort left inside the cell.  Then the whole particle record moves from the old set to the new one.
-// With rec_a / rec_b given ("resolve"=3) the moving state goes into the two 16-byte records the tile kernel stages with
-// bulk copies (ppc_gs.cuh) instead of Out.pv, which that kernel then writes itself:
-//   rec_a = {x, y, radius, API index}   rec_b = {v_x, v_y, mass byte (:141-142) | cell column byte << 8, empty list head}
+// With rec_a / mcol given ("resolve"=3) the gather also leaves what the tile kernel stages with bulk copies (ppc_gs.cuh):
+//   rec_a = {x, y, radius, API index}   mcol = mass byte (:141-142) | cell column byte << 8
 __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const ParticleSet In, const ParticleSet Out,
                                                                         const uint32_t *__restrict__ slot_of,
                                                                         const uint32_t *__restrict__ cell_start, const size_t n,
                                                                         const int move_colour, const uint32_t unranked_cell,
-                                                                        float4 *__restrict__ rec_a, float4 *__restrict__ rec_b, const uint32_t cols ) {
+                                                                        float4 *__restrict__ rec_a, uint16_t *__restrict__ mcol, const uint32_t cols ) {
     const size_t pos = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( pos >= n )
         return;
@@ -129,10 +128,9 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
     if ( rec_a ) {
         const uint32_t cx = c - ( c / cols ) * cols;
         rec_a[ dst ] = make_float4( s4.x, s4.y, a2.x, __uint_as_float( g ) );
-        rec_b[ dst ] = make_float4( s4.z, s4.w, __uint_as_float( ( (unsigned)__float2int_rz( a2.y ) & 0xffu ) | ( ( cx & 0xffu ) << 8 ) ),
-                                    __uint_as_float( 0xffffu ) );
-    } else
-        Out.pv[ dst ] = s4;
+        mcol[ dst ]  = (uint16_t)( ( (unsigned)__float2int_rz( a2.y ) & 0xffu ) | ( ( cx & 0xffu ) << 8 ) );
+    }
+    Out.pv[ dst ]  = s4;
     Out.rm[ dst ]  = a2;
     Out.gid[ dst ] = g;
     Out.key[ dst ] = c;
@@ -180,13 +178,12 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_unpack_download( const Par
 }
 
 // "resolve"=3 keeps the pre-resolve positions in the tile kernel's staged records; the pair exporter wants them as pv
-__global__ void __launch_bounds__( STREAM_THREADS ) k_rec_to_pv( const float4 *__restrict__ rec_a, const float4 *__restrict__ rec_b,
-                                                                 float4 *__restrict__ pv, const size_t n ) {
+__global__ void __launch_bounds__( STREAM_THREADS ) k_rec_to_pv( const float4 *__restrict__ rec_a, float4 *__restrict__ pv, const size_t n ) {
     const size_t k = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( k >= n )
         return;
-    const float4 a = rec_a[ k ], b = rec_b[ k ];
-    pv[ k ] = make_float4( a.x, a.y, b.x, b.y );
+    const float4 a = rec_a[ k ];
+    pv[ k ] = make_float4( a.x, a.y, 0.0f, 0.0f );
 }
 
 // keys by API index / sorted order, for the parity exporters

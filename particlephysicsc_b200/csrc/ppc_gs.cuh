@@ -1,10 +1,10 @@
 // ppc_gs.cuh -- K7 of the "resolve"=3 path: narrow phase, position pushes and a bounded-pass, deterministic Gauss-Seidel
-// velocity resolve, all inside the shared memory of one tile.  No contact lists in global memory, no cooperative launch,
-// no grid-wide rounds: four ordinary launches (one per tile colour) per substep.
+// velocity resolve, tile by tile in shared memory.  No per-particle contact lists in global memory, no cooperative launch,
+// no grid-wide dependency rounds: one launch of k_gs_pairs and four launches (one per tile colour) of k_gs_resolve per substep.
 //
 // Relation to the reference (src/particles_solver.c):
 //  * candidate pairs: the reference's (3x3 cell neighbourhood :331-340, AABB reject and inclusive circle test :352-362,
-//    same float operations) -- as in k_collide_tile2 (ppc_collide.cuh), whose fine x-bins this kernel shares;
+//    same float operations) -- as in k_collide_tile2 (ppc_collide.cuh), whose fine x-bins k_gs_pairs shares;
 //  * contact geometry frozen before anything moves (pass 1, :84-127); position pushes (:145-156) summed per particle in
 //    the order the reference's pair list touches it, so POSITIONS ARE BIT-IDENTICAL to the reference;
 //  * velocity impulses (:158-190): every pair is applied exactly once, from the CURRENT velocities of its two particles,
@@ -15,22 +15,29 @@
 //
 // The order (see also the oracle):
 //  1. Tiles of GS_R cell rows x wc cell columns, anchored at the whole field's cell (0, 0), coloured
-//     (tx & 1) + 2 (ty & 1).  One launch per colour; tiles of one colour touch disjoint particles (a tile touches its
-//     cells and a one-cell halo; tiles are >= 2 cells wide).  A tile whose staged particles would overflow shared memory
-//     is cut into column strips (greedily from the left, as wide as fits), which its CTA runs one after the other.
+//     (tx & 1) + 2 (ty & 1).  Tiles of one colour touch disjoint particles (a tile touches its cells and a one-cell halo;
+//     tiles are >= 2 cells wide).  A tile whose staged particles would overflow shared memory is cut into column strips
+//     (greedily from the left, as wide as fits), which its CTA runs one after the other.
 //  2. A pair belongs to the sub-tile (tile, strip) holding both particles, else to the EARLIER of the two sub-tiles
 //     (lower colour; inside a tile the lower strip).  The owner applies the impulse to both particles; what it did to a
-//     halo particle is written back to global memory, where that particle's own sub-tile picks it up later.  After a
-//     sub-tile has run, all pairs of its own particles are done, so it writes their final state.
-//  3. Inside a sub-tile, nine phases separated by CTA barriers: pairs inside one cell; pairs with the east neighbour cell,
-//     base column even / odd; with the south, south-east, south-west neighbour, base row even / odd.  The cell pairs of
-//     one phase are disjoint, so one thread per cell pair runs its pairs one after the other with no conflicts.
+//     halo particle is in global memory before that particle's own sub-tile runs.
+//  3. Inside a sub-tile, nine phases: pairs inside one cell; pairs with the east neighbour cell, base column even / odd;
+//     with the south, south-east, south-west neighbour, base row even / odd.  The cell pairs of one phase are disjoint.
 //  4. Inside a cell pair: by anchor particle (ascending index), then by position in the anchor's contact list.
 //
-// Data movement: the canonical gather (ppc_grid.cuh) leaves two 16-byte records per particle in sorted order,
-//   rec_a = {x, y, radius, API index}    rec_b = {v_x, v_y, mass byte | cell column byte << 8, list head = none}
-// so the GS_R + 2 slot runs of a tile and its halo are contiguous byte ranges, staged by the TMA (cp.async.bulk +
-// mbarrier, ppc_tma.cuh): no load instructions, no address arithmetic per particle.
+// Execution.  Positions do not depend on velocities, so the work splits into two kernels:
+//   k_gs_pairs   (all tiles at once)  stages a tile and its halo, finds the contacts of every centre particle, adds its
+//                position pushes in the reference's order, and writes the pairs the sub-tile owns as 16-byte records
+//                {particle numbers, unit normal, Baumgarte term} into one contiguous chunk per sub-tile, sorted by
+//                LEVEL = 1 + the level of the previous pair of either particle in the order above.  Pairs of one level share no particle.
+//   k_gs_resolve (one launch per colour)  loads the current velocities of a sub-tile and its halo, then fires the records
+//                level by level, one thread per pair, and writes back what changed.  Each particle receives its impulses
+//                in exactly the order of 3. and 4., so the result is the sequential one.
+//
+// Data movement: the canonical gather (ppc_grid.cuh) leaves, besides the ordinary sorted state, one 16-byte record
+// {x, y, radius, API index} and one 16-bit word {mass byte, cell column byte} per particle in sorted order, so the GS_R + 2
+// slot runs of a tile and its halo are contiguous byte ranges, staged by the TMA (cp.async.bulk + mbarrier, ppc_tma.cuh):
+// no load instructions and no address arithmetic per staged particle.
 #pragma once
 #include "ppc_collide.cuh"
 #include "ppc_tma.cuh"
@@ -44,48 +51,64 @@ namespace ppc {
 #define PPC_GS_MINBLOCKS 3
 #endif
 #ifndef PPC_GS_CAP
-#define PPC_GS_CAP 1152    // staged particles (centre + halo) per sub-tile
+#define PPC_GS_CAP 1024    // staged particles (centre + halo) per sub-tile
 #endif
 #ifndef PPC_GS_POOL
 #define PPC_GS_POOL 6144   // contact entries per sub-tile (a centre-centre pair takes two)
 #endif
 #ifndef PPC_GS_TARGET
-#define PPC_GS_TARGET 430  // centre particles per tile the host aims for
+#define PPC_GS_TARGET 520  // centre particles per tile the host aims for
 #endif
 #ifndef PPC_GS_TMA
 #define PPC_GS_TMA 1       // 0: stage with ordinary loads (debugging aid)
 #endif
-constexpr int      GS_THREADS = PPC_GS_THREADS;
-constexpr int      GS_R       = TILE_R;              // centre rows per tile
-constexpr int      GS_CAP     = PPC_GS_CAP;
-constexpr int      GS_POOL    = PPC_GS_POOL;
-constexpr int      GS_TARGET  = PPC_GS_TARGET;
-constexpr int      GS_F       = 4;                   // fine bins per cell
-constexpr int      GS_MAXC    = 64;                  // staged columns (centre + halo)
-constexpr int      GS_NB      = GS_MAXC * GS_F;      // fine bins per staged row
-constexpr int      GS_BINS    = ( GS_R + 2 ) * GS_NB;
-constexpr int      GS_STRIP_LIMIT = GS_CAP;          // staged particles (strip + halo) a strip may hold
-constexpr uint32_t GS_NONE    = 0xffffu;
-constexpr uint32_t GS_TOUCHED = 0x10000u;            // rec_b.aux: a sub-tile that owns a pair with this halo particle changed its velocity
-constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u;
-static_assert( GS_CAP <= 2048, "contact entries hold the partner in 11 bits" );
+#ifndef PPC_GSB_THREADS
+#define PPC_GSB_THREADS 128
+#endif
+#ifndef PPC_GSB_SLICE
+#define PPC_GSB_SLICE 256  // pair records per slice of the chunk k_gs_resolve streams through shared memory
+#endif
+constexpr int      GS_THREADS  = PPC_GS_THREADS;
+constexpr int      GSB_THREADS = PPC_GSB_THREADS;
+constexpr int      GSB_SLICE   = PPC_GSB_SLICE;
+constexpr int      GS_R        = TILE_R;              // centre rows per tile
+constexpr int      GS_CAP      = PPC_GS_CAP;
+constexpr int      GS_POOL     = PPC_GS_POOL;
+constexpr int      GS_TARGET   = PPC_GS_TARGET;
+constexpr int      GS_F        = 4;                   // fine bins per cell
+constexpr int      GS_MAXC     = 64;                  // staged columns (centre + halo)
+constexpr int      GS_NB       = GS_MAXC * GS_F;      // fine bins per staged row
+constexpr int      GS_BINS     = ( GS_R + 2 ) * GS_NB;
+constexpr int      GS_STRIP_LIMIT = GS_CAP;           // staged particles (strip + halo) a strip may hold
+constexpr int      GS_BUCKETS  = 256;                 // levels a sub-tile's pairs may span (level 0 is unused)
+constexpr int      GS_MAXSTRIPS = 64;                 // descriptor slots per tile (a strip is at least one column, a tile <= 62)
+constexpr int      GS_MC_PAD   = 8;                   // mass/column words are copied from an 8-element (16-byte) boundary
+constexpr uint32_t GS_NONE     = 0xffffu;
+constexpr uint32_t GS_LAST_STRIP = 0x80000000u;
+constexpr uint32_t GS_HDR_UNITS = ( 2 * ( GS_R + 2 ) + 1 + 3 ) / 4;   // 21 words
+constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u, GS_ERR_CHUNK = 8u;
+static_assert( GS_CAP <= 2048, "contact entries and pair records hold a particle in 11 bits" );
 static_assert( GS_BINS * 4 <= GS_POOL * 4, "the bin counters alias the contact pool" );
 static_assert( GS_BINS % GS_THREADS == 0, "bins per thread" );
 
 struct GsSmem {
     float4   a[ GS_CAP ];           // x, y, radius, API index (bits), in storage order
-    float4   b[ GS_CAP ];           // v_x, v_y (current), mass byte | column byte << 8, list head | flags
     uint16_t pool_val[ GS_POOL ];   // contact entry: partner [10:0], row offset + 1 [12:11], column offset + 1 [14:13], anchored [15]
     uint16_t pool_next[ GS_POOL ];  // next entry of the same particle; the two arrays double as 32-bit bin counters during binning
+    uint16_t pool_aux[ GS_POOL ];   // level of an entry that stands for a pair this sub-tile owns
     uint16_t fend[ GS_BINS ];       // end (exclusive) of fine bin f = row * GS_NB + bin in perm; its begin is fend[f - 1]
     uint16_t perm[ GS_CAP ];        // staged indices sorted by (staged row, fine bin)
+    uint16_t mc[ GS_CAP + ( GS_R + 2 ) * 2 * GS_MC_PAD ];   // mass byte | cell column byte << 8, row by row from 16-byte boundaries
+    uint16_t head[ GS_CAP ];        // first contact entry of a centre particle
+    uint8_t  lvl[ GS_CAP ];         // level of the latest pair of every staged particle
     uint16_t cstart[ ( GS_R + 2 ) * ( GS_MAXC + 1 ) ];   // first staged index of staged cell (row, column); [row][ncol] = end of the row
     float    inv_lut[ 256 ];        // 1 / (float)k, the inverse masses of :146-147
     uint32_t run_g0[ GS_R + 2 ], run_s0[ GS_R + 3 ], cen_g0[ GS_R + 1 ], cen_s0[ GS_R + 1 ];
-    uint32_t wsum[ 32 ];
+    uint32_t mc_s0[ GS_R + 2 ];     // mc index of the first staged particle of each row
+    uint32_t wsum[ 32 ], wsum2[ 32 ];
     uint32_t colp[ GS_MAXC + 2 ];   // column sums of cell_start over the staged rows (strip planning)
-    uint32_t lcount[ 256 ];         // pairs per level, then running begin / end of each level in the level-sorted entry list
-    uint32_t rmax_bits, pool_n, err;
+    uint32_t bcount[ GS_BUCKETS ];  // pairs per level, then running begin / end of each level in the record chunk
+    uint32_t rmax_bits, pool_n, err, chunk_base, n_buckets, phase_mask;
     unsigned long long mbar;
 };
 
@@ -93,12 +116,26 @@ struct GsLaunch {
     int wc;          // tile width in cells
     int tiles_x;     // tiles per tile row
     int ty_first;    // global tile row of the grid's first row (slab windows; 0 for a whole field)
-    int colour;      // 0..3: (tx & 1) + 2 (ty & 1) of the tiles this launch runs
-    int ntx;         // tiles of this colour per tile row
-    int ty_start;    // first local tile row of this colour
+    int colour;      // k_gs_resolve: 0..3 = (tx & 1) + 2 (ty & 1) of the tiles this launch runs
+    int ntx;         // k_gs_resolve: tiles of this colour per tile row
+    int ty_start;    // k_gs_resolve: first local tile row of this colour
 };
 
-// optional dump of the pairs this kernel resolves (parity tests: the hot kernel's own pair set)
+// Pair records of one substep: one chunk per sub-tile, allocated with one atomic add, in units of 16 bytes:
+//   GS_HDR_UNITS      run table of the sub-tile: first storage slot of each of its GS_R + 2 staged rows, then the running
+//                     staged count at the begin of each row and in total (k_gs_resolve maps staged numbers to slots with it)
+//   then              bucket table: end (exclusive) of every bucket in use, 16-bit, in bucket order, padded to whole units
+//   then              one record per pair, sorted by bucket: {lo [10:0] | hi [21:11] (staged indices; lo = the lower API
+//                     index = the reference's i), n_x, n_y, Baumgarte velocity term}
+struct GsPairs {
+    uint4    *chunks;
+    uint32_t *cursor;   // units handed out so far
+    uint32_t  cap;      // units
+    uint2    *desc;     // [tile * GS_MAXSTRIPS + strip] = {first unit of that sub-tile's chunk + 1 (0: it owns no pair),
+                        //  pairs | buckets in use << 16 | GS_LAST_STRIP for the tile's last strip}
+};
+
+// optional dump of the pairs k_gs_pairs hands to the resolve (parity tests: the hot kernel's own pair set)
 struct GsDump {
     uint32_t *pairs;   // 2 words per pair: API index of i, of j
     uint32_t *count;
@@ -111,38 +148,39 @@ __device__ __forceinline__ int gs_fine_bin( const float x, const float x0, const
     return b < nb ? b : nb - 1;
 }
 
-// One Gauss-Seidel step: the impulse of :158-190 for the pair (a, p) from the current velocities in shared memory.
-__device__ __forceinline__ void gs_fire( GsSmem &T, const uint32_t a, const uint32_t p, const float dt ) {
-    const float4   A = T.a[ a ], P = T.a[ p ];
-    const bool     a_lo = __float_as_uint( A.w ) < __float_as_uint( P.w );   // lo = the lower API index = the reference's i
-    const uint32_t lo = a_lo ? a : p, hi = a_lo ? p : a;
-    const float4   L = a_lo ? A : P, H = a_lo ? P : A;
-    const ContactGeom C = contact_geom( L.x, L.y, L.z, H.x, H.y, H.z, dt );
-    float2      *vl = reinterpret_cast<float2 *>( &T.b[ lo ] ), *vh = reinterpret_cast<float2 *>( &T.b[ hi ] );
-    float2       ul = *vl, uh = *vh;
-    const float  wl = T.inv_lut[ __float_as_uint( T.b[ lo ].z ) & 0xffu ], wh = T.inv_lut[ __float_as_uint( T.b[ hi ].z ) & 0xffu ];
-    const ImpulseTerms I = impulse_terms( C, wl, wh, ul.x, ul.y, uh.x, uh.y );
-    if ( I.impulse ) {
-        ul.x = __fadd_rn( ul.x, I.dvx_lo );
-        ul.y = __fadd_rn( ul.y, I.dvy_lo );
-        uh.x = __fsub_rn( uh.x, I.dvx_hi );
-        uh.y = __fsub_rn( uh.y, I.dvy_hi );
-        *vl  = ul;
-        *vh  = uh;
+// Column sums of the tile and its halo: cell_start is a running sum along a grid row, so with P[c] = sum over the staged
+// rows of cell_start[row][c0 + c] the staged particle count of the columns [a, b) is P[b] - P[a].  Ends with a barrier.
+// (k_gs_resolve runs one-warp CTAs, where the barrier costs no more than a __syncwarp.)
+__device__ __forceinline__ void gs_column_sums( uint32_t *colp, const uint32_t *__restrict__ cell_start, const GridDims &G, const int c0, const int c1,
+                                                const int cy0, const int nthreads ) {
+    for ( int c = threadIdx.x; c <= c1 - c0; c += nthreads ) {
+        uint32_t sum = 0;
+        for ( int j = 0; j < GS_R + 2; j++ ) {
+            const int gy = cy0 - 1 + j;
+            if ( gy >= 0 && gy < G.rows )
+                sum += cell_start[ (size_t)gy * G.cols + c0 + c ];
+        }
+        colp[ c ] = sum;
     }
+    __syncthreads();
 }
 
-// One sub-tile: centre columns [cx0, cx1) of the tile [tcx0, tcx1), centre rows [cy0, cy0 + GS_R) (clipped to the grid).
-__device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict__ rec_a, float4 *rec_b, float4 *__restrict__ pv_out,
-                                            const uint32_t *__restrict__ cell_start, const GridDims &G, const float dt, const int cx0, const int cx1,
-                                            const int tcx0, const int tcx1, const int cy0, const int tx, const int tyg, const int my_colour,
-                                            uint32_t &phase_parity, const bool later_strip, uint32_t *__restrict__ err_flags, const GsDump D ) {
-    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
-    const int ncol = c1 - c0, nb = ncol * GS_F;
-    uint32_t *cnt32 = reinterpret_cast<uint32_t *>( T.pool_val );       // bin counters / cursors while binning (pool unused then)
-    __syncthreads();                                                    // shared memory may still be in use by the previous strip
+// End of the strip that starts at column sx: a tile that would overflow shared memory is cut greedily from the left, each strip
+// taking as many columns as keep its staged particles (strip + one halo column either side) within GS_STRIP_LIMIT, at least one.
+__device__ __forceinline__ int gs_strip_end( const uint32_t *colp, const uint32_t total, const int sx, const int cx1, const int c0, const int c1 ) {
+    if ( total <= (uint32_t)GS_STRIP_LIMIT )
+        return cx1;
+    int ex = sx + 1;
+    while ( ex < cx1 && colp[ min( ex + 2, c1 ) - c0 ] - colp[ max( sx - 1, c0 ) - c0 ] <= (uint32_t)GS_STRIP_LIMIT )
+        ex++;
+    return ex;
+}
 
-    // ---- run table: staged row j = 0 .. GS_R+1 is grid row cy0 - 1 + j ----
+// Run table of a sub-tile: staged row j = 0 .. GS_R+1 is grid row cy0 - 1 + j, columns [c0, c1); centre = columns [cx0, cx1) of rows
+// 1 .. GS_R.  One thread then turns the lengths into running sums.  Needs a barrier before, between and after (the caller's).
+__device__ __forceinline__ void gs_run_lengths( uint32_t *run_g0, uint32_t *run_s0, uint32_t *cen_g0, uint32_t *cen_s0,
+                                                const uint32_t *__restrict__ cell_start, const GridDims &G, const int c0, const int c1, const int cx0,
+                                                const int cx1, const int cy0 ) {
     if ( threadIdx.x < GS_R + 2 ) {
         const int j = threadIdx.x, gy = cy0 - 1 + j;
         uint32_t  g0 = 0, g1 = 0, m0 = 0, m1 = 0;
@@ -152,47 +190,78 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
             if ( j >= 1 && j <= GS_R )
                 m0 = cell_start[ row + cx0 ], m1 = cell_start[ row + cx1 ];
         }
-        T.run_g0[ j ] = g0;
-        T.run_s0[ j ] = g1 - g0;   // length for now
+        run_g0[ j ] = g0;
+        run_s0[ j ] = g1 - g0;   // length for now
         if ( j >= 1 && j <= GS_R ) {
-            T.cen_g0[ j - 1 ] = m0;
-            T.cen_s0[ j - 1 ] = m1 - m0;   // length for now
+            cen_g0[ j - 1 ] = m0;
+            cen_s0[ j - 1 ] = m1 - m0;   // length for now
         }
     }
+}
+__device__ __forceinline__ void gs_run_sums( uint32_t *run_s0, uint32_t *cen_s0 ) {   // one thread
+    uint32_t run = 0;
+    for ( int j = 0; j < GS_R + 2; j++ ) {
+        const uint32_t len = run_s0[ j ];
+        run_s0[ j ]        = run;
+        run += len;
+    }
+    run_s0[ GS_R + 2 ] = run;
+    uint32_t cen = 0;
+    for ( int j = 0; j < GS_R; j++ ) {
+        const uint32_t len = cen_s0[ j ];
+        cen_s0[ j ]        = cen;
+        cen += len;
+    }
+    cen_s0[ GS_R ] = cen;
+}
+
+// ====================================================================================================================
+// k_gs_pairs: one sub-tile = centre columns [cx0, cx1) of the tile [tcx0, tcx1), centre rows [cy0, cy0 + GS_R) (clipped).
+// ====================================================================================================================
+__device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__restrict__ rec_a, const uint16_t *__restrict__ mcol, float4 *__restrict__ pv_out,
+                                                  const uint32_t *__restrict__ cell_start, const GridDims &G, const float dt, const int cx0, const int cx1,
+                                                  const int tcx0, const int tcx1, const int cy0, const int tx, const int tyg, const int my_colour,
+                                                  uint32_t &phase_parity, uint2 *__restrict__ desc_slot, const uint32_t last_flag, const GsPairs PR,
+                                                  uint32_t *__restrict__ err_flags, const GsDump D ) {
+    const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
+    const int ncol = c1 - c0, nb = ncol * GS_F;
+    uint32_t *cnt32 = reinterpret_cast<uint32_t *>( T.pool_val );       // bin counters / cursors while binning (pool unused then)
+    __syncthreads();                                                    // shared memory may still be in use by the previous strip
+
+    gs_run_lengths( T.run_g0, T.run_s0, T.cen_g0, T.cen_s0, cell_start, G, c0, c1, cx0, cx1, cy0 );
     for ( int f = threadIdx.x; f < GS_BINS; f += GS_THREADS )
         cnt32[ f ] = 0;
     __syncthreads();
     if ( threadIdx.x == 0 ) {
-        uint32_t run = 0;
+        // the 16-bit mass/column words of a row are copied from the 16-byte boundary at or below its first slot
+        uint32_t mc_at = 0;
         for ( int j = 0; j < GS_R + 2; j++ ) {
-            const uint32_t len = T.run_s0[ j ];
-            T.run_s0[ j ]      = run;
-            run += len;
+            const uint32_t lead = T.run_g0[ j ] & ( GS_MC_PAD - 1 );
+            T.mc_s0[ j ]        = mc_at + lead;
+            mc_at += ( lead + T.run_s0[ j ] + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 );   // run_s0 still holds the lengths
         }
-        T.run_s0[ GS_R + 2 ] = run;
-        uint32_t cen = 0;
-        for ( int j = 0; j < GS_R; j++ ) {
-            const uint32_t len = T.cen_s0[ j ];
-            T.cen_s0[ j ]      = cen;
-            cen += len;
-        }
-        T.cen_s0[ GS_R ] = cen;
-        T.rmax_bits      = 0u;
-        T.err            = 0u;
+        gs_run_sums( T.run_s0, T.cen_s0 );
+        T.rmax_bits = 0u;
+        T.err       = 0u;
 #if PPC_GS_TMA
+        const uint32_t run = T.run_s0[ GS_R + 2 ], cen = T.cen_s0[ GS_R ];
         if ( run != 0 && cen != 0 && run <= (uint32_t)GS_CAP ) {   // stage the runs: two bulk copies per row, one barrier phase
-            if ( later_strip )
-                __threadfence();   // velocities the previous strip wrote back are read by these copies
-            fence_proxy_async();
-            mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar ), run * 32u );
-            uint32_t at = 0;
+            fence_proxy_async();   // the previous strip read this shared memory with ordinary loads
+            uint32_t bytes = 0;
             for ( int j = 0; j < GS_R + 2; j++ ) {
-                const uint32_t len = ( j < GS_R + 1 ? T.run_s0[ j + 1 ] : run ) - at;
+                const uint32_t len = T.run_s0[ j + 1 ] - T.run_s0[ j ];
+                if ( len )
+                    bytes += len * 16u + ( ( ( ( T.run_g0[ j ] & ( GS_MC_PAD - 1 ) ) + len + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 ) ) * 2u );
+            }
+            mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar ), bytes );
+            for ( int j = 0; j < GS_R + 2; j++ ) {
+                const uint32_t len = T.run_s0[ j + 1 ] - T.run_s0[ j ];
                 if ( len ) {
-                    tma_load_1d( &T.a[ at ], rec_a + T.run_g0[ j ], len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
-                    tma_load_1d( &T.b[ at ], rec_b + T.run_g0[ j ], len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
+                    const uint32_t g0 = T.run_g0[ j ], lead = g0 & ( GS_MC_PAD - 1 );
+                    tma_load_1d( &T.a[ T.run_s0[ j ] ], rec_a + g0, len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
+                    tma_load_1d( &T.mc[ T.mc_s0[ j ] - lead ], mcol + ( g0 - lead ), ( ( lead + len + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 ) ) * 2u,
+                                 reinterpret_cast<uint64_t *>( &T.mbar ) );
                 }
-                at += len;
             }
         }
 #endif
@@ -200,14 +269,16 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
     __syncthreads();
     const uint32_t staged = T.run_s0[ GS_R + 2 ], centre = T.cen_s0[ GS_R ];
     if ( staged == 0 || centre == 0 )
-        return;
+        return;   // (the kernel has already marked this sub-tile as owning no pair)
     if ( staged > (uint32_t)GS_CAP ) {   // a one-column strip that still does not fit: this mode has no generic path
-        if ( threadIdx.x == 0 )
+        if ( threadIdx.x == 0 ) {
             atomicOr( err_flags, GS_ERR_CAP );
+            *desc_slot = make_uint2( 0u, last_flag );
+        }
         return;
     }
 
-    // ---- while the copies are in flight: staged cell table, inverse-mass table ----
+    // ---- while the copies are in flight: staged cell table, inverse-mass table, list heads ----
     for ( int e = threadIdx.x; e < ( GS_R + 2 ) * ( ncol + 1 ); e += GS_THREADS ) {
         const int j = e / ( ncol + 1 ), i = e - j * ( ncol + 1 ), gy = cy0 - 1 + j;
         uint32_t  v = T.run_s0[ j ];
@@ -217,6 +288,14 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
     }
     if ( threadIdx.x < 256 )
         T.inv_lut[ threadIdx.x ] = __fdiv_rn( 1.0f, (float)threadIdx.x );
+    for ( uint32_t t = threadIdx.x; t < staged; t += GS_THREADS ) {
+        T.head[ t ] = (uint16_t)GS_NONE;
+        T.lvl[ t ]  = 0;
+    }
+    if ( threadIdx.x == 0 )
+        T.phase_mask = 0u;
+    for ( int b = threadIdx.x; b < GS_BUCKETS; b += GS_THREADS )
+        T.bcount[ b ] = 0u;
 #if PPC_GS_TMA
     mbar_wait( reinterpret_cast<uint64_t *>( &T.mbar ), phase_parity );
     phase_parity ^= 1u;
@@ -227,10 +306,12 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
             j++;
         const uint32_t g = T.run_g0[ j ] + ( t - T.run_s0[ j ] );
         T.a[ t ] = rec_a[ g ];
-        T.b[ t ] = __ldcg( rec_b + g );
+        T.mc[ T.mc_s0[ j ] + ( t - T.run_s0[ j ] ) ] = mcol[ g ];
     }
     __syncthreads();
 #endif
+    // mass/column word of staged particle t in staged row j
+#define GS_MC( t, j ) T.mc[ T.mc_s0[ j ] + ( ( t ) - T.run_s0[ j ] ) ]
 
     // ---- histogram of (row, fine bin); largest radius ----
     const float x0 = __fmul_rn( (float)c0, G.cell_size ), inv_w = __fdiv_rn( (float)GS_F, G.cell_size );
@@ -312,8 +393,8 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
         const float4   me4  = T.a[ self ];
         const float    x = me4.x, y = me4.y, r = me4.z;
         const uint32_t gid   = __float_as_uint( me4.w );
-        const uint32_t mcol  = __float_as_uint( T.b[ self ].z );
-        const int      mycol = (int)( ( mcol >> 8 ) & 0xffu );
+        const uint32_t mcw   = GS_MC( self, j );
+        const int      mycol = (int)( mcw >> 8 );
         const int      gy    = cy0 - 1 + j;
         const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
         const int      b_lo  = gs_fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = gs_fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
@@ -329,7 +410,8 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
                 continue;
             if ( d == 2 && __fadd_rn( y, reach ) < bot )
                 continue;
-            const int      f_lo = ( j - 1 + d ) * GS_NB + b_lo, f_hi = ( j - 1 + d ) * GS_NB + b_hi;
+            const int      jr = j - 1 + d;   // staged row scanned
+            const int      f_lo = jr * GS_NB + b_lo, f_hi = jr * GS_NB + b_hi;
             const uint32_t rb = f_lo > 0 ? T.fend[ f_lo - 1 ] : 0u, re = T.fend[ f_hi ];
 #pragma unroll 2
             for ( uint32_t q = rb; q < re; q++ ) {
@@ -344,7 +426,7 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
                     continue;
                 const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
                 if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
-                    const int dc = (int)(int8_t)( ( ( __float_as_uint( T.b[ s ].z ) >> 8 ) & 0xffu ) - (uint32_t)mycol );
+                    const int dc = (int)(int8_t)( ( (uint32_t)GS_MC( s, jr ) >> 8 ) - (uint32_t)mycol );
                     if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
                         continue;
                     const uint32_t at = atomicAdd( &T.pool_n, 1u );
@@ -366,21 +448,23 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
             // The list is put into the order the reference's pair list touches this particle -- pairs (i, me), i < me, by
             // ascending i; then pairs (me, j) by scan cell (dy outer, dx inner), descending index inside a cell (:311-383) --
             // by selection, swapping entry values along the links; each entry is consumed as soon as it is in place.
-            auto sort_key = [ & ]( const uint32_t v ) -> unsigned long long {
-                const uint32_t g = __float_as_uint( T.a[ v & 0x7ffu ].w );
-                return g < gid ? (unsigned long long)g
-                               : ( 1ull << 48 ) | ( (unsigned long long)( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) << 32 ) | ( 0xffffffffu - g );
+            // Keys: a pair (i, me) sorts by i; a pair (me, j) by 2^31 | scan cell << 11 | (2047 - staged number of j), the
+            // staged numbers of one cell ascending with the index.
+            auto sort_key = [ & ]( const uint32_t v ) -> uint32_t {
+                const uint32_t s = v & 0x7ffu, g = __float_as_uint( T.a[ s ].w );
+                return g < gid ? g : 0x80000000u | ( ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) << 11 ) | ( 2047u - s );
             };
-            const float wme      = T.inv_lut[ mcol & 0xffu ];
+            const float wme      = T.inv_lut[ mcw & 0xffu ];
             const bool  row_last = ( j == GS_R ), row_first = ( j == 1 );
+            const int   my_gc    = c0 + ( ( mycol - c0 ) & 0xff );   // this particle's grid column
 #pragma unroll 1
             for ( uint32_t e = head; e != GS_NONE; e = T.pool_next[ e ] ) {
-                uint32_t           best = e, v = T.pool_val[ e ];
-                unsigned long long bkey = sort_key( v );
+                uint32_t best = e, v = T.pool_val[ e ];
+                uint32_t bkey = sort_key( v );
 #pragma unroll 1
                 for ( uint32_t f = T.pool_next[ e ]; f != GS_NONE; f = T.pool_next[ f ] ) {
-                    const uint32_t           vf = T.pool_val[ f ];
-                    const unsigned long long kf = sort_key( vf );
+                    const uint32_t vf = T.pool_val[ f ];
+                    const uint32_t kf = sort_key( vf );
                     if ( kf < bkey ) {
                         bkey = kf;
                         best = f;
@@ -394,7 +478,7 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
                 const float4   c     = T.a[ s ];
                 const uint32_t cg    = __float_as_uint( c.w );
                 const bool     me_lo = gid < cg;
-                const float    wq    = T.inv_lut[ __float_as_uint( T.b[ s ].z ) & 0xffu ];
+                const float    wq    = T.inv_lut[ GS_MC( s, j + d ) & 0xffu ];
                 {   // position push, operands selected by role (lo = the pair's i), :145-156
                     const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
                                                                   me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
@@ -404,7 +488,7 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
                     }
                 }
                 // who resolves this pair's impulse, and which of its two particles lists it (see the header)
-                const int  pc       = c0 + ( mycol - ( c0 & 0xff ) & 0xff ) + dc;          // partner's grid column
+                const int  pc       = my_gc + dc;   // partner's grid column
                 const bool p_row_in = !( ( row_first && d < 0 ) || ( row_last && d > 0 ) );
                 const bool p_col_in = pc >= cx0 && pc < cx1;
                 bool       anchored;
@@ -416,56 +500,82 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
                         anchored = pc >= cx1;   // a later strip of this tile
                     else
                         anchored = ( ( ( tx + dtx ) & 1 ) | ( ( ( tyg + dty ) & 1 ) << 1 ) ) > my_colour;
-                    if ( anchored )
-                        atomicOr( reinterpret_cast<uint32_t *>( &T.b[ s ].w ), GS_TOUCHED );
                 }
                 T.pool_val[ e ] = (uint16_t)( v | ( anchored ? 0x8000u : 0u ) );
-                if ( anchored && D.pairs ) {
-                    const uint32_t at = atomicAdd( D.count, 1u );
-                    if ( at < D.cap ) {
-                        D.pairs[ 2 * at ]     = me_lo ? gid : cg;
-                        D.pairs[ 2 * at + 1 ] = me_lo ? cg : gid;
-                    }
-                }
             }
-            T.b[ self ].w = __uint_as_float( ( __float_as_uint( T.b[ self ].w ) & ~0xffffu ) | head );
+            T.head[ self ] = (uint16_t)head;
         }
-        *reinterpret_cast<float2 *>( pv_out + gk ) = make_float2( X, Y );
+        *reinterpret_cast<float2 *>( pv_out + gk ) = make_float2( X, Y );   // the velocity half stays as the gather left it
     }
     __syncthreads();
     if ( T.err ) {
-        if ( threadIdx.x == 0 )
+        if ( threadIdx.x == 0 ) {
             atomicOr( err_flags, T.err );
+            *desc_slot = make_uint2( 0u, last_flag );
+        }
         return;
     }
 
-    // ---- Gauss-Seidel over the pairs of this sub-tile ----
-    // The ORDER is the nine phases of disjoint cell pairs described in the header; the EXECUTION is levelled: every pair gets
-    // level = 1 + max(level of the previous pair of either particle in that order), a cheap integer pass; pairs of one level
-    // share no particle and fire together, one thread per pair, all lanes busy.  Each particle still receives its impulses
-    // in exactly the order of the phases, so the result is the sequential one.
-    const int ncell  = ( GS_R + 2 ) * ncol;   // <= GS_THREADS (the host bounds the tile width): one thread per staged cell
-    const int row_g0 = G.row0 + cy0 - 1;      // whole-field row of staged row 0
-    uint16_t *seg    = T.fend;                // fend + perm are dead: entry numbers, first by (cell, direction), later by level
-    static_assert( sizeof( T.fend ) + sizeof( T.perm ) >= GS_POOL / 2 * sizeof( uint16_t ), "an anchored entry per pair" );
+    if ( T.pool_n == 0u ) {   // no contact at all in this sub-tile
+        if ( threadIdx.x == 0 )
+            *desc_slot = make_uint2( 0u, last_flag );
+        return;
+    }
+
+    // ---- the pairs this sub-tile owns, as records sorted by LEVEL ----
+    // The ORDER of the pairs is the nine phases of disjoint cell pairs described in the header.  Their EXECUTION (k_gs_resolve)
+    // is levelled: level(pair) = 1 + max(level of the previous pair of either particle in that order), a cheap integer pass
+    // done here; the pairs of one level share no particle and fire together, and every particle still receives its impulses in
+    // exactly the order of the phases.  A dense packing has ~70 (phase, position) steps per sub-tile but only ~15 levels.
+    // One thread per staged cell (the host bounds the tile width accordingly).  All pairs of a cell pair are listed by particles
+    // of ONE cell with ONE direction code (the base cell when it is inside the sub-tile, else the other one): ascending particle,
+    // list order -- the order inside the cell pair.
+    const int  ncell  = ( GS_R + 2 ) * ncol;
+    const int  row_g0 = G.row0 + cy0 - 1;      // whole-field row of staged row 0
     const int  xj = (int)threadIdx.x / ncol, xc = (int)threadIdx.x - xj * ncol;                       // this thread's cell
     const bool x_in = (int)threadIdx.x < ncell && xj >= 1 && xj <= GS_R && c0 + xc >= cx0 && c0 + xc < cx1;   // anchors are centre particles
     const uint32_t x_pb = x_in ? T.cstart[ xj * ( GS_MAXC + 1 ) + xc ] : 0u, x_pe = x_in ? T.cstart[ xj * ( GS_MAXC + 1 ) + xc + 1 ] : 0u;
-    // (a) anchored entries of this cell per direction code d * 3 + dc (nine 7-bit counters in one word)
+    uint16_t *seg = T.fend;   // fend + perm are dead: entry numbers grouped by (cell, direction code)
+    constexpr uint32_t SEG_CAP = ( sizeof( T.fend ) + sizeof( T.perm ) ) / sizeof( uint16_t );
+    // phase of the pairs a cell lists under direction code d * 3 + dc: class by the direction as seen from the base cell, parity of
+    // the base cell's whole-field column (east) or row (the southward classes)
+    auto phase_of = [ & ]( const uint32_t code ) -> uint32_t {
+        const int  dj = (int)( code / 3u ) - 1, dcl = (int)( code % 3u ) - 1;
+        const bool fwd = dj > 0 || ( dj == 0 && dcl >= 0 );                    // this cell is the base
+        const int  bj = fwd ? xj : xj + dj, bc = fwd ? xc : xc + dcl;          // base cell
+        const int  uj = fwd ? dj : -dj, uc = fwd ? dcl : -dcl;                 // direction from the base
+        const int  cls = uj == 0 ? ( uc == 0 ? 0 : 1 ) : ( uc == 0 ? 2 : ( uc > 0 ? 3 : 4 ) );
+        const int  par = cls == 1 ? ( ( c0 + bc ) & 1 ) : ( ( row_g0 + bj ) & 1 );
+        return cls == 0 ? 0u : (uint32_t)( 2 * cls - 1 + par );
+    };
+    // (a) this cell's pairs per direction code: nine 7-bit counters in one word
     unsigned long long cnt = 0ull;
     uint32_t           mine = 0;
 #pragma unroll 1
     for ( uint32_t a = x_pb; a < x_pe; a++ )
 #pragma unroll 1
-        for ( uint32_t e = __float_as_uint( T.b[ a ].w ) & 0xffffu; e != GS_NONE; e = T.pool_next[ e ] ) {
+        for ( uint32_t e = T.head[ a ]; e != GS_NONE; e = T.pool_next[ e ] ) {
             const uint32_t v = T.pool_val[ e ];
             if ( v & 0x8000u ) {
                 cnt += 1ull << ( 7u * ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) );
                 mine++;
             }
         }
-    if ( threadIdx.x < 256 )
-        T.lcount[ threadIdx.x ] = 0u;
+    unsigned long long pre = 0ull;   // running sums of the nine counters, same packing (all below 128 when mine is)
+    uint32_t           phases = 0;   // phases in which this cell has pairs
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for ( uint32_t c = 0; c < 9; c++ ) {
+            pre |= (unsigned long long)( run & 127u ) << ( 7u * c );
+            const uint32_t k = (uint32_t)( cnt >> ( 7u * c ) ) & 127u;
+            run += k;
+            if ( k && x_in )
+                phases |= 1u << phase_of( c );
+        }
+    }
+    if ( phases )
+        atomicOr( &T.phase_mask, phases );
     uint32_t seg_base;   // exclusive scan of `mine` over the CTA
     {
         uint32_t inc = mine;
@@ -487,15 +597,17 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
         }
         const unsigned wid = threadIdx.x >> 5;
         seg_base           = ( wid ? __shfl_sync( 0xffffffffu, ws, wid - 1 ) : 0u ) + inc - mine;
-        if ( __shfl_sync( 0xffffffffu, ws, GS_THREADS / 32 - 1 ) > (uint32_t)( ( sizeof( T.fend ) + sizeof( T.perm ) ) / sizeof( uint16_t ) ) )
+        if ( __shfl_sync( 0xffffffffu, ws, 31 ) > SEG_CAP )
             T.err = GS_ERR_POOL;   // more pairs than the entry list takes (same value in every thread)
     }
     if ( mine > 127u )   // a 7-bit counter may have wrapped (dozens of particles on one spot): not a field for this mode
-        T.err = GS_ERR_POOL;
+        T.err = GS_ERR_DEPTH;
     __syncthreads();
     if ( T.err ) {
-        if ( threadIdx.x == 0 )
+        if ( threadIdx.x == 0 ) {
             atomicOr( err_flags, T.err );
+            *desc_slot = make_uint2( 0u, last_flag );
+        }
         return;
     }
     // (b) entry numbers of this cell, grouped by direction code; the entry remembers its anchor where its link was
@@ -504,18 +616,13 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
 #pragma unroll 1
         for ( uint32_t a = x_pb; a < x_pe; a++ )
 #pragma unroll 1
-            for ( uint32_t e = __float_as_uint( T.b[ a ].w ) & 0xffffu; e != GS_NONE; ) {
+            for ( uint32_t e = T.head[ a ]; e != GS_NONE; ) {
                 const uint32_t nxt = T.pool_next[ e ], v = T.pool_val[ e ];
                 if ( v & 0x8000u ) {
                     const uint32_t code = ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u );
-                    uint32_t       pre  = 0;
-#pragma unroll
-                    for ( uint32_t k = 0; k < 8; k++ )
-                        pre += k < code ? (uint32_t)( cnt >> ( 7u * k ) ) & 127u : 0u;
-                    seg[ seg_base + pre + ( (uint32_t)( cur >> ( 7u * code ) ) & 127u ) ] = (uint16_t)e;
+                    seg[ seg_base + ( (uint32_t)( pre >> ( 7u * code ) ) & 127u ) + ( (uint32_t)( cur >> ( 7u * code ) ) & 127u ) ] = (uint16_t)e;
                     cur += 1ull << ( 7u * code );
-                    T.pool_next[ e ] = (uint16_t)a;   // bits [10:0] anchor; [15:11] and pool_val [14:11] will hold the level
-                    T.pool_val[ e ]  = (uint16_t)( v & 0x87ffu );
+                    T.pool_next[ e ] = (uint16_t)a;
                 }
                 e = nxt;
             }
@@ -523,150 +630,293 @@ __device__ __forceinline__ void gs_subtile( GsSmem &T, const float4 *__restrict_
     __syncthreads();
     // (c) levels, phase by phase: in a phase a cell's thread walks the pairs of ONE direction code (towards the phase's other
     //     cell when this cell is the base, i.e. has the phase's parity; backwards to a halo base cell otherwise)
+    const uint32_t phase_mask = T.phase_mask;
 #pragma unroll 1
     for ( int phase = 0; phase < 9; phase++ ) {
-        const int cls = phase == 0 ? 0 : ( phase + 1 ) >> 1;   // 0 same cell, 1 east, 2 south, 3 south-east, 4 south-west
-        const int par = phase == 0 ? 0 : ( phase + 1 ) & 1;
-        if ( x_in && mine ) {
+        if ( !( ( phase_mask >> phase ) & 1u ) )
+            continue;   // no pair of this sub-tile in this phase
+        if ( ( phases >> phase ) & 1u ) {
+            const int      cls = phase == 0 ? 0 : ( phase + 1 ) >> 1;   // 0 same cell, 1 east, 2 south, 3 south-east, 4 south-west
+            const int      par = phase == 0 ? 0 : ( phase + 1 ) & 1;
             const bool     base = cls == 0 || ( ( cls == 1 ? c0 + xc : row_g0 + xj ) & 1 ) == par;
             const int      dj = cls >= 2 ? 1 : 0, dcl = cls == 1 || cls == 3 ? 1 : ( cls == 4 ? -1 : 0 );
             const uint32_t code = (uint32_t)( ( ( base ? dj : -dj ) + 1 ) * 3 + ( base ? dcl : -dcl ) + 1 );
-            uint32_t       pre  = 0;
-#pragma unroll
-            for ( uint32_t k = 0; k < 8; k++ )
-                pre += k < code ? (uint32_t)( cnt >> ( 7u * k ) ) & 127u : 0u;
-            const uint32_t kb = seg_base + pre, ke = kb + ( (uint32_t)( cnt >> ( 7u * code ) ) & 127u );
+            const uint32_t kb = seg_base + ( (uint32_t)( pre >> ( 7u * code ) ) & 127u ), ke = kb + ( (uint32_t)( cnt >> ( 7u * code ) ) & 127u );
 #pragma unroll 1
             for ( uint32_t k = kb; k < ke; k++ ) {
                 const uint32_t e = seg[ k ];
-                const uint32_t a = T.pool_next[ e ] & 0x7ffu, q = T.pool_val[ e ] & 0x7ffu;
-                uint32_t      *wa = reinterpret_cast<uint32_t *>( &T.b[ a ].w ), *wq = reinterpret_cast<uint32_t *>( &T.b[ q ].w );
-                const uint32_t ua = *wa, uq = *wq;
-                uint32_t       lv = max( ( ua >> 17 ) & 0x3ffu, ( uq >> 17 ) & 0x3ffu ) + 1u;
-                if ( lv > 255u ) {
+                const uint32_t a = T.pool_next[ e ], q = T.pool_val[ e ] & 0x7ffu;
+                uint32_t       lv = max( (uint32_t)T.lvl[ a ], (uint32_t)T.lvl[ q ] ) + 1u;
+                if ( lv >= (uint32_t)GS_BUCKETS ) {
                     T.err = GS_ERR_DEPTH;
-                    lv    = 255u;
+                    lv    = GS_BUCKETS - 1;
                 }
-                *wa = ( ua & 0x1ffffu ) | ( lv << 17 );
-                *wq = ( uq & 0x1ffffu ) | ( lv << 17 );
-                T.pool_val[ e ]  = (uint16_t)( 0x8000u | q | ( ( lv & 15u ) << 11 ) );
-                T.pool_next[ e ] = (uint16_t)( a | ( ( lv >> 4 ) << 11 ) );
-                atomicAdd( &T.lcount[ lv ], 1u );
+                T.lvl[ a ]      = (uint8_t)lv;
+                T.lvl[ q ]      = (uint8_t)lv;
+                T.pool_aux[ e ] = (uint16_t)lv;
+                atomicAdd( &T.bcount[ lv ], 1u );
             }
         }
         __syncthreads();
     }
     if ( T.err ) {
-        if ( threadIdx.x == 0 )
+        if ( threadIdx.x == 0 ) {
             atomicOr( err_flags, T.err );
+            *desc_slot = make_uint2( 0u, last_flag );
+        }
         return;
     }
-    // (d) entries by level: scan of the level counts, scatter (the order inside a level is immaterial)
-    const uint32_t n_entries = min( T.pool_n, (uint32_t)GS_POOL );
-    if ( threadIdx.x < 32 ) {
-        uint32_t loc[ 8 ], sum = 0;
+    // exclusive scan of the level counts and of the "level in use" flags over the CTA; the chunk; the table of level ends
+    {
+        constexpr int PER = ( GS_BUCKETS + GS_THREADS - 1 ) / GS_THREADS;
+        const int     f0  = threadIdx.x * PER;
+        uint32_t      loc[ PER ], sum = 0, used = 0;
 #pragma unroll
-        for ( int i = 0; i < 8; i++ ) {
-            loc[ i ] = T.lcount[ threadIdx.x * 8 + i ];
+        for ( int i = 0; i < PER; i++ ) {
+            loc[ i ] = f0 + i < GS_BUCKETS ? T.bcount[ f0 + i ] : 0u;
             sum += loc[ i ];
+            used += loc[ i ] ? 1u : 0u;
         }
-        uint32_t inc = sum;
+        uint32_t inc = sum, uinc = used;
 #pragma unroll
         for ( int d = 1; d < 32; d <<= 1 ) {
-            const uint32_t o = __shfl_up_sync( 0xffffffffu, inc, d );
-            if ( threadIdx.x >= (unsigned)d )
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, inc, d ), u = __shfl_up_sync( 0xffffffffu, uinc, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d ) {
                 inc += o;
-        }
-        uint32_t run = inc - sum;
-#pragma unroll
-        for ( int i = 0; i < 8; i++ ) {
-            T.lcount[ threadIdx.x * 8 + i ] = run;   // begin of the level; the scatter advances it to the end
-            run += loc[ i ];
-        }
-        if ( threadIdx.x == 31 )
-            T.wsum[ 0 ] = run;   // pairs of this sub-tile
-    }
-    __syncthreads();
-    const uint32_t n_pairs = T.wsum[ 0 ];
-    for ( uint32_t e = threadIdx.x; e < n_entries; e += GS_THREADS ) {
-        const uint32_t v = T.pool_val[ e ];
-        if ( v & 0x8000u )
-            seg[ atomicAdd( &T.lcount[ ( ( v >> 11 ) & 15u ) | ( ( (uint32_t)T.pool_next[ e ] >> 11 ) << 4 ) ], 1u ) ] = (uint16_t)e;
-    }
-    __syncthreads();
-    // (e) fire, level by level
-    {
-        uint32_t kb = 0;
-#pragma unroll 1
-        for ( uint32_t lv = 1; kb < n_pairs; lv++ ) {
-            const uint32_t ke = T.lcount[ lv ];
-            for ( uint32_t k = kb + threadIdx.x; k < ke; k += GS_THREADS ) {
-                const uint32_t e = seg[ k ];
-                gs_fire( T, T.pool_next[ e ] & 0x7ffu, T.pool_val[ e ] & 0x7ffu, dt );
+                uinc += u;
             }
-            kb = ke;
-            __syncthreads();
+        }
+        if ( ( threadIdx.x & 31u ) == 31u ) {
+            T.wsum[ threadIdx.x >> 5 ]  = inc;
+            T.wsum2[ threadIdx.x >> 5 ] = uinc;
+        }
+        __syncthreads();
+        const bool in = ( threadIdx.x & 31u ) < (unsigned)( GS_THREADS / 32 );
+        uint32_t   ws = in ? T.wsum[ threadIdx.x & 31u ] : 0u, us = in ? T.wsum2[ threadIdx.x & 31u ] : 0u;   // every warp scans the warp sums
+#pragma unroll
+        for ( int d = 1; d < 32; d <<= 1 ) {
+            const uint32_t o = __shfl_up_sync( 0xffffffffu, ws, d ), u = __shfl_up_sync( 0xffffffffu, us, d );
+            if ( ( threadIdx.x & 31u ) >= (unsigned)d ) {
+                ws += o;
+                us += u;
+            }
+        }
+        const unsigned wid     = threadIdx.x >> 5;
+        const uint32_t n_pairs = __shfl_sync( 0xffffffffu, ws, 31 ), n_used = __shfl_sync( 0xffffffffu, us, 31 );
+        uint32_t       run     = ( wid ? __shfl_sync( 0xffffffffu, ws, wid - 1 ) : 0u ) + inc - sum;
+        uint32_t       urun    = ( wid ? __shfl_sync( 0xffffffffu, us, wid - 1 ) : 0u ) + uinc - used;
+        if ( threadIdx.x == 0 ) {
+            const uint32_t units = GS_HDR_UNITS + ( n_used * 2u + 15u ) / 16u + n_pairs;
+            uint32_t       base  = 0xffffffffu;
+            if ( n_pairs ) {
+                base = atomicAdd( PR.cursor, units );
+                if ( base + units > PR.cap ) {   // pair buffer full
+                    atomicOr( err_flags, GS_ERR_CHUNK );
+                    base = 0xffffffffu;
+                }
+            }
+            T.chunk_base = base;
+            T.n_buckets  = n_used;
+            *desc_slot   = base != 0xffffffffu ? make_uint2( base + 1u, n_pairs | ( n_used << 16 ) | last_flag ) : make_uint2( 0u, last_flag );
+        }
+        __syncthreads();
+        uint16_t *table = T.chunk_base != 0xffffffffu ? reinterpret_cast<uint16_t *>( PR.chunks + T.chunk_base + GS_HDR_UNITS ) : nullptr;
+        if ( table && threadIdx.x < 2 * ( GS_R + 2 ) + 1 )   // the run table
+            reinterpret_cast<uint32_t *>( PR.chunks + T.chunk_base )[ threadIdx.x ] =
+                threadIdx.x < GS_R + 2 ? T.run_g0[ threadIdx.x ] : T.run_s0[ threadIdx.x - ( GS_R + 2 ) ];
+#pragma unroll
+        for ( int i = 0; i < PER; i++ )
+            if ( f0 + i < GS_BUCKETS ) {
+                T.bcount[ f0 + i ] = run;   // begin of the bucket; the scatter below advances it to the end
+                run += loc[ i ];
+                if ( loc[ i ] && table )
+                    table[ urun++ ] = (uint16_t)run;   // end of the bucket, among the buckets in use
+            }
+    }
+    __syncthreads();
+    if ( T.chunk_base == 0xffffffffu )
+        return;   // no pair, or no room
+    {
+        uint4         *rec = PR.chunks + T.chunk_base + GS_HDR_UNITS + ( T.n_buckets * 2u + 15u ) / 16u;
+        const uint32_t n_entries = min( T.pool_n, (uint32_t)GS_POOL );
+        for ( uint32_t e = threadIdx.x; e < n_entries; e += GS_THREADS ) {
+            const uint32_t v = T.pool_val[ e ];
+            if ( !( v & 0x8000u ) )
+                continue;
+            const uint32_t a = T.pool_next[ e ], q = v & 0x7ffu;
+            const float4   A = T.a[ a ], Q = T.a[ q ];
+            const bool     a_lo = __float_as_uint( A.w ) < __float_as_uint( Q.w );   // lo = the lower API index = the reference's i
+            const float4   L = a_lo ? A : Q, H = a_lo ? Q : A;
+            const ContactGeom C = contact_geom( L.x, L.y, L.z, H.x, H.y, H.z, dt );
+            const uint32_t at = atomicAdd( &T.bcount[ T.pool_aux[ e ] ], 1u );   // the order inside a bucket is immaterial
+            rec[ at ] = make_uint4( ( a_lo ? a : q ) | ( ( a_lo ? q : a ) << 11 ), __float_as_uint( C.nx ), __float_as_uint( C.ny ), __float_as_uint( C.vbias ) );
+            if ( D.pairs ) {
+                const uint32_t k = atomicAdd( D.count, 1u );
+                if ( k < D.cap ) {
+                    D.pairs[ 2 * k ]     = __float_as_uint( L.w );
+                    D.pairs[ 2 * k + 1 ] = __float_as_uint( H.w );
+                }
+            }
         }
     }
-
-    // ---- final velocities of this sub-tile's particles; velocities of halo particles it changed go back in place ----
-    for ( uint32_t t = threadIdx.x; t < centre; t += GS_THREADS ) {
-        int j = 1;
-        while ( j < GS_R && t >= T.cen_s0[ j ] )
-            j++;
-        const uint32_t gk   = T.cen_g0[ j - 1 ] + ( t - T.cen_s0[ j - 1 ] );
-        const uint32_t self = T.run_s0[ j ] + ( gk - T.run_g0[ j ] );
-        *( reinterpret_cast<float2 *>( pv_out + gk ) + 1 ) = *reinterpret_cast<const float2 *>( &T.b[ self ] );
-    }
-    for ( uint32_t t = threadIdx.x; t < staged; t += GS_THREADS )
-        if ( __float_as_uint( T.b[ t ].w ) & GS_TOUCHED ) {
-            int j = 0;
-            while ( j < GS_R + 1 && t >= T.run_s0[ j + 1 ] )
-                j++;
-            *reinterpret_cast<float2 *>( rec_b + ( T.run_g0[ j ] + ( t - T.run_s0[ j ] ) ) ) = *reinterpret_cast<const float2 *>( &T.b[ t ] );
-        }
+#undef GS_MC
 }
 
-__global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_collide_gs( const float4 *__restrict__ rec_a, float4 *rec_b, float4 *__restrict__ pv_out,
-                                                               const uint32_t *__restrict__ cell_start, const GridDims G, const float dt,
-                                                               const GsLaunch L, uint32_t *__restrict__ err_flags, const GsDump D ) {
+__global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_gs_pairs( const float4 *__restrict__ rec_a, const uint16_t *__restrict__ mcol,
+                                                             float4 *__restrict__ pv_out, const uint32_t *__restrict__ cell_start, const GridDims G,
+                                                             const float dt, const GsLaunch L, const GsPairs PR, uint32_t *__restrict__ err_flags,
+                                                             const GsDump D ) {
     extern __shared__ __align__( 16 ) unsigned char smem_raw[];
     GsSmem &T = *reinterpret_cast<GsSmem *>( smem_raw );
-    const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
-    const int tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;   // ty: tile row inside this grid
+    const int tx = (int)( blockIdx.x % (unsigned)L.tiles_x ), ty = (int)( blockIdx.x / (unsigned)L.tiles_x );   // ty: tile row inside this grid
     const int tyg = L.ty_first + ty;                                       // tile row of the whole field
     const int cx0 = tx * L.wc, cx1 = min( cx0 + L.wc, G.cols );
     const int cy0 = tyg * GS_R - G.row0;                                   // may be negative for a slab window's first tile row
     if ( threadIdx.x == 0 )
         mbar_init( reinterpret_cast<uint64_t *>( &T.mbar ), 1u );
-    // Column sums of the tile and its halo: cell_start is a running sum along a grid row, so P[c] = sum over the staged rows of
-    // cell_start[row][c0 + c] makes the staged particle count of the columns [a, b) equal to P[b] - P[a].
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );
-    for ( int c = threadIdx.x; c <= c1 - c0; c += GS_THREADS ) {
-        uint32_t sum = 0;
-        for ( int j = 0; j < GS_R + 2; j++ ) {
-            const int gy = cy0 - 1 + j;
-            if ( gy >= 0 && gy < G.rows )
-                sum += cell_start[ (size_t)gy * G.cols + c0 + c ];
-        }
-        T.colp[ c ] = sum;
-    }
-    __syncthreads();
+    gs_column_sums( T.colp, cell_start, G, c0, c1, cy0, GS_THREADS );
     const uint32_t total = T.colp[ c1 - c0 ] - T.colp[ 0 ];
-    if ( total == 0 )
+    uint2         *desc  = PR.desc + (size_t)blockIdx.x * GS_MAXSTRIPS;
+    if ( total == 0 ) {
+        if ( threadIdx.x == 0 )
+            desc[ 0 ] = make_uint2( 0u, GS_LAST_STRIP );
         return;
-    // A tile that would overflow shared memory is cut into column strips, greedily from the left: each strip takes as many
-    // columns as keep its staged particles (strip + one halo column either side) within GS_STRIP_LIMIT, and at least one.
+    }
     uint32_t parity = 0;
-    for ( int sx = cx0; sx < cx1; ) {
-        int ex = cx1;
-        if ( total > (uint32_t)GS_STRIP_LIMIT ) {
-            ex = sx + 1;
-            while ( ex < cx1 && T.colp[ min( ex + 2, c1 ) - c0 ] - T.colp[ max( sx - 1, c0 ) - c0 ] <= (uint32_t)GS_STRIP_LIMIT )
-                ex++;
-        }
-        gs_subtile( T, rec_a, rec_b, pv_out, cell_start, G, dt, sx, ex, cx0, cx1, cy0, tx, tyg, L.colour, parity, sx != cx0, err_flags, D );
+    int      strip  = 0;
+    for ( int sx = cx0; sx < cx1; strip++ ) {
+        const int      ex   = gs_strip_end( T.colp, total, sx, cx1, c0, c1 );
+        const uint32_t last = ex >= cx1 ? GS_LAST_STRIP : 0u;
+        if ( threadIdx.x == 0 )
+            desc[ strip ] = make_uint2( 0u, last );   // until the sub-tile turns out to own pairs (same thread, program order)
+        gs_pairs_subtile( T, rec_a, mcol, pv_out, cell_start, G, dt, sx, ex, cx0, cx1, cy0, tx, tyg, ( tx & 1 ) | ( ( tyg & 1 ) << 1 ), parity,
+                          desc + strip, last, PR, err_flags, D );
         sx = ex;
+    }
+}
+
+// ====================================================================================================================
+// k_gs_resolve: the velocity impulses of the pairs a sub-tile owns, bucket by bucket (one launch per tile colour).
+// ====================================================================================================================
+// A sub-tile's records are one contiguous chunk, read front to back: the TMA streams it through shared memory in slices of
+// GSB_SLICE records, two slices in flight, so a record is never waited for at HBM latency.  CTAs are small (the pairs of a bucket
+// are a few dozen) and hold little shared memory, so many tiles are resident per SM and their dependent steps interleave.
+struct GsbSmem {
+    uint4    recs[ 2 ][ GSB_SLICE ];         // two slices of the record chunk
+    float2   v[ GS_CAP ];                    // current velocity of every staged particle
+    uint8_t  m[ GS_CAP ];                    // mass byte (:141-142)
+    uint8_t  dirty[ GS_CAP ];                // an impulse changed this particle's velocity
+    uint16_t bend[ GS_BUCKETS ];             // end of every bucket in use
+    float    inv_lut[ 256 ];                 // 1 / (float)k, the inverse masses of :146-147
+    uint32_t run[ 2 * ( GS_R + 2 ) + 1 + 3 ];   // run table of the sub-tile, as k_gs_pairs left it: run_g0[GS_R + 2], run_s0[GS_R + 3]
+    uint2    desc;
+    unsigned long long mbar[ 2 ];
+};
+
+__global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *__restrict__ mcol, float4 *pv, const GsLaunch L, const GsPairs PR ) {
+    __shared__ __align__( 16 ) GsbSmem T;
+    const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
+    const int tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;   // ty: tile row inside this grid
+    const uint2 *desc = PR.desc + ( (size_t)ty * L.tiles_x + tx ) * GS_MAXSTRIPS;
+    uint32_t     parity[ 2 ] = { 0u, 0u };
+    bool         ready = false;
+    for ( int strip = 0;; strip++ ) {
+        __syncthreads();   // shared memory may still be in use by the previous strip
+        if ( threadIdx.x == 0 )
+            T.desc = desc[ strip ];
+        __syncthreads();
+        const uint2 d = T.desc;
+        if ( d.x != 0 ) {
+            if ( !ready ) {   // first sub-tile with pairs (most tiles of a dilute field never get here)
+                if ( threadIdx.x == 0 ) {
+                    mbar_init( reinterpret_cast<uint64_t *>( &T.mbar[ 0 ] ), 1u );
+                    mbar_init( reinterpret_cast<uint64_t *>( &T.mbar[ 1 ] ), 1u );
+                }
+                for ( int i = threadIdx.x; i < 256; i += GSB_THREADS )
+                    T.inv_lut[ i ] = __fdiv_rn( 1.0f, (float)i );
+                ready = true;
+            }
+            const uint32_t n_pairs = d.y & 0xffffu, n_used = ( d.y >> 16 ) & 0x7fffu;
+            const uint4   *chunk   = PR.chunks + ( d.x - 1u );
+            const uint4   *rec     = chunk + GS_HDR_UNITS + ( n_used * 2u + 15u ) / 16u;
+            const uint32_t n_slices = ( n_pairs + GSB_SLICE - 1 ) / GSB_SLICE;
+            if ( threadIdx.x < 2 * ( GS_R + 2 ) + 1 )
+                T.run[ threadIdx.x ] = reinterpret_cast<const uint32_t *>( chunk )[ threadIdx.x ];
+            for ( uint32_t b = threadIdx.x; b < n_used; b += GSB_THREADS )
+                T.bend[ b ] = reinterpret_cast<const uint16_t *>( chunk + GS_HDR_UNITS )[ b ];
+            __syncthreads();   // run table; the barriers initialised
+            auto load_slice = [ & ]( const uint32_t i ) {   // one thread
+                const uint32_t count = min( (uint32_t)GSB_SLICE, n_pairs - i * GSB_SLICE );
+                fence_proxy_async();
+                mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar[ i & 1u ] ), count * 16u );
+                tma_load_1d( T.recs[ i & 1u ], rec + (size_t)i * GSB_SLICE, count * 16u, reinterpret_cast<uint64_t *>( &T.mbar[ i & 1u ] ) );
+            };
+            if ( threadIdx.x == 0 ) {
+                load_slice( 0u );
+                if ( n_slices > 1 )
+                    load_slice( 1u );
+            }
+            const uint32_t *run_g0 = T.run, *run_s0 = T.run + ( GS_R + 2 );
+            // current velocities (earlier sub-tiles may have changed them) and mass bytes of the staged particles, row by row so
+            // that the loads of a row are independent of each other and many are in flight
+            for ( int j = 0; j < GS_R + 2; j++ ) {
+                const uint32_t s0 = run_s0[ j ], len = run_s0[ j + 1 ] - s0, g0 = run_g0[ j ];
+#pragma unroll 8
+                for ( uint32_t t = threadIdx.x; t < len; t += GSB_THREADS ) {
+                    T.v[ s0 + t ]     = __ldcg( reinterpret_cast<const float2 *>( pv + g0 + t ) + 1 );
+                    T.m[ s0 + t ]     = (uint8_t)( mcol[ g0 + t ] & 0xffu );
+                    T.dirty[ s0 + t ] = 0;
+                }
+            }
+            __syncthreads();
+            // Fire, bucket by bucket (the pairs of a bucket share no particle), in segments that end where a bucket or a slice ends.
+            uint32_t k = 0, b = 0;
+#pragma unroll 1
+            while ( k < n_pairs ) {
+                const uint32_t slice = k / GSB_SLICE, s_end = min( ( slice + 1u ) * GSB_SLICE, n_pairs );
+                const uint32_t b_end = T.bend[ b ], seg_end = min( b_end, s_end );
+                if ( k == slice * GSB_SLICE ) {   // first record of a slice: it must have landed
+                    mbar_wait( reinterpret_cast<uint64_t *>( &T.mbar[ slice & 1u ] ), parity[ slice & 1u ] );
+                    parity[ slice & 1u ] ^= 1u;
+                }
+                const uint4 *buf = T.recs[ slice & 1u ] - (size_t)slice * GSB_SLICE;
+#pragma unroll 1
+                for ( uint32_t q = k + threadIdx.x; q < seg_end; q += GSB_THREADS ) {
+                    const uint4    r  = buf[ q ];
+                    const uint32_t lo = r.x & 0x7ffu, hi = ( r.x >> 11 ) & 0x7ffu;
+                    ContactGeom    C;
+                    C.nx = __uint_as_float( r.y ), C.ny = __uint_as_float( r.z ), C.vbias = __uint_as_float( r.w ), C.raw = 0.0f, C.corrected = 0.0f;
+                    float2             ul = T.v[ lo ], uh = T.v[ hi ];
+                    const ImpulseTerms I  = impulse_terms( C, T.inv_lut[ T.m[ lo ] ], T.inv_lut[ T.m[ hi ] ], ul.x, ul.y, uh.x, uh.y );   // :158-190
+                    if ( I.impulse ) {
+                        ul.x = __fadd_rn( ul.x, I.dvx_lo );
+                        ul.y = __fadd_rn( ul.y, I.dvy_lo );
+                        uh.x = __fsub_rn( uh.x, I.dvx_hi );
+                        uh.y = __fsub_rn( uh.y, I.dvy_hi );
+                        T.v[ lo ]     = ul;
+                        T.v[ hi ]     = uh;
+                        T.dirty[ lo ] = 1;
+                        T.dirty[ hi ] = 1;
+                    }
+                }
+                __syncthreads();
+                if ( seg_end == s_end && slice + 2u < n_slices && threadIdx.x == 0 )
+                    load_slice( slice + 2u );   // the slice just finished frees its buffer
+                k = seg_end;
+                if ( k == b_end )
+                    b++;
+            }
+            // what changed goes back: this sub-tile's own particles are final, halo particles are picked up by their own sub-tile later
+            for ( int j = 0; j < GS_R + 2; j++ ) {
+                const uint32_t s0 = run_s0[ j ], len = run_s0[ j + 1 ] - s0, g0 = run_g0[ j ];
+                for ( uint32_t t = threadIdx.x; t < len; t += GSB_THREADS )
+                    if ( T.dirty[ s0 + t ] )
+                        *( reinterpret_cast<float2 *>( pv + g0 + t ) + 1 ) = T.v[ s0 + t ];
+            }
+        }
+        if ( d.y & GS_LAST_STRIP )
+            break;
     }
 }
 
