@@ -187,6 +187,14 @@ int ppc_grid_dims( uint16_t window_width, uint16_t window_height, float max_radi
  * in the whole field (it fixes the pair order on every rank alike); max_radius is the maximum over the WHOLE field. */
 int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids, uint16_t window_width, uint16_t window_height, float max_radius,
                    int own_row_begin, int own_row_end, int halo_rows );
+/* "resolve"=3 on slabs: every rank sets "gs_wc" to ppc_gs_auto_tile_width( particles, cells of the WHOLE field ) -- the tile order
+ * is part of the result -- and needs at least ppc_slab_gs_halo() ghost rows (9 to 16 on the side where an odd tile row borders, 1
+ * to 8 on the other; ppc_slab_finish returns -4 otherwise).  Owned positions and velocities are then bit-identical to the
+ * single-GPU run by construction; there is no inexactness mark in this mode.
+ * "slab_nb_lo_rows" / "slab_nb_hi_rows" (ppc_set_option, before ppc_slab_init): cell rows the neighbouring ranks own; ppc_slab_init
+ * returns -5 for a halo deeper than that (ghost rows only come from the direct neighbours). */
+int ppc_slab_gs_halo( int own_row_begin, int own_row_end, int rows_total );
+int ppc_gs_auto_tile_width( double particles, double cells );
 int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t send_counts[ 2 ] /* to lower / upper rows */ );
 /* with_header: messages of a fixed, agreed size -- record 0 of each buffer holds the number of records that follow, so the
  * receiver needs no count in advance (ppc_slab_finish then takes the buffers' CAPACITIES and reports the counts received) */

@@ -50,6 +50,7 @@ struct Store {
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
     int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi, 3 tile Gauss-Seidel
+    int      opt_nb_lo_rows = 0, opt_nb_hi_rows = 0;   // slab mode: cell rows the lower / upper neighbour owns (0: not told)
     int      opt_gs_wc = 0, opt_gs_dump = 0;   // tile width of the "resolve"=3 kernel (0: from the particle density); dump the pairs it resolves
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
@@ -235,7 +236,7 @@ static void ensure_wave_buffers( Store *st ) {
     st->events_grid = per_sm * sms;   // latency bound: as many loads in flight as the SM holds
 }
 
-static void check_device_flags( Store *st ) {   // after a stream synchronise
+static void check_gs_flags( Store *st ) {   // after a stream synchronise
     if ( st->gs_flags ) {
         uint32_t flags = 0;
         PPC_CK( cudaMemcpy( &flags, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost ) );
@@ -248,6 +249,10 @@ static void check_device_flags( Store *st ) {   // after a stream synchronise
             abort();
         }
     }
+}
+
+static void check_device_flags( Store *st ) {   // after a stream synchronise
+    check_gs_flags( st );
     if ( !st->wave.counters )
         return;
     uint32_t flags = 0;
@@ -610,12 +615,15 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
 // Narrow phase + contact resolution over the first n slots of the (sorted) current set on grid G (K7, K7b).
 // "resolve"=3: narrow phase, position pushes and the tile Gauss-Seidel velocity resolve in one kernel (ppc_gs.cuh), one launch
 // per tile colour.  Reads the staged records the gather wrote, writes the final state into the sorted set's pv array.
+static int gs_auto_width( const double particles, const double cells ) {
+    const double per_cell = cells > 0 ? particles / cells : 0.0;
+    return (int)( (double)GS_TARGET / ( GS_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
+}
+
 static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
     int wc = st->opt_gs_wc;
-    if ( wc <= 0 ) {
-        const double per_cell = (double)n / (double)G.cells;
-        wc = (int)( (double)GS_TARGET / ( GS_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
-    }
+    if ( wc <= 0 )
+        wc = gs_auto_width( (double)n, (double)G.cells );
     const int wc_max = GS_THREADS / ( GS_R + 2 ) - 2 < GS_MAXC - 2 ? GS_THREADS / ( GS_R + 2 ) - 2 : GS_MAXC - 2;   // one thread per staged cell
     return wc < 2 ? 2 : ( wc > wc_max ? wc_max : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
 }
@@ -1093,6 +1101,10 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_wave_mode = (int)value;
     else if ( !strcmp( name, "slab_strict" ) )
         st->opt_slab_strict = (int)value;
+    else if ( !strcmp( name, "slab_nb_lo_rows" ) )
+        st->opt_nb_lo_rows = (int)value;
+    else if ( !strcmp( name, "slab_nb_hi_rows" ) )
+        st->opt_nb_hi_rows = (int)value;
     else if ( !strcmp( name, "gs_wc" ) )
         st->opt_gs_wc = (int)value;
     else if ( !strcmp( name, "gs_dump" ) )
@@ -1274,12 +1286,48 @@ extern "C" int ppc_grid_dims( uint16_t window_width, uint16_t window_height, flo
     return 0;
 }
 
+// "resolve"=3 on a slab.  The tile order is anchored at the whole field's cell (0, 0), so a rank computes the tiles of its window
+// exactly as the single-GPU run does, PROVIDED the window holds every tile an owned particle's velocity depends on.  Tiles of even
+// tile rows (colours 0, 1) depend on their own tile row plus one cell row either side; tiles of odd tile rows (colours 2, 3) on the
+// complete tile rows above and below as well.  Returns the ghost rows that takes for the owned rows [own_row_begin, own_row_end).
+extern "C" int ppc_slab_gs_halo( int own_row_begin, int own_row_end, int rows_total ) {
+    int need = 1;
+    if ( own_row_begin > 0 ) {
+        const int t0 = own_row_begin / GS_R;
+        const int first = ( t0 & 1 ) ? GS_R * t0 - GS_R - 1 : GS_R * t0 - 1;   // first cell row needed
+        const int lo = own_row_begin - ( first > 0 ? first : 0 );
+        need = lo > need ? lo : need;
+    }
+    if ( own_row_end < rows_total ) {
+        const int t1 = ( own_row_end - 1 ) / GS_R;
+        const int last = ( t1 & 1 ) ? GS_R * t1 + 2 * GS_R : GS_R * t1 + GS_R;   // last cell row needed
+        const int hi = ( last < rows_total - 1 ? last : rows_total - 1 ) - ( own_row_end - 1 );
+        need = hi > need ? hi : need;
+    }
+    return need;
+}
+
+// Tile width "resolve"=3 chooses for a whole field of `particles` particles on `cells` cells: what the ranks of a slab
+// decomposition must all set as "gs_wc" to reproduce the single-GPU pair order.
+extern "C" int ppc_gs_auto_tile_width( double particles, double cells ) {
+    Store tmp;
+    tmp.opt_gs_wc = gs_auto_width( particles, cells );
+    GridDims G = {};
+    G.cells = 1;
+    return gs_tile_width( &tmp, 1, G );
+}
+
 extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids, uint16_t window_width, uint16_t window_height,
                               float max_radius, int own_row_begin, int own_row_end, int halo_rows ) {
     Store         *st = store_of( p );
     const GridDims G  = world_grid( window_width, window_height, max_radius );
     if ( G.cols < 1 || G.rows < 1 || own_row_begin < 0 || own_row_end > G.rows || own_row_begin >= own_row_end || halo_rows < 1 || p->length > p->size )
         return -1;
+    // Ghost rows come from the two neighbouring ranks only, and a neighbour sends what it OWNS: a halo deeper than a neighbour's
+    // slab would leave the outer part of the window empty without anything noticing ("slab_nb_lo_rows" / "slab_nb_hi_rows").
+    if ( ( own_row_begin > 0 && st->opt_nb_lo_rows > 0 && halo_rows > st->opt_nb_lo_rows ) ||
+         ( own_row_end < G.rows && st->opt_nb_hi_rows > 0 && halo_rows > st->opt_nb_hi_rows ) )
+        return -5;
     if ( p->size != st->cap ) {
         PPC_CK( cudaStreamSynchronize( st->stream ) );
         resize_particle_arrays( st, p->size, 0 );
@@ -1323,6 +1371,7 @@ extern "C" int ppc_slab_init( struct Particles_t *p, const uint32_t *global_ids,
 // Did the last resolve keep the owned particles exact?  The resolve marks every particle whose result may differ from the
 // whole-field run (ST_TAINT, csrc/ppc_collide.cuh) and reports when the mark reaches an owned particle.  Stream must be idle.
 static int slab_halo_ok( Store *st ) {
+    check_gs_flags( st );
     if ( !st->wave.counters )
         return 1;
     uint32_t w[ 12 ];   // one read: error flags [3], taint reached an owned particle [10], rows it travelled [11]
@@ -1411,6 +1460,8 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
                  (unsigned long long)( n_lo + n_hi ), st->own_first, st->cap );
         abort();
     }
+    if ( st->opt_resolve == 3 && ( st->opt_gs_wc <= 0 || R.halo < ppc_slab_gs_halo( R.own_begin, R.own_end, GW.rows ) ) )
+        return -4;   // the tile order must be the whole field's ("gs_wc") and the window must hold every tile an owned particle depends on
     const int row_lo = R.own_begin - R.halo > 0 ? R.own_begin - R.halo : 0;
     const int row_hi = R.own_end + R.halo < GW.rows ? R.own_end + R.halo : GW.rows;
     GridDims  G;

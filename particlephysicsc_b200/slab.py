@@ -76,6 +76,19 @@ def required_halo(taint_rows: int, margin: int = 2) -> int:
     return int(taint_rows) + 1 + margin
 
 
+def gs_required_halo(ranges, rows: int) -> int:
+    """Ghost rows the "resolve"=3 path needs on a slab decomposition `ranges` of `rows` cell rows (the largest over the ranks):
+    its tile order is anchored at the whole field, and a window must hold every tile an owned particle depends on."""
+    lib = api.load_library()
+    return max(int(lib.ppc_slab_gs_halo(b, e, rows)) for b, e in ranges)
+
+
+def gs_options(n_total: int, W: int, H: int, max_radius: float) -> dict:
+    """Options that make every rank run the "resolve"=3 tile order of the WHOLE field (the tile width is part of the result)."""
+    _, cols, rows = grid_dims(W, H, max_radius)
+    return {"resolve": 3, "gs_wc": int(api.load_library().ppc_gs_auto_tile_width(float(n_total), float(cols) * float(rows)))}
+
+
 class HaloTooShallow(RuntimeError):
     """The dependency depth of a substep exceeded what the halo guarantees; owned velocities may be inexact."""
 
@@ -109,6 +122,8 @@ class DeviceSlab:
     def _init(self, ids, halo):
         W, H, max_radius, own_rows = self.geometry
         rc = self.p.lib.ppc_slab_init(C.byref(self.p.s), ids.ctypes.data_as(api.u32p), W, H, max_radius, own_rows[0], own_rows[1], halo)
+        if rc == -5:
+            raise ValueError(f"halo of {halo} rows is deeper than a neighbouring slab: ghost rows only come from the direct neighbours")
         if rc != 0:
             raise ValueError(f"ppc_slab_init failed ({rc})")
         self.halo = halo
@@ -150,6 +165,11 @@ class DeviceSlab:
         """With header=True n_lo / n_hi are the capacities of fixed-size messages; self.received holds the counts they carried."""
         got = (C.c_uint64 * 2)()
         n = int(self.p.lib.ppc_slab_finish(C.byref(self.p.s), dt, buf_lo.data_ptr(), n_lo, buf_hi.data_ptr(), n_hi, int(header), got))
+        if n == -4:
+            raise HaloTooShallow(f'"resolve"=3 needs "gs_wc" set and at least {self.p.lib.ppc_slab_gs_halo(*self.geometry[3], 1 << 30)} ghost rows here; '
+                                 f"this slab has {self.halo}")
+        if n < 0:
+            raise RuntimeError(f"ppc_slab_finish failed ({n})")
         self.received = (int(got[0]), int(got[1]))
         return n
 
@@ -401,6 +421,10 @@ def make_device_slabs(sc, world: int, halo: int, device_of=lambda k: 0, only_ran
             continue
         ii = idx[k]
         cap = int(need[k] * slack) + 65536
+        options = dict(options or {})
+        # ghost rows come from the direct neighbours only: the library refuses a halo deeper than a neighbour's slab
+        options["slab_nb_lo_rows"] = ranges[k - 1][1] - ranges[k - 1][0] if k > 0 else 0
+        options["slab_nb_hi_rows"] = ranges[k + 1][1] - ranges[k + 1][0] if k + 1 < world else 0
         out.append(DeviceSlab(sc.px[ii], sc.py[ii], sc.vx[ii], sc.vy[ii], sc.mass[ii], sc.radius[ii], sc.rgba[ii], ii.astype(np.uint32), sc.W, sc.H,
                               max_radius, ranges[k], halo, capacity=cap, device=device_of(k), options=options))
     return out

@@ -130,12 +130,84 @@ def test_shallow_halo_is_reported():
 
 
 def test_standard_entry_points_refuse_a_slab_store():
-    # misuse is loud, not silent: a slab store only holds part of the field
-    sc = scenes.uniform_random(5000, 2.0, 0.30, seed=406)
-    ranks = slab.make_device_slabs(sc, 2, 4)
-    assert ranks[0].info().halo_rows == 4 and ranks[0].info().n_owned + ranks[1].info().n_owned == sc.n
+    """Misuse is loud, not silent: a slab store only holds part of the field, so the whole-field entry points abort with a
+    message (checked in a child process: the library has no error return on the reference's void entry points)."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from particlephysicsc_b200 import scenes, slab\n"
+        "sc = scenes.uniform_random(5000, 2.0, 0.30, seed=406)\n"
+        "ranks = slab.make_device_slabs(sc, 2, 4)\n"
+        "assert ranks[0].info().halo_rows == 4 and ranks[0].info().n_owned + ranks[1].info().n_owned == sc.n\n"
+        "print('slabs ready', flush=True)\n"
+        "ranks[0].p.Update(0.001)\n"
+        "print('not reached', flush=True)\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "slabs ready" in out.stdout and "not reached" not in out.stdout
+    assert out.returncode != 0
+    assert "one slab of a multi-GPU field" in out.stderr
+
+
+def test_a_halo_deeper_than_a_neighbouring_slab_is_refused():
+    """Ghost rows only come from the two direct neighbours, which send what they own: a window reaching past a neighbour's slab
+    would stay partly empty without anything noticing, so the library refuses it at set-up."""
+    sc = scenes.uniform_random(20000, 2.0, 0.30, seed=412)
+    _, cols, rows = slab.grid_dims(sc.W, sc.H, 6.0)
+    thin = rows // 8   # rows per slab when cut into eight
+    with pytest.raises(ValueError, match="deeper than a neighbouring slab"):
+        slab.make_device_slabs(sc, 8, thin + 1)
+    for r in slab.make_device_slabs(sc, 8, thin):
+        r.free()
+
+
+# ---- "resolve"=3 (tile Gauss-Seidel) on slabs: exact by construction ----------------------------------------------------------
+GS_CASES = [
+    ("uniform_phi30_w4", lambda: scenes.uniform_random(300000, 2.0, 0.30, seed=421, vmax=300.0), 4, 8, False),
+    ("lattice_phi50_w3", lambda: scenes.jittered_lattice(200000, 2.0, 0.50, seed=422, vmax=500.0), 3, 8, False),
+    ("pile_w2_by_load", lambda: scenes.polydisperse_pile(150000, seed=423, vmax=20.0), 2, 6, True),
+    ("uniform_r1_phi40_w5", lambda: scenes.uniform_random(400000, 1.0, 0.40, seed=424, vmax=100.0), 5, 4, False),
+]
+
+
+@pytest.mark.parametrize("name,make,world,steps,by_load", GS_CASES)
+def test_tile_gauss_seidel_slabs_equal_the_whole_field(name, make, world, steps, by_load):
+    """The tile order is anchored at the whole field, so with the ghost rows ppc_slab_gs_halo asks for every rank computes its
+    owned particles exactly as the single-GPU run: positions, velocities, sorted order, cell-start table and pair set."""
+    sc = make()
+    want, grid, pairs, _ = single_gpu(sc, steps, {"resolve": 3})   # the single GPU chooses its tile width itself ...
+    max_radius = float(max(6.0, float(np.max(sc.radius))))
+    options = slab.gs_options(sc.n, sc.W, sc.H, max_radius)        # ... and the ranks are told the same one
+    _, ranges, _, _ = slab.split_scene(sc, world, 1, by_load)
+    _, cols, rows = slab.grid_dims(sc.W, sc.H, max_radius)
+    halo = slab.gs_required_halo(ranges, rows)
+    assert 1 <= halo <= 16
+    ranks = slab.make_device_slabs(sc, world, halo, options=options, by_load=by_load)
+    for _ in range(steps):
+        slab.local_step(ranks, DT)
+    got = gather(ranks, sc.n)
+    for k in want:
+        assert_bits_equal(got[k], want[k], f"{name} halo {halo} {k}")
+    order, starts = [], []
+    for r in ranks:
+        w = r.debug_window()
+        i = w["info"]
+        order.append(w["order"][i.own_first:i.own_first + i.n_owned])
+        c0, c1 = (i.own_row_begin - i.row_lo) * i.cols, (i.own_row_end - i.row_lo) * i.cols
+        starts.append(w["cell_start"][c0:c1].astype(np.int64) - int(i.own_first) + sum(len(o) for o in order[:-1]))
+    assert np.array_equal(np.concatenate(order), grid["order"])
+    assert np.array_equal(np.concatenate(starts), grid["cell_start"][:-1].astype(np.int64))
+    mine = np.concatenate([r.debug_pairs() for r in ranks]).astype(np.int64)
+    p64 = pairs.astype(np.int64)
+    assert np.array_equal(mine[np.lexsort((mine[:, 1], mine[:, 0]))], p64[np.lexsort((p64[:, 1], p64[:, 0]))])
     for r in ranks:
         r.free()
+    # one ghost row less than asked for is refused, not computed inexactly
+    if halo > 1:
+        ranks = slab.make_device_slabs(sc, world, halo - 1, options=options, by_load=by_load)
+        with pytest.raises(slab.HaloTooShallow):
+            slab.local_step(ranks, DT)
+        for r in ranks:
+            r.free()
 
 
 # ---- two processes, two GPUs, NCCL ---------------------------------------------------------------------------------
