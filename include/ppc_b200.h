@@ -152,6 +152,10 @@ int64_t ppc_debug_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs
 int64_t ppc_debug_hot_pairs( struct Particles_t *p, int32_t *pairs, size_t max_pairs );
 /* tile geometry of the last "resolve"=3 substep: {tile width, tile height (cells), strip threshold, strip capacity (particles)} */
 int     ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] );
+/* "resolve"=3 holds a sub-tile's particles, contacts and dependency levels in shared memory.  A substep in which some sub-tile
+ * does not fit (a region far denser than the rest of the field) is run on the exact resolve instead, for the whole field, so
+ * the result stays a function of the state alone.  Returns how many substeps of this store did that. */
+unsigned long long ppc_gs_fallbacks( struct Particles_t *p );
 /* last sequential-equivalent resolve: rounds = depth of the reference's pair dependency graph, visits = particle visits */
 int     ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *rounds, unsigned long long *visits );
 

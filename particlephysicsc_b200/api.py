@@ -60,7 +60,7 @@ REFERENCE_SYMBOLS = ["particlesCreate", "particlesFree", "particlesAddParticle",
                      "particlesCollisionsCheck_Grid"]
 EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_mask", "ppc_request_colors", "ppc_host_modified",
                      "ppc_download", "ppc_download_async", "ppc_download_wait", "ppc_synchronize", "ppc_run_substeps", "ppc_set_option", "ppc_debug_grid_info", "ppc_debug_keys",
-                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_hot_pairs", "ppc_debug_gs_params", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
+                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_hot_pairs", "ppc_debug_gs_params", "ppc_gs_fallbacks", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
 SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_gs_halo", "ppc_gs_auto_tile_width", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_download_async", "ppc_slab_info",
@@ -108,6 +108,7 @@ def load_library() -> C.CDLL:
     L.ppc_debug_pairs.argtypes, L.ppc_debug_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     L.ppc_debug_hot_pairs.argtypes, L.ppc_debug_hot_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     L.ppc_debug_gs_params.argtypes, L.ppc_debug_gs_params.restype = [PP, C.POINTER(C.c_int)], C.c_int
+    L.ppc_gs_fallbacks.argtypes, L.ppc_gs_fallbacks.restype = [PP], C.c_ulonglong
     L.ppc_debug_wave_stats.argtypes = [PP, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.ppc_debug_wave_stats.restype = C.c_int
     L.ppc_stream.argtypes, L.ppc_stream.restype = [PP], C.c_void_p
@@ -282,6 +283,10 @@ class Particles:
         if self.lib.ppc_debug_gs_params(C.byref(self.s), out) != 0:
             raise RuntimeError("no tile Gauss-Seidel substep has run")
         return dict(wc=out[0], tile_r=out[1], strip_limit=out[2], cap=out[3])
+
+    def gs_fallbacks(self) -> int:
+        """Substeps on which "resolve"=3 ran the exact resolve instead because a sub-tile overflowed the tile kernel."""
+        return int(self.lib.ppc_gs_fallbacks(C.byref(self.s)))
 
     def wave_stats(self):
         """(rounds, particle visits) of the last sequential-equivalent resolve."""

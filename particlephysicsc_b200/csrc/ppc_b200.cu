@@ -51,7 +51,7 @@ struct Store {
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
     int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi, 3 tile Gauss-Seidel
     int      opt_nb_lo_rows = 0, opt_nb_hi_rows = 0;   // slab mode: cell rows the lower / upper neighbour owns (0: not told)
-    int      opt_gs_wc = 0, opt_gs_dump = 0;   // tile width of the "resolve"=3 kernel (0: from the particle density); dump the pairs it resolves
+    int      opt_gs_wc = 0, opt_gs_dump = 0, opt_gs_strip = 0;   // tile width of the "resolve"=3 kernel (0: from the particle density); dump the pairs it resolves
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
     float pending_dt = 0.0f;
@@ -82,8 +82,11 @@ struct Store {
     size_t       gs_desc_cap = 0;
     uint32_t    *gs_flags = nullptr, *gs_dump = nullptr;   // gs_flags[0] error bits, [1] pairs dumped, [2] chunk units handed out
     uint32_t     gs_dump_cap = 0;
-    int          gs_wc = 0;
+    int          gs_wc = 0, gs_strip = 0;
     bool         gs_attr_set = false;
+    uint32_t    *h_gs_flag = nullptr;                       // pinned copy of gs_flags[0] after the narrow phase of the current substep
+    cudaEvent_t  ev_gs = nullptr;
+    unsigned long long gs_fallbacks = 0;                    // substeps the tile kernel could not hold and the exact resolve ran instead
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     WaveRecs     recs = {};          // packed records of the event-driven rounds
     int          events_grid = 0;
@@ -628,7 +631,8 @@ static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
     return wc < 2 ? 2 : ( wc > wc_max ? wc_max : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
 }
 
-static void resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
+// Returns true when the field did not fit and the caller must run the exact resolve on the (restored) sorted state instead.
+static bool resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
     if ( !st->gs_attr_set ) {
         PPC_CK( cudaFuncSetAttribute( k_gs_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( GsSmem ) ) );
         st->gs_attr_set = true;
@@ -637,6 +641,7 @@ static void resolve_gs( Store *st, const size_t n, const GridDims &G, const floa
     L.wc       = st->gs_wc = gs_tile_width( st, n, G );
     L.tiles_x  = ( G.cols + L.wc - 1 ) / L.wc;
     L.ty_first = G.row0 / GS_R;
+    L.strip_limit = st->gs_strip = ( st->opt_gs_strip > 0 && st->opt_gs_strip < GS_STRIP_LIMIT ) ? st->opt_gs_strip : GS_STRIP_LIMIT;
     const int    tiles_y = ( G.row0 + G.rows + GS_R - 1 ) / GS_R - L.ty_first;
     const size_t tiles   = (size_t)L.tiles_x * tiles_y;
     if ( tiles * GS_MAXSTRIPS > st->gs_desc_cap ) {
@@ -655,23 +660,44 @@ static void resolve_gs( Store *st, const size_t n, const GridDims &G, const floa
         PPC_LAUNCH( k_gs_pairs, (unsigned)tiles, GS_THREADS, sizeof( GsSmem ), st->stream, (const float4 *)st->rec_a, (const uint16_t *)st->gs_mcol,
                     st->set[ st->cur ].pv, st->cell_start, G, dt, L, PR, st->gs_flags, D );
     }
-    StageTimer T( st, ST_WAVEFRONT );     // velocity impulses: tiles of one colour at a time
-    for ( int colour = 0; colour < 4; colour++ ) {
-        L.colour   = colour;
-        L.ntx      = ( L.tiles_x - ( colour & 1 ) + 1 ) / 2;
-        L.ty_start = ( ( colour >> 1 ) - L.ty_first ) & 1;
-        const int nty = ( tiles_y - L.ty_start + 1 ) / 2;
-        if ( L.ntx <= 0 || nty <= 0 )
-            continue;
-        PPC_LAUNCH( k_gs_resolve, (unsigned)( L.ntx * nty ), GSB_THREADS, 0, st->stream, (const uint16_t *)st->gs_mcol, st->set[ st->cur ].pv, L, PR );
+    // Did every sub-tile fit the kernel's shared-memory capacities?  The answer travels to the host behind the narrow phase; the
+    // velocity kernels are queued meanwhile and do nothing if it is no, so the GPU never waits for the host.
+    if ( !st->h_gs_flag ) {
+        PPC_CK( cudaHostAlloc( (void **)&st->h_gs_flag, sizeof( uint32_t ), cudaHostAllocDefault ) );
+        PPC_CK( cudaEventCreateWithFlags( &st->ev_gs, cudaEventDisableTiming ) );
     }
+    PPC_CK( cudaMemcpyAsync( st->h_gs_flag, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaEventRecord( st->ev_gs, st->stream ) );
+    {
+        StageTimer T( st, ST_WAVEFRONT );     // velocity impulses: tiles of one colour at a time
+        for ( int colour = 0; colour < 4; colour++ ) {
+            L.colour   = colour;
+            L.ntx      = ( L.tiles_x - ( colour & 1 ) + 1 ) / 2;
+            L.ty_start = ( ( colour >> 1 ) - L.ty_first ) & 1;
+            const int nty = ( tiles_y - L.ty_start + 1 ) / 2;
+            if ( L.ntx <= 0 || nty <= 0 )
+                continue;
+            PPC_LAUNCH( k_gs_resolve, (unsigned)( L.ntx * nty ), GSB_THREADS, 0, st->stream, (const uint16_t *)st->gs_mcol, st->set[ st->cur ].pv, L, PR,
+                        (const uint32_t *)st->gs_flags );
+        }
+    }
+    PPC_CK( cudaEventSynchronize( st->ev_gs ) );
+    if ( *st->h_gs_flag == 0u )
+        return false;
+    if ( st->slab )    // a rank cannot fall back on its own: the single-GPU run it must equal would have done so for the whole field
+        return false;  // (the flag stays set; the next synchronising call reports it)
+    // Some sub-tile overflowed (a region far denser than the rest: an impact front, a clump of overlapping particles).  This substep
+    // runs on the exact resolve instead -- for the WHOLE field, so the result is a function of the state alone: positions back to what
+    // the pair search saw (the velocities are untouched: the velocity kernels above saw the flag), then the reference's order.
+    st->gs_fallbacks++;
+    PPC_CK( cudaMemsetAsync( st->gs_flags, 0, sizeof( uint32_t ), st->stream ) );
+    PPC_LAUNCH( k_rec_to_positions, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, st->set[ st->cur ].pv, n );
+    return true;
 }
 
 static void resolve_stage( Store *st, const size_t n, const GridDims &G, const float dt ) {
-    if ( st->opt_resolve == 3 ) {
-        resolve_gs( st, n, G, dt );
+    if ( st->opt_resolve == 3 && !resolve_gs( st, n, G, dt ) )
         return;
-    }
     ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
     if ( st->opt_resolve ) {
         const bool jacobi = st->opt_resolve == 2;
@@ -931,6 +957,10 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFree( st->wave_items );
         cudaFree( st->wave_n_items );
         cudaFree( st->gs_flags );
+        if ( st->h_gs_flag ) {
+            cudaFreeHost( st->h_gs_flag );
+            cudaEventDestroy( st->ev_gs );
+        }
         cudaEventDestroy( st->ev0 );
         cudaEventDestroy( st->ev1 );
         cudaStreamDestroy( st->stream );
@@ -1107,6 +1137,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_nb_hi_rows = (int)value;
     else if ( !strcmp( name, "gs_wc" ) )
         st->opt_gs_wc = (int)value;
+    else if ( !strcmp( name, "gs_strip" ) )
+        st->opt_gs_strip = (int)value;
     else if ( !strcmp( name, "gs_dump" ) )
         st->opt_gs_dump = (int)value;
     else
@@ -1253,9 +1285,12 @@ extern "C" int ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] ) {
     Store *st = store_of( p );
     if ( st->opt_resolve != 3 || st->gs_wc == 0 )
         return -1;
-    out[ 0 ] = st->gs_wc, out[ 1 ] = GS_R, out[ 2 ] = GS_STRIP_LIMIT, out[ 3 ] = GS_CAP;
+    out[ 0 ] = st->gs_wc, out[ 1 ] = GS_R, out[ 2 ] = st->gs_strip, out[ 3 ] = GS_CAP;
     return 0;
 }
+
+// Substeps of this store on which "resolve"=3 fell back to the exact resolve because a sub-tile overflowed the tile kernel.
+extern "C" unsigned long long ppc_gs_fallbacks( struct Particles_t *p ) { return store_of( p )->gs_fallbacks; }
 
 // =================================================================================================================
 // Part 3: multi-GPU slab decomposition (one store per rank; the caller moves the exchange buffers, e.g. with

@@ -186,6 +186,15 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_rec_to_pv( const float4 *_
     pv[ k ] = make_float4( a.x, a.y, 0.0f, 0.0f );
 }
 
+// "resolve"=3 fell back to the exact resolve: positions back to what the pair search saw; the velocities were not touched
+__global__ void __launch_bounds__( STREAM_THREADS ) k_rec_to_positions( const float4 *__restrict__ rec_a, float4 *__restrict__ pv, const size_t n ) {
+    const size_t k = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    if ( k >= n )
+        return;
+    const float4 a = rec_a[ k ];
+    *reinterpret_cast<float2 *>( pv + k ) = make_float2( a.x, a.y );
+}
+
 // keys by API index / sorted order, for the parity exporters
 __global__ void __launch_bounds__( STREAM_THREADS ) k_export_keys( const ParticleSet S, uint32_t *__restrict__ keys_by_gid, const size_t n ) {
     const size_t k = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;

@@ -119,6 +119,7 @@ struct GsLaunch {
     int colour;      // k_gs_resolve: 0..3 = (tx & 1) + 2 (ty & 1) of the tiles this launch runs
     int ntx;         // k_gs_resolve: tiles of this colour per tile row
     int ty_start;    // k_gs_resolve: first local tile row of this colour
+    int strip_limit; // staged particles (strip + halo) above which a tile is cut into strips, and which a strip may hold (<= GS_CAP)
 };
 
 // Pair records of one substep: one chunk per sub-tile, allocated with one atomic add, in units of 16 bytes:
@@ -166,12 +167,13 @@ __device__ __forceinline__ void gs_column_sums( uint32_t *colp, const uint32_t *
 }
 
 // End of the strip that starts at column sx: a tile that would overflow shared memory is cut greedily from the left, each strip
-// taking as many columns as keep its staged particles (strip + one halo column either side) within GS_STRIP_LIMIT, at least one.
-__device__ __forceinline__ int gs_strip_end( const uint32_t *colp, const uint32_t total, const int sx, const int cx1, const int c0, const int c1 ) {
-    if ( total <= (uint32_t)GS_STRIP_LIMIT )
+// taking as many columns as keep its staged particles (strip + one halo column either side) within the limit, at least one.
+__device__ __forceinline__ int gs_strip_end( const uint32_t *colp, const uint32_t total, const int sx, const int cx1, const int c0, const int c1,
+                                             const uint32_t limit ) {
+    if ( total <= limit )
         return cx1;
     int ex = sx + 1;
-    while ( ex < cx1 && colp[ min( ex + 2, c1 ) - c0 ] - colp[ max( sx - 1, c0 ) - c0 ] <= (uint32_t)GS_STRIP_LIMIT )
+    while ( ex < cx1 && colp[ min( ex + 2, c1 ) - c0 ] - colp[ max( sx - 1, c0 ) - c0 ] <= limit )
         ex++;
     return ex;
 }
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_gs_pairs( co
     uint32_t parity = 0;
     int      strip  = 0;
     for ( int sx = cx0; sx < cx1; strip++ ) {
-        const int      ex   = gs_strip_end( T.colp, total, sx, cx1, c0, c1 );
+        const int      ex   = gs_strip_end( T.colp, total, sx, cx1, c0, c1, (uint32_t)L.strip_limit );
         const uint32_t last = ex >= cx1 ? GS_LAST_STRIP : 0u;
         if ( threadIdx.x == 0 )
             desc[ strip ] = make_uint2( 0u, last );   // until the sub-tile turns out to own pairs (same thread, program order)
@@ -814,8 +816,11 @@ struct GsbSmem {
     unsigned long long mbar[ 2 ];
 };
 
-__global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *__restrict__ mcol, float4 *pv, const GsLaunch L, const GsPairs PR ) {
+__global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *__restrict__ mcol, float4 *pv, const GsLaunch L, const GsPairs PR,
+                                                                const uint32_t *__restrict__ err_flags ) {
     __shared__ __align__( 16 ) GsbSmem T;
+    if ( *err_flags )   // some sub-tile did not fit: the host runs the exact resolve for this substep instead
+        return;
     const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
     const int tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;   // ty: tile row inside this grid
     const uint2 *desc = PR.desc + ( (size_t)ty * L.tiles_x + tx ) * GS_MAXSTRIPS;

@@ -113,6 +113,39 @@ def test_tiny_and_degenerate_fields(oracle):
         p.Free()
 
 
+def test_an_overfull_tile_runs_that_substep_on_the_exact_resolve(oracle):
+    """A region far denser than the tile kernel's shared memory takes (here: clumps of hundreds of overlapping particles) makes
+    the WHOLE substep fall back to the exact resolve, so that substep equals the sequential reference bit for bit; the
+    substeps that fit keep following the tile Gauss-Seidel model.  Never an abort, never a silent partial resolve."""
+    from oracle.oracle import State
+    n, W, H = 12000, 3000, 3000
+    rng = scenes.Stream(121)
+    s = State.empty(n)
+    cx, cy = rng.unit(30) * (W - 400) + 200, rng.unit(30) * (H - 400) + 200      # 30 clumps of 400 particles within 90 px
+    k = np.arange(n) % 30
+    s.px[:] = cx[k] + (rng.unit(n) - 0.5) * 90
+    s.py[:] = cy[k] + (rng.unit(n) - 0.5) * 90
+    s.vx[:] = (rng.unit(n) - 0.5) * 100
+    s.vy[:] = (rng.unit(n) - 0.5) * 100
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 1.5 + rng.unit(n) * 4.5
+    ref = s.copy()
+    p = gs_store(s)
+    fell_back = []
+    for step in range(6):
+        before = p.gs_fallbacks()
+        p.Update(DT)
+        p.CollisionsCheck_Grid(W, H, DT)
+        fell_back.append(p.gs_fallbacks() - before)
+        par = p.gs_params()
+        oracle.set_tilegs(par["wc"], par["tile_r"], par["strip_limit"])
+        oracle.substep(ref, W, H, DT, 0 if fell_back[-1] else 3, False)
+        assert_state_bits(gpu_state(p), ref, f"clumps, substep {step}, fell back: {fell_back[-1]}")
+    print("clumps: substeps that fell back to the exact resolve:", fell_back)
+    assert fell_back[0] == 1
+    p.Free()
+
+
 # ---- statistics against the compiled reference ----------------------------------------------------------------------
 def _reference_runs(sc, steps, dt):
     from oracle import oracle as om
@@ -162,6 +195,8 @@ def test_thousand_substeps_on_the_dense_pile_within_the_references_own_spread(or
     p = gs_store(state_from_scene(sc))
     p.run_substeps(sc.W, sc.H, dt, steps)
     got = gpu_state(p)
+    print(f"\ndense pile: {p.gs_fallbacks()} of {steps} substeps fell back to the exact resolve (a sub-tile overflowed the tile kernel)")
+    assert p.gs_fallbacks() < steps // 4
     p.Free()
     assert np.isfinite(got.px).all() and np.isfinite(got.py).all() and np.isfinite(got.vx).all() and np.isfinite(got.vy).all()
     dev, spread = _report(oracle, sc, got, _reference_runs(sc, steps, dt), f"dense pile, {steps} substeps")
@@ -176,6 +211,8 @@ def test_sixteen_million_pile_stays_finite_for_a_thousand_substeps():
     p = gs_store(state_from_scene(sc))
     p.run_substeps(sc.W, sc.H, DT, 1000)
     got = gpu_state(p)
+    print(f"\n16M pile: {p.gs_fallbacks()} of 1000 substeps fell back to the exact resolve")
+    assert p.gs_fallbacks() == 0
     p.Free()
     for a in (got.px, got.py, got.vx, got.vy):
         assert np.isfinite(a).all()
