@@ -27,6 +27,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RESOLVE_NAMES = {1: "sequential-equivalent wavefront (replays the reference's pair order: positions and velocities bit-exact)",
+                 2: "jacobi",
+                 3: "tile Gauss-Seidel in shared memory (deterministic, bounded passes; integer work and positions bit-exact, velocities = "
+                    "the reference's sequential pass 2 in a tile order, checked bit for bit against its CPU model)"}
 METRIC = "particle-substeps/sec (collisions on)"
 UNIT = "particle-substeps/s"
 ALGO_BYTES_PER_PARTICLE_SUBSTEP = 40.0   # read p,v,r,m (24 B) + write p,v (16 B)
@@ -154,7 +158,7 @@ def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float =
         step(s, sc.W, sc.H)
         per_particle = (time.perf_counter() - t0) / (1 << 16)
         want = budget_s / max(1, steps + warmup) / per_particle
-        n = 1 << max(14, min(20, int(np.floor(np.log2(max(want, 1.0))))))
+        n = 1 << max(14, min(24, int(np.floor(np.log2(max(want, 1.0))))))
         n = min(n, WORKLOADS[workload][0])
     sc, s = field(n)
     for _ in range(warmup):
@@ -172,13 +176,103 @@ def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float =
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    value, ms, base = time_reference_cpu(args.workload, args.steps, args.warmup, budget_s=90.0)
+    value, ms, base = time_reference_cpu(args.workload, args.steps, args.warmup, budget_s=170.0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][1], "sample": base["sample"]},
             "cpu_baseline": base, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def one_slab(api, torch, local_rank: int, n_per: int, steps: int, settle: int, warmup: int, peak: float, resolve: int = 1, opts=None):
+    """BASELINE configs[3]'s per-GPU workload as ONE slab on ONE GPU (no neighbours): the denominator of the weak-scaling
+    efficiency.  Returns value (state resident) and e2e (owned positions + colours to the host every 8th substep)."""
+    from particlephysicsc_b200 import scenes, slab
+    rows_per = max(8, int(round(SLAB_ROWS_PER_GPU * n_per / float(1 << 25))))
+    H = rows_per * SLAB_CELL
+    sc = scenes.uniform_slab(n_per, SLAB_RADIUS, SLAB_W, H, 0, H, seed=0x5EED0004)
+    o = dict(opts or {})
+    o["resolve"] = resolve = int(o.get("resolve", resolve))
+    if resolve == 3:   # the tile order is part of the result: every slab of a field is told the whole field's tile width
+        o.update(slab.gs_options(n_per, SLAB_W, H, 6.0))
+    me = slab.DeviceSlab(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba, np.arange(n_per, dtype=np.uint32), SLAB_W, H, 6.0, (0, rows_per), 4,
+                         capacity=int(1.15 * n_per) + 65536, device=local_rank, options=o)
+
+    def run(k, colour_every=0):
+        for s in range(k):
+            slab.local_step([me], DT, bool(colour_every) and (s % colour_every == colour_every - 1))
+
+    run(settle + warmup)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(me.stream)
+    run(steps)
+    e1.record(me.stream)
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    frames = max(1, steps // SUBSTEPS_PER_FRAME)
+    e0.record(me.stream)
+    for _ in range(frames):
+        run(SUBSTEPS_PER_FRAME, colour_every=SUBSTEPS_PER_FRAME)
+        me.sync_host_async()
+    me.sync_host_wait()
+    e1.record(me.stream)
+    e1.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / (frames * SUBSTEPS_PER_FRAME)
+    me.free()
+    return {"workload": WORKLOADS["slab32m"][1] + " -- one slab on one GPU, no neighbours", "resolve_option": resolve, "particles": n_per,
+            "value": n_per / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "e2e": {"value": n_per / (e2e_ms * 1e-3), "unit": UNIT},
+            "roofline_substep_frac": ALGO_BYTES_PER_PARTICLE_SUBSTEP * n_per / (ms * 1e-3) / 1e9 / peak}
+
+
+def state_digest(ids, *arrays) -> int:
+    """Sum over particles of a 64-bit mix of (index, field bit patterns): independent of the order and of how particles are split."""
+    with np.errstate(over="ignore"):
+        h = ids.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+        for a in arrays:
+            h = (h ^ np.ascontiguousarray(a).view(np.uint32).astype(np.uint64)) * np.uint64(0xBF58476D1CE4E5B9)
+            h ^= h >> np.uint64(29)
+        return int(np.sum(h, dtype=np.uint64))
+
+
+def slab_equivalence(api, torch, dist, rank: int, world: int, local_rank: int, particles: int = 1 << 21, steps: int = 8, halo: int = 8):
+    """Before anything is timed: a small field cut into `world` slabs and stepped over NCCL must equal the same field stepped as a
+    whole on one GPU -- an order-independent 64-bit digest of (global index, p_x, p_y, v_x, v_y bit patterns) over all particles."""
+    from particlephysicsc_b200 import scenes, slab
+    sc = scenes.uniform_random(particles, 2.0, 0.30, seed=0x5EED0006, vmax=200.0)
+    me = slab.make_device_slabs(sc, world, halo, device_of=lambda k: local_rank, only_rank=rank)[0]
+    tr = slab.DistTransport(dist, torch.device("cuda", local_rank))
+    travelled = 0
+    for _ in range(steps):
+        slab.slab_step(me, tr, DT)
+        travelled = max(travelled, int(me.info().taint_rows))
+    d = me.download()
+    full = state_digest(d["ids"], d["p_x"], d["p_y"], d["v_x"], d["v_y"])
+    # digests are sums modulo 2^64; add them as two 32-bit halves so that the int64 all_reduce cannot overflow
+    parts = torch.tensor([full & 0xFFFFFFFF, full >> 32, len(d["ids"]), int(d["halo_ok"])], dtype=torch.int64, device="cuda")
+    dist.all_reduce(parts, op=dist.ReduceOp.SUM)   # set-up check, not the data path
+    tmax = torch.tensor([travelled], dtype=torch.int64, device="cuda")
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    me.free()
+    out = None
+    if rank == 0:
+        lo, hi, count, ok = (int(x) for x in parts.tolist())
+        slabs = (lo + (hi << 32)) & 0xFFFFFFFFFFFFFFFF
+        p = api.Particles(sc.n, device=local_rank)
+        p.set_sync_policy(api.PPC_SYNC_MANUAL)
+        p.fill(sc.px, sc.py, sc.vx, sc.vy, sc.mass, sc.radius, sc.rgba)
+        p.run_substeps(sc.W, sc.H, DT, steps)
+        p.download(api.PPC_DL_ALL)
+        whole = state_digest(np.arange(sc.n, dtype=np.uint32), p.array("p_x"), p.array("p_y"), p.array("v_x"), p.array("v_y"))
+        p.Free()
+        out = {"bit_identical": slabs == whole and count == sc.n and ok == world, "particles": sc.n, "substeps": steps, "slabs": world,
+               "halo_rows": halo, "inexactness_travel_rows": int(tmax.item()), "all_ranks_report_exact": ok == world,
+               "particles_owned_by_all_ranks": count, "digest_slabs": f"{slabs:016x}", "digest_single_gpu": f"{whole:016x}",
+               "what": "r=2 uniform random field at area fraction 0.30, initial speeds up to 200 px/s (particles migrate between slabs), slabs over "
+                       "NCCL send/recv vs the whole field on one GPU; digest over (global index, p_x, p_y, v_x, v_y) bit patterns"}
+    dist.barrier()
+    return out
 
 
 def run_b200(args, rank: int, world: int, local_rank: int):
@@ -268,10 +362,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # algorithmic bytes per particle of each kernel: what that kernel cannot avoid moving
     algo = {"integrate_walls_keys": 36.0, "collide": 40.0, "resolve_wavefront": 16.0, "canonical_gather": 60.0, "cell_sort": 8.0}.get(
         dom, ALGO_BYTES_PER_PARTICLE_SUBSTEP)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+    traffic = substep_traffic = None
+    try:   # DRAM bytes per launch (per substep for kernels launched several times) from the ncu --set full captures under profiles/
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+            per_stage = json.load(f).get(f"{args.workload}_resolve{args.resolve}", {})
+        traffic = per_stage.get(dom)
+        substep_traffic = per_stage.get("whole_substep")
     except Exception:
         traffic = None
     roofline = None
@@ -283,13 +379,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                     "stage_ms_per_substep": {k: round(v[0], 4) for k, v in stages.items()}}
     substep_gbs = ALGO_BYTES_PER_PARTICLE_SUBSTEP * n * world * args.steps / (ms_total * 1e-3) / 1e9
 
-    def quick_value(workload: str, steps: int = 16):
+    def quick_value(workload: str, steps: int = 16, resolve: int | None = None, scene=None, label: str | None = None):
         """particle-substeps/s of another single-GPU configuration (state resident, same timing rules), for context."""
-        m, _ = WORKLOADS[workload]
-        sc2 = make_scene(workload, m)
+        resolve = args.resolve if resolve is None else resolve
+        sc2 = scene if scene is not None else make_scene(workload, WORKLOADS[workload][0])
+        m = sc2.n
         q = api.Particles(m, device=local_rank)
         q.set_sync_policy(api.PPC_SYNC_MANUAL)
-        q.set_option("resolve", args.resolve)
+        q.set_option("resolve", resolve)
         q.fill(sc2.px, sc2.py, sc2.vx, sc2.vy, sc2.mass, sc2.radius, sc2.rgba)
         q.run_substeps(sc2.W, sc2.H, DT, args.settle + args.warmup)
         ext2 = torch.cuda.ExternalStream(q.stream(), device=torch.device("cuda", local_rank))
@@ -300,10 +397,31 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         a1.record(ext2)
         a1.synchronize()
         ms = a0.elapsed_time(a1) / steps
+        fell = q.gs_fallbacks() if resolve == 3 else None
         q.Free()
-        return {"workload": WORKLOADS[workload][1], "value": m / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+        return {"workload": label or WORKLOADS[workload][1], "resolve_option": resolve, "value": m / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                 "roofline_substep_frac": ALGO_BYTES_PER_PARTICLE_SUBSTEP * m / (ms * 1e-3) / 1e9 / peak,
+                "gs_substeps_that_fell_back": fell,
                 "l2": "state larger than L2" if 28.0 * m > 126e6 else "state fits the 126 MB L2 (no flush): not an HBM-roofline number"}
+
+    def other_configs():
+        """Context for the headline, measured in this same run: the same field under the other resolve, the other single-GPU
+        configurations of BASELINE.json, three points of the configs[4] density sweep, and one slab of the configs[3] field
+        (the weak-scaling denominator of the multi-GPU runs: value AND end-to-end)."""
+        from particlephysicsc_b200 import scenes
+        out = {}
+        other = 1 if args.resolve == 3 else 3
+        out[f"{args.workload}_resolve{other}"] = quick_value(args.workload, resolve=other)
+        for w in ("uniform16m", "uniform1m"):
+            if w != args.workload:
+                out[w] = quick_value(w)
+        out[f"uniform16m_resolve{other}"] = quick_value("uniform16m", resolve=other)
+        out["density_sweep_16m"] = [
+            dict(quick_value("uniform16m", steps=8, scene=scenes.uniform_random(1 << 24, 2.0, phi, seed=0x5EED0005, vmax=0.0),
+                             label=f"16M equal-radius particles (r=2), uniform random, area fraction {phi} (BASELINE configs[4])"),
+                 area_fraction=phi) for phi in (0.05, 0.40, 0.80)]
+        out["slab32m_one_slab"] = one_slab(api, torch, local_rank, 1 << 25, args.steps, args.settle, args.warmup, peak)
+        return out
 
     line = None
     if rank == 0:
@@ -312,7 +430,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             _, _, cpu = time_reference_cpu(args.workload, 3, 1)
         others = None
         if world == 1 and not args.no_other_configs:
-            others = {w: quick_value(w) for w in ("uniform16m", "uniform1m") if w != args.workload}
+            others = other_configs()
         g = p.grid_info()
         wave = p.wave_stats()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -320,12 +438,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 "data": "synthetic",
                 "config": {"workload": descr, "particles_per_gpu": n, "box": [W, H], "dt": DT, "grid": [g.cols, g.rows],
                            "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
-                           "resolve": {1: "sequential-equivalent wavefront (bit-exact)", 2: "jacobi"}.get(args.resolve, str(args.resolve)),
+                           "resolve": RESOLVE_NAMES.get(args.resolve, str(args.resolve)),
+                           "resolve_option": args.resolve,
+                           "gs_substeps_that_fell_back_to_the_exact_resolve": p.gs_fallbacks() if args.resolve == 3 else None,
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n / 1e6),
                            "parallelism": "independent replicas" if world > 1 else "single GPU"},
                 "roofline": roofline,
                 "roofline_substep": {"bound": "hbm", "achieved": substep_gbs / world, "peak": peak, "unit": "GB/s",
-                                     "frac": substep_gbs / world / peak, "note": "40 B x particles x substeps / time, whole substep, per GPU"},
+                                     "frac": substep_gbs / world / peak, "traffic": substep_traffic,
+                                     "note": "40 B x particles x substeps / time, whole substep, per GPU; traffic = DRAM bytes of all kernels of "
+                                             "one substep (ncu capture under profiles/)"},
                 "cpu_baseline": cpu,
                 "other_configs": others,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step,
@@ -359,6 +481,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     rows_per = max(8, int(round(SLAB_ROWS_PER_GPU * n_per / float(1 << 25))))
     n_total = n_per if split else n_per * world
     opts = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}
+    opts.setdefault("resolve", args.resolve)
+    gs = opts["resolve"] == 3
     whole = make_scene(args.workload, n_per) if split else None
     box_w = whole.W if split else SLAB_W
 
@@ -423,10 +547,25 @@ def run_slab(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)   # set-up only; nothing on the data path is a collective
         return int(t.item())
 
-    me, H = make_rank(rank, world, args.settle_halo)
-    me.p.set_option("slab_strict", 0)   # a halo that turns out too thin is counted, then the phase is redone with a wider one
+    equivalence = None
+    if dist is not None and not args.no_equivalence:
+        equivalence = slab_equivalence(api, torch, dist, rank, world, local_rank)
     tr = slab.DistTransport(dist, dev) if dist is not None else None
-    halo, rounds, travelled = settle_and_choose_halo(me, tr, group_max)
+    if gs:   # "resolve"=3: the ghost rows the tile order needs (exact by construction: nothing to measure, nothing to retry)
+        if split:
+            _, ranges, _, _ = slab.split_scene(whole, world, 1, True)
+            _, _, rows_all = slab.grid_dims(whole.W, whole.H, float(max(6.0, float(np.max(whole.radius)))))
+            opts.update(slab.gs_options(whole.n, whole.W, whole.H, float(max(6.0, float(np.max(whole.radius))))))
+        else:
+            ranges, rows_all = [(k * rows_per, (k + 1) * rows_per) for k in range(world)], rows_per * world
+            opts.update(slab.gs_options(n_per * world, SLAB_W, rows_all * SLAB_CELL, 6.0))
+        halo, rounds, travelled = (slab.gs_required_halo(ranges, rows_all) if world > 1 else 1), 0, 0
+        me, H = make_rank(rank, world, halo)
+        run(me, tr, args.settle)
+    else:
+        me, H = make_rank(rank, world, args.settle_halo)
+        me.p.set_option("slab_strict", 0)   # a halo that turns out too thin is counted, then the phase is redone with a wider one
+        halo, rounds, travelled = settle_and_choose_halo(me, tr, group_max)
     halo_retries = 0
     while True:
         run(me, tr, args.warmup)
@@ -484,18 +623,22 @@ def run_slab(args, rank: int, world: int, local_rank: int):
 
     # the same per-GPU workload on ONE GPU (a single slab, no neighbours), measured by rank 0 in this same job: the
     # denominator of the parallel efficiency
-    ref_value = None
+    ref_value = ref_e2e = None
     barrier()
     if rank == 0 and world > 1 and not args.no_scaling_reference:
         me.free()
-        solo, _ = make_rank(0, 1, 4)
-        run(solo, None, args.settle + args.warmup)
-        e0.record(solo.stream)
-        run(solo, None, args.steps)
-        e1.record(solo.stream)
-        e1.synchronize()
-        ref_value = ( n_total if split else n_per ) * args.steps / (e0.elapsed_time(e1) * 1e-3)
-        solo.free()
+        if split:
+            solo, _ = make_rank(0, 1, 4)
+            run(solo, None, args.settle + args.warmup)
+            e0.record(solo.stream)
+            run(solo, None, args.steps)
+            e1.record(solo.stream)
+            e1.synchronize()
+            ref_value = n_total * args.steps / (e0.elapsed_time(e1) * 1e-3)
+            solo.free()
+        else:
+            ref = one_slab(api, torch, local_rank, n_per, args.steps, args.settle, args.warmup, peak, opts=opts)
+            ref_value, ref_e2e = ref["value"], ref["e2e"]["value"]
     if dist is not None:
         dist.barrier()
 
@@ -508,8 +651,8 @@ def run_slab(args, rank: int, world: int, local_rank: int):
             ach = algo * info.n_window / (stages[dom][0] * 1e-3) / 1e9
             traffic = None
             try:   # bytes per launch from the ncu --set full capture of one 2**25-particle slab (profiles/)
-                with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                    traffic = json.load(f).get("slab32m", {}).get(dom) if (not split and n_per == 1 << 25) else None
+                with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                    traffic = json.load(f).get(f"slab32m_resolve{opts['resolve']}", {}).get(dom) if (not split and n_per == 1 << 25) else None
             except Exception:
                 traffic = None
             roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
@@ -524,7 +667,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                            "inexactness_travel_rows": travelled, "halo_retries": halo_retries,
                            "owned_particles_exact_in_timed_region": exact, "dt": DT,
                            "substeps_per_frame": SUBSTEPS_PER_FRAME, "settle_substeps": args.settle,
-                           "resolve": "sequential-equivalent wavefront (bit-exact)",
+                           "resolve": RESOLVE_NAMES.get(int(opts.get("resolve", args.resolve)), "?"), "resolve_option": int(opts.get("resolve", args.resolve)),
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n_per / 1e6),
                            "parallelism": f"{world} slabs of cell rows, neighbour send/recv (NCCL) of migrants + {halo} ghost rows per substep"
                                           if world > 1 else "one slab (no neighbours)",
@@ -538,7 +681,9 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                     "note": ("the whole field as one slab on one GPU, measured by rank 0 in this job; parallel efficiency = value / (n_gpus x this)"
                              if split else "the same per-GPU workload as one slab on one GPU, measured by rank 0 in this job; "
                              "parallel efficiency = value / (n_gpus x this)"),
-                    "parallel_efficiency": value / (world * ref_value)},
+                    "parallel_efficiency": value / (world * ref_value),
+                    "e2e": None if ref_e2e is None else {"value": ref_e2e, "unit": UNIT, "parallel_efficiency": e2e_value / (world * ref_e2e)}},
+                "equivalence": equivalence,
                 "cpu_baseline": None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12.0 * n_down / SUBSTEPS_PER_FRAME,
                         "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays (asynchronously: a frame's "
@@ -569,18 +714,23 @@ def main():
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
     ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--no-equivalence", action="store_true", help="skip the N-slabs == one-GPU digest check that precedes the timing")
     ap.add_argument("--replicas", action="store_true", help="with --gpus N and a single-GPU workload: N independent copies instead of N slabs of one field")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the context measurements of the other single-GPU configurations")
-    ap.add_argument("--resolve", type=int, default=1, help="1 = sequential-equivalent wavefront (default, bit-exact), 2 = Jacobi")
+    ap.add_argument("--resolve", type=int, default=0,
+                    help="3 = tile Gauss-Seidel (deterministic bounded passes; default on one GPU), 1 = sequential-equivalent wavefront "
+                         "(bit-exact replay of the reference's pair order; default for slabs), 2 = Jacobi")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload is None:
         args.workload = "pile16m" if args.gpus == 1 else "slab32m"
+    if args.resolve == 0:
+        args.resolve = 1 if (args.workload == "slab32m" or (args.gpus > 1 and not args.replicas)) else 3
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -16,6 +16,10 @@
 #include <stdlib.h>
 #include <time.h>
 
+/* The B200 library's frame copy-back moves what the draw loop reads (p_x, p_y, colors); velocities come on request.  The symbol is
+ * weak so that this file still links against the reference's own objects, where the host arrays ARE the state. */
+extern void ppc_download( struct Particles_t *p, unsigned mask ) __attribute__( ( weak ) );
+
 static uint64_t g_state = 0x5EED0001ull;
 static uint64_t next_u64( void ) {
     uint64_t z = ( g_state += 0x9E3779B97F4A7C15ull );
@@ -49,6 +53,8 @@ int main( int argc, char **argv ) {
     clock_gettime( CLOCK_MONOTONIC, &t1 );
     const double secs = ( t1.tv_sec - t0.tv_sec ) + 1e-9 * ( t1.tv_nsec - t0.tv_nsec );
     double       sx = 0, sy = 0, ke = 0;
+    if ( ppc_download )
+        ppc_download( &particles, PPC_DL_VEL );
     for ( size_t k = 0; k < particles.length; k++ ) {
         sx += particles.p_x[ k ];
         sy += particles.p_y[ k ];

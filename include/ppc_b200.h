@@ -96,7 +96,10 @@ enum { PPC_DL_POS = 1, PPC_DL_VEL = 2, PPC_DL_COLOR = 4, PPC_DL_ALL = 7 };
 
 void ppc_set_device( int cuda_device );                               /* before the first particlesCreate; default 0 or $PPC_DEVICE */
 void ppc_set_sync_policy( struct Particles_t *p, int policy );
-void ppc_set_download_mask( struct Particles_t *p, unsigned mask );   /* arrays moved by the automatic copy-back */
+void ppc_set_download_mask( struct Particles_t *p, unsigned mask );   /* arrays moved by the automatic copy-back; default by policy:
+                                                                       * FRAME = PPC_DL_POS | PPC_DL_COLOR, what particlesDraw reads
+                                                                       * (src/particles_arrays.c:317-320; velocities stay on the device until
+                                                                       * asked for -- particlesRemoveParticle does), EVERY_CALL = PPC_DL_ALL */
 void ppc_request_colors( struct Particles_t *p );                     /* MANUAL policy: the next particlesUpdate also computes colours */
 void ppc_host_modified( struct Particles_t *p );                      /* caller wrote the host arrays directly: re-upload at next call */
 void ppc_download( struct Particles_t *p, unsigned mask );            /* make host arrays current now (blocking) */

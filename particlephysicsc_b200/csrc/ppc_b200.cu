@@ -46,7 +46,8 @@ struct Store {
     bool        lists_unverified = true;   // particles were uploaded since the contact-list length was last checked synchronously
     // policy
     int      sync_policy   = PPC_SYNC_FRAME;
-    unsigned dl_mask       = PPC_DL_ALL;
+    unsigned dl_mask       = 0;   // 0: by policy -- FRAME copies what the draw loop reads (p_x, p_y, colors: 12 B per particle, reference
+                                  // src/particles_arrays.c:317-320), EVERY_CALL (fully transparent) copies the velocities as well
     bool     colour_wanted = false;
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
     int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi, 3 tile Gauss-Seidel
@@ -95,7 +96,8 @@ struct Store {
     WaveItem    *wave_items = nullptr;   // work items of the tile passes (4 lists)
     uint32_t    *wave_n_items = nullptr;
     size_t       wave_items_stride = 0;
-    uint32_t    *h_active = nullptr;   // pinned [5]: particles with contacts, densest tile (per 1024 cells), -, -, longest unstored contact list, as of a recent substep
+    uint32_t    *h_active_dma = nullptr;   // pinned [5]: where the device's report lands behind every resolve (see take_activity_report)
+    uint32_t    *h_active = nullptr;   // host copy [5] of the report as last looked at: particles with contacts, densest tile (per 1024 cells), -, -, longest unstored contact list, as of a recent substep
     // slab mode (multi-GPU decomposition): this store holds the particles of one slab of cell rows
     bool      slab = false;
     SlabRows  slab_rows = {};
@@ -181,7 +183,24 @@ static void free_wave_buffers( Store *st ) {
 // with more contacts than that still resolves correctly -- its list entries are recomputed on demand -- but very slowly, so
 // when a substep reports such lists (heavily overlapping fields: many particles spawned on one spot) the lists are
 // lengthened for the following substeps, as far as 4 GB of list storage go.
+// The wavefront reports its activity (particles in contact, longest unstored list, ...) through five pinned words that a
+// device-to-host copy rewrites behind every resolve while the host, which queues substeps far ahead of the device, looks at them
+// when it queues the next one.  Waiting for the copy would stall the queue, and a report ordered by an event is as old as the
+// host is ahead (measured: the engine choice below then runs a whole batch on the report of the batch's first substep).  So the
+// words are read as they are: each is an independent, naturally aligned 32-bit value written whole by the copy engine, so the
+// host sees an older or a newer report, never a torn one -- and no consumer's RESULT depends on which: both wavefront engines
+// are exact, and list growth only ever acts on the largest length seen.
+static void take_activity_report( Store *st ) {
+    const volatile uint32_t *src = st->h_active_dma;
+    const uint32_t pending_grow = st->h_active[ 4 ];
+    for ( int k = 0; k < 5; k++ )
+        st->h_active[ k ] = src[ k ];
+    if ( pending_grow > st->h_active[ 4 ] )
+        st->h_active[ 4 ] = pending_grow;
+}
+
 static void grow_contact_lists( Store *st ) {
+    take_activity_report( st );
     const uint32_t seen = st->h_active[ 4 ];   // a substep or two old
     if ( !st->wave.deg || seen <= st->wave.maxdeg )
         return;
@@ -446,8 +465,11 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
     PPC_CK( cudaEventCreate( &st->ev0 ) );
     PPC_CK( cudaEventCreate( &st->ev1 ) );
     st->d_word = dev_alloc<uint32_t>( 4 );
-    PPC_CK( cudaHostAlloc( (void **)&st->h_active, 5 * sizeof( uint32_t ), cudaHostAllocDefault ) );
-    st->h_active[ 0 ] = 0xffffffffu;   // unknown yet: assume dense
+    PPC_CK( cudaHostAlloc( (void **)&st->h_active_dma, 5 * sizeof( uint32_t ), cudaHostAllocDefault ) );
+    st->h_active      = (uint32_t *)malloc( 5 * sizeof( uint32_t ) );
+    st->h_active_dma[ 0 ] = st->h_active[ 0 ] = 0xffffffffu;   // unknown yet: assume dense
+    for ( int k = 1; k < 5; k++ )
+        st->h_active_dma[ k ] = 0;
     st->h_active[ 1 ] = st->h_active[ 2 ] = st->h_active[ 3 ] = st->h_active[ 4 ] = 0;
     resize_particle_arrays( st, p->size, 0 );
     g_stores.push_back( st );
@@ -544,6 +566,12 @@ static void absorb_host_changes( Store *st, struct Particles_t *p ) {
                     st->max_radius = p->radius[ k ];
         st->pre_valid = false;
     }
+}
+
+static unsigned auto_download_mask( const Store *st ) {
+    if ( st->dl_mask )
+        return st->dl_mask;
+    return st->sync_policy == PPC_SYNC_EVERY_CALL ? (unsigned)PPC_DL_ALL : (unsigned)( PPC_DL_POS | PPC_DL_COLOR );
 }
 
 // ---- the substep ----------------------------------------------------------------------------------------------
@@ -761,9 +789,10 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
             const uint32_t *cs     = st->cell_start;
             // tile passes pay off when most particles are in contact (deep dependency chains); sparse contact sets
             // are cheaper on the compact queues of the global rounds.  The count is a few substeps old.
+            take_activity_report( st );
             const bool      dense  = *st->h_active == 0xffffffffu || (double)*st->h_active > 0.25 * (double)n;
             const int       passes = ( st->opt_wave_passes < 0 ) ? -st->opt_wave_passes : ( dense ? st->opt_wave_passes : 0 );
-            PPC_CK( cudaMemcpyAsync( st->h_active, st->wave.counters + 8, 5 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+            PPC_CK( cudaMemcpyAsync( st->h_active_dma, st->wave.counters + 8, 5 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
             st->wave_hops = passes > 0 ? 0 : 1;
             if ( passes > 0 ) {   // shared-memory tile passes over four half-shifted tilings
                 if ( !st->wtile_attr_set ) {
@@ -953,7 +982,8 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         cudaFree( st->slab_counts );
         if ( st->h_slab )
             cudaFreeHost( st->h_slab );
-        cudaFreeHost( st->h_active );
+        cudaFreeHost( st->h_active_dma );
+        free( st->h_active );
         cudaFree( st->wave_items );
         cudaFree( st->wave_n_items );
         cudaFree( st->gs_flags );
@@ -996,6 +1026,9 @@ static void grow_arrays( Store *st, struct Particles_t *p ) {
         fprintf( stderr, "particlephysicsc_b200: cannot grow arrays that particlesCreate did not allocate\n" );
         abort();
     }
+    // an asynchronous copy-back may still be writing the host arrays: let it land before they are copied and freed
+    copy_wait( st );
+    PPC_CK( cudaStreamSynchronize( st->stream ) );
     void  **slots[ 7 ] = { (void **)&p->mass, (void **)&p->radius, (void **)&p->colors, (void **)&p->p_x,
                            (void **)&p->p_y,  (void **)&p->v_x,    (void **)&p->v_y };
     for ( int a = 0; a < 7; a++ ) {
@@ -1061,7 +1094,7 @@ extern "C" void particlesUpdate( struct Particles_t *particles, const float time
     st->pending_colour = st->sync_policy != PPC_SYNC_MANUAL || st->colour_wanted;
     st->colour_wanted  = false;
     if ( st->sync_policy == PPC_SYNC_EVERY_CALL )
-        download( st, particles, st->dl_mask );
+        download( st, particles, auto_download_mask( st ) );
 }
 
 extern "C" void particlesCollisionsCheck_Grid( struct Particles_t *particles, const uint16_t window_width, const uint16_t window_height,
@@ -1070,7 +1103,7 @@ extern "C" void particlesCollisionsCheck_Grid( struct Particles_t *particles, co
     absorb_host_changes( st, particles );
     collide_step( st, window_width, window_height, time_step );
     if ( st->sync_policy != PPC_SYNC_MANUAL )
-        download( st, particles, st->dl_mask );
+        download( st, particles, auto_download_mask( st ) );
 }
 
 // =================================================================================================================
@@ -1545,6 +1578,8 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     const size_t n_work = st->h_slab[ 6 ];
     if ( received )
         received[ 0 ] = st->h_slab[ 3 ], received[ 1 ] = st->h_slab[ 7 ];
+    if ( with_header && ( st->h_slab[ 3 ] > n_lo || st->h_slab[ 7 ] > n_hi ) )
+        return -3;   // a neighbour had more records than the agreed message size: what arrived is incomplete
     st->own_first  = st->h_slab[ 4 ];
     st->n_own      = st->h_slab[ 5 ] - st->h_slab[ 4 ];
     st->n          = n_work;

@@ -87,7 +87,7 @@ constexpr uint32_t GS_NONE     = 0xffffu;
 constexpr uint32_t GS_LAST_STRIP = 0x80000000u;
 constexpr uint32_t GS_HDR_UNITS = ( 2 * ( GS_R + 2 ) + 1 + 3 ) / 4;   // 21 words
 constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u, GS_ERR_CHUNK = 8u;
-static_assert( GS_CAP <= 2048, "contact entries and pair records hold a particle in 11 bits" );
+static_assert( GS_CAP <= 1024, "T.ord holds a staged index in 10 bits" );
 static_assert( GS_BINS * 4 <= GS_POOL * 4, "the bin counters alias the contact pool" );
 static_assert( GS_BINS % GS_THREADS == 0, "bins per thread" );
 
@@ -101,6 +101,10 @@ struct GsSmem {
     uint16_t mc[ GS_CAP + ( GS_R + 2 ) * 2 * GS_MC_PAD ];   // mass byte | cell column byte << 8, row by row from 16-byte boundaries
     uint16_t head[ GS_CAP ];        // first contact entry of a centre particle
     uint8_t  lvl[ GS_CAP ];         // level of the latest pair of every staged particle
+    uint16_t ord[ GS_CAP ];         // centre particle t: staged index [9:0] | staged row << 10
+    uint16_t perm2[ GS_CAP ];       // centre particle t: rank inside its class of contact count
+    uint8_t  kk[ GS_CAP ];          // centre particle t: number of contacts (saturating)
+    uint32_t kcnt[ 4 ];             // centre particles with contacts, per class of contact count
     uint16_t cstart[ ( GS_R + 2 ) * ( GS_MAXC + 1 ) ];   // first staged index of staged cell (row, column); [row][ncol] = end of the row
     float    inv_lut[ 256 ];        // 1 / (float)k, the inverse masses of :146-147
     uint32_t run_g0[ GS_R + 2 ], run_s0[ GS_R + 3 ], cen_g0[ GS_R + 1 ], cen_s0[ GS_R + 1 ];
@@ -111,6 +115,8 @@ struct GsSmem {
     uint32_t rmax_bits, pool_n, err, chunk_base, n_buckets, phase_mask;
     unsigned long long mbar;
 };
+
+static_assert( ( sizeof( GsSmem ) + 1024 ) * PPC_GS_MINBLOCKS <= 232448, "PPC_GS_MINBLOCKS CTAs of k_gs_pairs must fit the 227 KB of an SM" );
 
 struct GsLaunch {
     int wc;          // tile width in cells
@@ -382,10 +388,12 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
     __syncthreads();   // the counters are dead from here on: their memory becomes the contact pool
     if ( threadIdx.x == 0 )
         T.pool_n = 0u;
+    if ( threadIdx.x < 4 )
+        T.kcnt[ threadIdx.x ] = 0u;
     __syncthreads();
     const float R = __uint_as_float( T.rmax_bits );
 
-    // ---- one thread per centre particle: candidates, contact list, position pushes ----
+    // ---- one thread per centre particle: candidates -> contact list (unordered) ----
     for ( uint32_t t = threadIdx.x; t < centre; t += GS_THREADS ) {
         int j = 1;
         while ( j < GS_R && t >= T.cen_s0[ j ] )
@@ -394,15 +402,13 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
         const uint32_t self = T.run_s0[ j ] + ( gk - T.run_g0[ j ] );          // staged index
         const float4   me4  = T.a[ self ];
         const float    x = me4.x, y = me4.y, r = me4.z;
-        const uint32_t gid   = __float_as_uint( me4.w );
-        const uint32_t mcw   = GS_MC( self, j );
-        const int      mycol = (int)( mcw >> 8 );
+        const int      mycol = (int)( GS_MC( self, j ) >> 8 );
         const int      gy    = cy0 - 1 + j;
         const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
         const int      b_lo  = gs_fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = gs_fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
 
-        uint32_t head = GS_NONE, tail = GS_NONE;
+        uint32_t head = GS_NONE, tail = GS_NONE, k = 0;
 #pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
             const int ry = gy - 1 + d;
@@ -440,13 +446,52 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
                         else
                             T.pool_next[ tail ] = (uint16_t)at;
                         tail = at;
+                        k++;
                     } else
                         T.err = GS_ERR_POOL;
                 }
             }
         }
+        // A particle without contacts is done: its position stands as the gather wrote it.  The others are handed out again below,
+        // grouped by their number of contacts, so that the lanes of a warp walk lists of similar length.
+        T.ord[ t ] = (uint16_t)( self | ( (uint32_t)j << 10 ) );
+        T.kk[ t ]  = (uint8_t)( k < 255u ? k : 255u );
+        if ( k ) {
+            T.head[ self ] = (uint16_t)head;
+            const uint32_t cls   = k <= 2u ? 3u : ( k <= 4u ? 2u : ( k <= 7u ? 1u : 0u ) );   // long lists first
+            const unsigned peers = __match_any_sync( __activemask(), cls );
+            const unsigned lane  = threadIdx.x & 31u, leader = (unsigned)( __ffs( peers ) - 1 );
+            uint32_t       base  = 0;
+            if ( lane == leader )
+                base = atomicAdd( &T.kcnt[ cls ], (uint32_t)__popc( peers ) );
+            base = __shfl_sync( peers, base, leader );
+            T.perm2[ t ] = (uint16_t)( base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) ) );   // rank inside its class
+        }
+    }
+    __syncthreads();   // every list is complete; fend / perm are dead
+    uint16_t *order = T.fend;   // centre particles with contacts, grouped by class
+    const uint32_t n0 = T.kcnt[ 0 ], n1 = n0 + T.kcnt[ 1 ], n2 = n1 + T.kcnt[ 2 ], with_contacts = n2 + T.kcnt[ 3 ];
+    for ( uint32_t t = threadIdx.x; t < centre; t += GS_THREADS ) {
+        const uint32_t k = T.kk[ t ];
+        if ( k )
+            order[ ( k <= 2u ? n2 : ( k <= 4u ? n1 : ( k <= 7u ? n0 : 0u ) ) ) + T.perm2[ t ] ] = T.ord[ t ];
+    }
+    __syncthreads();
+
+    // ---- one thread per centre particle with contacts: list into the reference's order, position pushes, who owns each pair ----
+    for ( uint32_t u = threadIdx.x; u < with_contacts; u += GS_THREADS ) {
+        const uint32_t ov   = order[ u ];
+        const uint32_t self = ov & 0x3ffu;
+        const int      j    = (int)( ov >> 10 );
+        const uint32_t gk   = T.run_g0[ j ] + ( self - T.run_s0[ j ] );
+        const float4   me4  = T.a[ self ];
+        const float    x = me4.x, y = me4.y, r = me4.z;
+        const uint32_t gid   = __float_as_uint( me4.w );
+        const uint32_t mcw   = GS_MC( self, j );
+        const int      mycol = (int)( mcw >> 8 );
+        const uint32_t head  = T.head[ self ];
         float X = x, Y = y;
-        if ( head != GS_NONE ) {
+        {
             // The list is put into the order the reference's pair list touches this particle -- pairs (i, me), i < me, by
             // ascending i; then pairs (me, j) by scan cell (dy outer, dx inner), descending index inside a cell (:311-383) --
             // by selection, swapping entry values along the links; each entry is consumed as soon as it is in place.
@@ -505,7 +550,6 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
                 }
                 T.pool_val[ e ] = (uint16_t)( v | ( anchored ? 0x8000u : 0u ) );
             }
-            T.head[ self ] = (uint16_t)head;
         }
         *reinterpret_cast<float2 *>( pv_out + gk ) = make_float2( X, Y );   // the velocity half stays as the gather left it
     }

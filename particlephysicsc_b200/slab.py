@@ -89,6 +89,10 @@ def gs_options(n_total: int, W: int, H: int, max_radius: float) -> dict:
     return {"resolve": 3, "gs_wc": int(api.load_library().ppc_gs_auto_tile_width(float(n_total), float(cols) * float(rows)))}
 
 
+class MessageOverflow(RuntimeError):
+    """A fixed-size halo message did not hold the records of this substep (raised on the sender AND on its receiver)."""
+
+
 class HaloTooShallow(RuntimeError):
     """The dependency depth of a substep exceeded what the halo guarantees; owned velocities may be inexact."""
 
@@ -168,6 +172,8 @@ class DeviceSlab:
         if n == -4:
             raise HaloTooShallow(f'"resolve"=3 needs "gs_wc" set and at least {self.p.lib.ppc_slab_gs_halo(*self.geometry[3], 1 << 30)} ghost rows here; '
                                  f"this slab has {self.halo}")
+        if n == -3:
+            raise MessageOverflow("a neighbour's halo message outgrew the agreed size (its header counts more records than arrived)")
         if n < 0:
             raise RuntimeError(f"ppc_slab_finish failed ({n})")
         self.received = (int(got[0]), int(got[1]))
@@ -346,15 +352,19 @@ def slab_step(rank, transport: DistTransport, dt: float, colour: bool = False, t
         if not hasattr(transport, "cap_send"):
             transport.negotiate(n_lo, n_hi)
         cs, cr = transport.cap_send, transport.cap_recv
-        if n_lo > cs[0] or n_hi > cs[1]:
-            raise RuntimeError(f"halo message grew from a capacity of {cs} to {(n_lo, n_hi)} records within one substep")
-        s_lo, s_hi = rank.buffer("send_lo", cs[0] + 1), rank.buffer("send_hi", cs[1] + 1)
+        # A message that outgrew the agreed size is still sent, cut to that size: its header carries the true count, so the
+        # receiver sees the overflow too and both ends raise in the same substep (an error on one rank only would leave the
+        # neighbours waiting in their receive for ever).
+        overflow = n_lo > cs[0] or n_hi > cs[1]
+        s_lo, s_hi = rank.buffer("send_lo", max(cs[0], n_lo) + 1), rank.buffer("send_hi", max(cs[1], n_hi) + 1)
         rank.pack(s_lo, s_hi, header=True)
         t = lap("pack", t)
         b_lo, b_hi = rank.buffer("recv_lo", cr[0] + 1), rank.buffer("recv_hi", cr[1] + 1)
         transport.exchange(s_lo[:cs[0] + 1 if cs[0] else 0], s_hi[:cs[1] + 1 if cs[1] else 0], b_lo[:cr[0] + 1 if cr[0] else 0],
                            b_hi[:cr[1] + 1 if cr[1] else 0])
         t = lap("exchange records", t)
+        if overflow:
+            raise MessageOverflow(f"halo message grew from a capacity of {cs} to {(n_lo, n_hi)} records within one substep")
         n = rank.finish(dt, b_lo, cr[0], b_hi, cr[1], header=True)
         transport.advance((n_lo, n_hi), rank.received)
         lap("finish (grid, narrow phase, resolve)", t)

@@ -114,7 +114,9 @@ class ModelSlab:
         for buf, n in ((buf_lo, n_lo), (buf_hi, n_hi)):
             b = buf.numpy()
             if header and n:   # n is the capacity; the header says how many records are real
-                n = int(np.ascontiguousarray(b[0, :4]).view("<u4")[0])
+                cap, n = n, int(np.ascontiguousarray(b[0, :4]).view("<u4")[0])
+                if n > cap:
+                    raise slab.MessageOverflow("a neighbour's halo message outgrew the agreed size")
                 b = b[1:]
             got.append(n)
             if n:

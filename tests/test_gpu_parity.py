@@ -308,6 +308,7 @@ def test_store_add_remove_semantics():
             p.CollisionsCheck_Grid(W, H, dt)
         snap, length = g[f"snap_{f}"], int(g["lengths"][f])
         assert p.length == length
+        p.download(api.PPC_DL_VEL)   # the frame copy-back moves what the draw loop reads (p_x, p_y, colors); velocities on request
         for row, a in enumerate(("p_x", "p_y", "v_x", "v_y", "mass", "radius")):
             assert_bits_equal(p.array(a, full=True)[: length + 1], snap[row], f"frame {f} {a}")
     assert p.size == int(g["size"])
@@ -337,6 +338,7 @@ def test_debug_scene_like_main_c(reference):
         p.CollisionsCheck_Grid(W, H, dt)
         if f % 20 == 19 or f == len(frames) - 1:
             assert p.length == rp.length and p.size == rp.size
+            p.download(api.PPC_DL_VEL)   # (see above)
             for a in ("p_x", "p_y", "v_x", "v_y", "mass", "radius"):
                 want = np.ctypeslib.as_array(getattr(rp, a), shape=(rp.size,))[: rp.length + 1]
                 assert_bits_equal(p.array(a, full=True)[: p.length + 1], want, f"frame {f} {a}")
@@ -529,6 +531,59 @@ def test_sixteen_million_particles_properties():
     g_kick = 3 * 9.81 * DT * np.sum(st.mass.astype(np.float64))
     assert np.all(np.abs(mom - mom0 - g_kick) < 0.02 * abs(g_kick) + 1e-3 * np.abs(mom0).max())
     p.Free()
+
+
+def test_sixteen_million_pile_one_substep_against_the_compiled_reference(oracle):
+    """BASELINE configs[2] at its stated size: the 16M polydisperse pile as the benchmark runs it (settled on the device), then
+    ONE substep on the compiled, unmodified reference (about 20 s of one host core) and on the device.
+      * default resolve: keys, sorted order, cell-start table, positions and velocities bit for bit;
+      * "resolve"=3 from the same state: positions bit for bit against the reference, the pair set the hot kernel resolved equal
+        to the reference's candidate-pair list, velocities bit for bit against the CPU model of its pair order."""
+    from oracle import oracle as om
+    if not om.reference_available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    n = 1 << 24
+    sc = scenes.polydisperse_pile(n, seed=0x5EED0003)
+    p = gpu_store(state_from_scene(sc))
+    p.run_substeps(sc.W, sc.H, DT, 32)          # the relaxed state is what gets benchmarked
+    start = gpu_state(p)
+    ref = start.copy()
+    R = om.Reference()
+    R.update(ref, DT)
+    pairs = R.collisions_check_grid(ref, sc.W, sc.H, DT, capture=True)
+    pre = start.copy()
+    oracle.update(pre, DT, False)
+    oracle.walls(pre, sc.W, sc.H)
+    grid = oracle.grid_build(pre, sc.W, sc.H)
+    # -- default (sequential-equivalent) resolve --
+    p.Update(DT)
+    p.CollisionsCheck_Grid(sc.W, sc.H, DT)
+    g = p.debug_grid()
+    assert np.array_equal(g["keys"], grid["keys"]), "cell keys"
+    assert np.array_equal(g["order"], grid["order"]), "sorted order"
+    assert np.array_equal(g["cell_start"], grid["cell_start"]), "cell-start table"
+    assert_state_bits(gpu_state(p), ref, "16M pile, one substep, default resolve")
+    p.Free()
+    print(f"\n16M pile: {len(pairs)} candidate pairs in the reference's list; default resolve bit-identical")
+    # -- tile Gauss-Seidel from the same state --
+    q = gpu_store(start)
+    q.set_option("resolve", 3)
+    q.set_option("gs_dump", 1)
+    q.Update(DT)
+    q.CollisionsCheck_Grid(sc.W, sc.H, DT)
+    assert q.gs_fallbacks() == 0
+    got = gpu_state(q)
+    assert_bits_equal(got.px, ref.px, "16M pile resolve=3: p_x vs the reference")
+    assert_bits_equal(got.py, ref.py, "16M pile resolve=3: p_y vs the reference")
+    hot = q.debug_hot_pairs()
+    want = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+    assert np.array_equal(hot, want), "pairs the hot kernel resolved vs the reference's pair list"
+    par = q.gs_params()
+    q.Free()
+    oracle.set_tilegs(par["wc"], par["tile_r"], par["strip_limit"])
+    model = start.copy()
+    oracle.substep(model, sc.W, sc.H, DT, 3, False)
+    assert_state_bits(got, model, "16M pile resolve=3 vs the CPU model of its pair order")
 
 
 def test_snapshot_resumes_bit_exactly(oracle, tmp_path):

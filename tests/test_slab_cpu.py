@@ -180,3 +180,43 @@ def test_two_ranks_over_gloo_equal_whole_field(oracle, fixed):
     assert (count == 1).all()
     for k in have:
         assert_bits_equal(have[k], getattr(ref, k), f"gloo world 2 {k}")
+
+
+def _overflow_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from oracle.oracle import Oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    sc = scenes.jittered_lattice(12000, 2.0, 0.30, seed=304, vmax=600.0)
+    me = model_slabs(Oracle(), sc, world, 12)[rank]
+    me.fixed_size_messages = True
+    tr = slab.DistTransport(dist, torch.device("cpu"))
+    slab.slab_step(me, tr, DT)            # negotiates the message sizes
+    if rank == 0:                         # rank 0's next message is "too large" for what was agreed ...
+        tr.cap_send[1] = 8
+    else:                                 # ... and rank 1 expects that agreed size
+        tr.cap_recv[0] = 8
+    try:
+        slab.slab_step(me, tr, DT)
+        out.put((rank, "no error"))
+    except slab.MessageOverflow as e:
+        out.put((rank, "MessageOverflow"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_an_outgrown_fixed_size_message_raises_on_both_ranks_instead_of_hanging():
+    """a rank whose halo message outgrew the agreed size used to raise before posting its send, leaving the
+    neighbour in its receive for ever.  The cut message is now sent with the true count in its header; both ends raise."""
+    ctx = mp.get_context("spawn")
+    out, port = ctx.Queue(), _free_port()
+    procs = [ctx.Process(target=_overflow_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(out.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: "MessageOverflow", 1: "MessageOverflow"}
