@@ -647,8 +647,11 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
 // "resolve"=3: narrow phase, position pushes and the tile Gauss-Seidel velocity resolve in one kernel (ppc_gs.cuh), one launch
 // per tile colour.  Reads the staged records the gather wrote, writes the final state into the sorted set's pv array.
 static int gs_auto_width( const double particles, const double cells ) {
+    // as wide as keeps a tile of average density, with its one-cell halo, just inside the kernel's staging capacity (measured: filling
+    // the shared memory beats one particle per thread -- uniform16m 1.71 -> 1.44 ms, pile16m 4.2 -> 4.0 ms); denser regions are cut
+    // into strips by the kernel itself
     const double per_cell = cells > 0 ? particles / cells : 0.0;
-    return (int)( (double)GS_TARGET / ( GS_R * ( per_cell > 0.05 ? per_cell : 0.05 ) ) );
+    return (int)( (double)GS_STAGE_TARGET / ( ( GS_R + 2 ) * ( per_cell > 0.05 ? per_cell : 0.05 ) ) ) - 2;
 }
 
 static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {

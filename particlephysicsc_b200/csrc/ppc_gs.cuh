@@ -57,7 +57,10 @@ namespace ppc {
 #define PPC_GS_POOL 6144   // contact entries per sub-tile (a centre-centre pair takes two)
 #endif
 #ifndef PPC_GS_TARGET
-#define PPC_GS_TARGET 520  // centre particles per tile the host aims for
+#define PPC_GS_TARGET 960  // staged particles (tile + halo) per tile of average density the host aims for
+#endif
+#ifndef PPC_GS_FLAT
+#define PPC_GS_FLAT 0      // 1: the three staged rows a particle scans are one loop (measured 10-20 % SLOWER: the state machine costs more than the lanes it keeps together); 0: one loop per row
 #endif
 #ifndef PPC_GS_TMA
 #define PPC_GS_TMA 1       // 0: stage with ordinary loads (debugging aid)
@@ -74,7 +77,7 @@ constexpr int      GSB_SLICE   = PPC_GSB_SLICE;
 constexpr int      GS_R        = TILE_R;              // centre rows per tile
 constexpr int      GS_CAP      = PPC_GS_CAP;
 constexpr int      GS_POOL     = PPC_GS_POOL;
-constexpr int      GS_TARGET   = PPC_GS_TARGET;
+constexpr int      GS_STAGE_TARGET = PPC_GS_TARGET;
 constexpr int      GS_F        = 4;                   // fine bins per cell
 constexpr int      GS_MAXC     = 64;                  // staged columns (centre + halo)
 constexpr int      GS_NB       = GS_MAXC * GS_F;      // fine bins per staged row
@@ -226,65 +229,81 @@ __device__ __forceinline__ void gs_run_sums( uint32_t *run_s0, uint32_t *cen_s0 
 // ====================================================================================================================
 // k_gs_pairs: one sub-tile = centre columns [cx0, cx1) of the tile [tcx0, tcx1), centre rows [cy0, cy0 + GS_R) (clipped).
 // ====================================================================================================================
-__device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__restrict__ rec_a, const uint16_t *__restrict__ mcol, float4 *__restrict__ pv_out,
+// Returns true when the sub-tile holds more than stage_limit staged particles (then nothing has been done).
+__device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__restrict__ rec_a, const uint16_t *__restrict__ mcol, float4 *__restrict__ pv_out,
                                                   const uint32_t *__restrict__ cell_start, const GridDims &G, const float dt, const int cx0, const int cx1,
                                                   const int tcx0, const int tcx1, const int cy0, const int tx, const int tyg, const int my_colour,
                                                   uint32_t &phase_parity, uint2 *__restrict__ desc_slot, const uint32_t last_flag, const GsPairs PR,
-                                                  uint32_t *__restrict__ err_flags, const GsDump D ) {
+                                                  uint32_t *__restrict__ err_flags, const GsDump D, const uint32_t stage_limit ) {
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
     const int ncol = c1 - c0, nb = ncol * GS_F;
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>( T.pool_val );       // bin counters / cursors while binning (pool unused then)
     __syncthreads();                                                    // shared memory may still be in use by the previous strip
 
-    gs_run_lengths( T.run_g0, T.run_s0, T.cen_g0, T.cen_s0, cell_start, G, c0, c1, cx0, cx1, cy0 );
-    for ( int f = threadIdx.x; f < GS_BINS; f += GS_THREADS )
-        cnt32[ f ] = 0;
-    __syncthreads();
-    if ( threadIdx.x == 0 ) {
-        // the 16-bit mass/column words of a row are copied from the 16-byte boundary at or below its first slot
-        uint32_t mc_at = 0;
-        for ( int j = 0; j < GS_R + 2; j++ ) {
-            const uint32_t lead = T.run_g0[ j ] & ( GS_MC_PAD - 1 );
-            T.mc_s0[ j ]        = mc_at + lead;
-            mc_at += ( lead + T.run_s0[ j ] + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 );   // run_s0 still holds the lengths
+    // Run table and staging by warp 0, one lane per staged row: row j = 0 .. GS_R+1 is grid row cy0 - 1 + j, columns [c0, c1); centre =
+    // columns [cx0, cx1) of rows 1 .. GS_R.  Lengths from the cell-start table, running sums by warp scans, and every lane posts the
+    // two bulk copies of its own row (records; 16-bit mass/column words from the 16-byte boundary at or below the row's first slot).
+    if ( threadIdx.x < 32 ) {
+        const int      j  = (int)threadIdx.x, gy = cy0 - 1 + j;
+        const bool     row = j < GS_R + 2 && gy >= 0 && gy < G.rows, mid = row && j >= 1 && j <= GS_R;
+        uint32_t       g0 = 0, g1 = 0, m0 = 0, m1 = 0;
+        if ( row ) {
+            const uint32_t *cs = cell_start + (size_t)gy * G.cols;
+            g0 = cs[ c0 ], g1 = cs[ c1 ];
+            if ( mid )
+                m0 = cs[ cx0 ], m1 = cs[ cx1 ];
         }
-        gs_run_sums( T.run_s0, T.cen_s0 );
-        T.rmax_bits = 0u;
-        T.err       = 0u;
-#if PPC_GS_TMA
-        const uint32_t run = T.run_s0[ GS_R + 2 ], cen = T.cen_s0[ GS_R ];
-        if ( run != 0 && cen != 0 && run <= (uint32_t)GS_CAP ) {   // stage the runs: two bulk copies per row, one barrier phase
-            fence_proxy_async();   // the previous strip read this shared memory with ordinary loads
-            uint32_t bytes = 0;
-            for ( int j = 0; j < GS_R + 2; j++ ) {
-                const uint32_t len = T.run_s0[ j + 1 ] - T.run_s0[ j ];
-                if ( len )
-                    bytes += len * 16u + ( ( ( ( T.run_g0[ j ] & ( GS_MC_PAD - 1 ) ) + len + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 ) ) * 2u );
+        const uint32_t len = g1 - g0, clen = m1 - m0, lead = g0 & ( GS_MC_PAD - 1 );
+        const uint32_t mclen = len ? ( ( lead + len + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 ) ) : 0u;
+        uint32_t s_inc = len, c_inc = clen, m_inc = mclen;
+#pragma unroll
+        for ( int d = 1; d < 16; d <<= 1 ) {
+            const uint32_t a = __shfl_up_sync( 0xffffffffu, s_inc, d ), b = __shfl_up_sync( 0xffffffffu, c_inc, d ), c = __shfl_up_sync( 0xffffffffu, m_inc, d );
+            if ( j >= d )
+                s_inc += a, c_inc += b, m_inc += c;
+        }
+        const uint32_t run = __shfl_sync( 0xffffffffu, s_inc, GS_R + 1 ), cen = __shfl_sync( 0xffffffffu, c_inc, GS_R + 1 );
+        const uint32_t mcb = __shfl_sync( 0xffffffffu, m_inc, GS_R + 1 );
+        if ( j < GS_R + 2 ) {
+            T.run_g0[ j ] = g0;
+            T.run_s0[ j ] = s_inc - len;
+            T.mc_s0[ j ]  = m_inc - mclen + lead;
+            if ( j >= 1 && j <= GS_R ) {
+                T.cen_g0[ j - 1 ] = m0;
+                T.cen_s0[ j - 1 ] = c_inc - clen;
             }
-            mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar ), bytes );
-            for ( int j = 0; j < GS_R + 2; j++ ) {
-                const uint32_t len = T.run_s0[ j + 1 ] - T.run_s0[ j ];
-                if ( len ) {
-                    const uint32_t g0 = T.run_g0[ j ], lead = g0 & ( GS_MC_PAD - 1 );
-                    tma_load_1d( &T.a[ T.run_s0[ j ] ], rec_a + g0, len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
-                    tma_load_1d( &T.mc[ T.mc_s0[ j ] - lead ], mcol + ( g0 - lead ), ( ( lead + len + GS_MC_PAD - 1 ) & ~(uint32_t)( GS_MC_PAD - 1 ) ) * 2u,
-                                 reinterpret_cast<uint64_t *>( &T.mbar ) );
-                }
+        }
+        if ( j == 0 ) {
+            T.run_s0[ GS_R + 2 ] = run;
+            T.cen_s0[ GS_R ]     = cen;
+            T.rmax_bits = 0u;
+            T.err       = 0u;
+            T.pool_n    = 0u;
+            T.phase_mask = 0u;
+        }
+        if ( j < 4 )
+            T.kcnt[ j ] = 0u;
+#if PPC_GS_TMA
+        if ( run != 0 && cen != 0 && run <= stage_limit ) {   // stage the runs: one barrier phase
+            fence_proxy_async();   // the previous strip read this shared memory with ordinary loads
+            if ( j == 0 )
+                mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar ), run * 16u + mcb * 2u );
+            __syncwarp();
+            if ( len ) {
+                tma_load_1d( &T.a[ s_inc - len ], rec_a + g0, len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
+                tma_load_1d( &T.mc[ m_inc - mclen ], mcol + ( g0 - lead ), mclen * 2u, reinterpret_cast<uint64_t *>( &T.mbar ) );
             }
         }
 #endif
     }
+    for ( int f = threadIdx.x; f < GS_BINS; f += GS_THREADS )
+        cnt32[ f ] = 0;
     __syncthreads();
     const uint32_t staged = T.run_s0[ GS_R + 2 ], centre = T.cen_s0[ GS_R ];
     if ( staged == 0 || centre == 0 )
-        return;   // (the kernel has already marked this sub-tile as owning no pair)
-    if ( staged > (uint32_t)GS_CAP ) {   // a one-column strip that still does not fit: this mode has no generic path
-        if ( threadIdx.x == 0 ) {
-            atomicOr( err_flags, GS_ERR_CAP );
-            *desc_slot = make_uint2( 0u, last_flag );
-        }
-        return;
-    }
+        return false;   // (the kernel has already marked this sub-tile as owning no pair)
+    if ( staged > stage_limit )
+        return true;    // nothing was staged: the caller cuts the tile into strips (or reports a strip that cannot be cut further)
 
     // ---- while the copies are in flight: staged cell table, inverse-mass table, list heads ----
     for ( int e = threadIdx.x; e < ( GS_R + 2 ) * ( ncol + 1 ); e += GS_THREADS ) {
@@ -300,8 +319,6 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
         T.head[ t ] = (uint16_t)GS_NONE;
         T.lvl[ t ]  = 0;
     }
-    if ( threadIdx.x == 0 )
-        T.phase_mask = 0u;
     for ( int b = threadIdx.x; b < GS_BUCKETS; b += GS_THREADS )
         T.bcount[ b ] = 0u;
 #if PPC_GS_TMA
@@ -386,11 +403,6 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
     for ( int f = threadIdx.x; f < GS_BINS; f += GS_THREADS )
         T.fend[ f ] = (uint16_t)cnt32[ f ];
     __syncthreads();   // the counters are dead from here on: their memory becomes the contact pool
-    if ( threadIdx.x == 0 )
-        T.pool_n = 0u;
-    if ( threadIdx.x < 4 )
-        T.kcnt[ threadIdx.x ] = 0u;
-    __syncthreads();
     const float R = __uint_as_float( T.rmax_bits );
 
     // ---- one thread per centre particle: candidates -> contact list (unordered) ----
@@ -409,6 +421,64 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
         const float    top   = __fmul_rn( (float)( gy + G.row0 ), G.cell_size ), bot = __fmul_rn( (float)( gy + G.row0 + 1 ), G.cell_size );
 
         uint32_t head = GS_NONE, tail = GS_NONE, k = 0;
+#if PPC_GS_FLAT
+        // The three staged rows a particle scans are ONE loop (a lane that has finished a row moves on to its next one while the
+        // others are still scanning theirs: the lanes of a warp stay together for the sum of their trip counts, not row by row).
+        int      d = -1, jr = 0;
+        uint32_t q = 0, qe = 0;
+#pragma unroll 1
+        for ( ;; ) {
+            if ( q >= qe ) {   // next row with candidates
+                bool more = false;
+                while ( ++d < 3 ) {
+                    const int ry = gy - 1 + d;
+                    if ( ry < 0 || ry >= G.rows )
+                        continue;
+                    if ( d == 0 && __fsub_rn( y, reach ) >= top )   // nothing in the row above can be within reach
+                        continue;
+                    if ( d == 2 && __fadd_rn( y, reach ) < bot )
+                        continue;
+                    jr = j - 1 + d;   // staged row scanned
+                    const int f_lo = jr * GS_NB + b_lo, f_hi = jr * GS_NB + b_hi;
+                    q  = f_lo > 0 ? T.fend[ f_lo - 1 ] : 0u;
+                    qe = T.fend[ f_hi ];
+                    if ( q < qe ) {
+                        more = true;
+                        break;
+                    }
+                }
+                if ( !more )
+                    break;
+            }
+            const uint32_t s  = T.perm[ q++ ];
+            const float4   c  = T.a[ s ];
+            const float    rs = __fadd_rn( r, c.z );
+            const float    dx = __fsub_rn( x, c.x );
+            if ( fabsf( dx ) > rs )   // :353
+                continue;
+            const float dy = __fsub_rn( y, c.y );
+            if ( fabsf( dy ) > rs )   // :356
+                continue;
+            const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
+            if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
+                const int dc = (int)(int8_t)( ( (uint32_t)GS_MC( s, jr ) >> 8 ) - (uint32_t)mycol );
+                if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
+                    continue;
+                const uint32_t at = atomicAdd( &T.pool_n, 1u );
+                if ( at < (uint32_t)GS_POOL ) {
+                    T.pool_val[ at ]  = (uint16_t)( s | ( (uint32_t)d << 11 ) | ( (uint32_t)( dc + 1 ) << 13 ) );
+                    T.pool_next[ at ] = (uint16_t)GS_NONE;
+                    if ( tail == GS_NONE )
+                        head = at;
+                    else
+                        T.pool_next[ tail ] = (uint16_t)at;
+                    tail = at;
+                    k++;
+                } else
+                    T.err = GS_ERR_POOL;
+            }
+        }
+#else
 #pragma unroll 1
         for ( int d = 0; d < 3; d++ ) {
             const int ry = gy - 1 + d;
@@ -452,6 +522,7 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
                 }
             }
         }
+#endif
         // A particle without contacts is done: its position stands as the gather wrote it.  The others are handed out again below,
         // grouped by their number of contacts, so that the lanes of a warp walk lists of similar length.
         T.ord[ t ] = (uint16_t)( self | ( (uint32_t)j << 10 ) );
@@ -559,13 +630,13 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
             atomicOr( err_flags, T.err );
             *desc_slot = make_uint2( 0u, last_flag );
         }
-        return;
+        return false;
     }
 
     if ( T.pool_n == 0u ) {   // no contact at all in this sub-tile
         if ( threadIdx.x == 0 )
             *desc_slot = make_uint2( 0u, last_flag );
-        return;
+        return false;
     }
 
     // ---- the pairs this sub-tile owns, as records sorted by LEVEL ----
@@ -654,7 +725,7 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
             atomicOr( err_flags, T.err );
             *desc_slot = make_uint2( 0u, last_flag );
         }
-        return;
+        return false;
     }
     // (b) entry numbers of this cell, grouped by direction code; the entry remembers its anchor where its link was
     {
@@ -710,7 +781,7 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
             atomicOr( err_flags, T.err );
             *desc_slot = make_uint2( 0u, last_flag );
         }
-        return;
+        return false;
     }
     // exclusive scan of the level counts and of the "level in use" flags over the CTA; the chunk; the table of level ends
     {
@@ -781,7 +852,7 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
     }
     __syncthreads();
     if ( T.chunk_base == 0xffffffffu )
-        return;   // no pair, or no room
+        return false;   // no pair, or no room
     {
         uint4         *rec = PR.chunks + T.chunk_base + GS_HDR_UNITS + ( T.n_buckets * 2u + 15u ) / 16u;
         const uint32_t n_entries = min( T.pool_n, (uint32_t)GS_POOL );
@@ -806,6 +877,7 @@ __device__ __forceinline__ void gs_pairs_subtile( GsSmem &T, const float4 *__res
         }
     }
 #undef GS_MC
+    return false;
 }
 
 __global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_gs_pairs( const float4 *__restrict__ rec_a, const uint16_t *__restrict__ mcol,
@@ -820,24 +892,30 @@ __global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_gs_pairs( co
     const int cy0 = tyg * GS_R - G.row0;                                   // may be negative for a slab window's first tile row
     if ( threadIdx.x == 0 )
         mbar_init( reinterpret_cast<uint64_t *>( &T.mbar ), 1u );
+    uint2         *desc  = PR.desc + (size_t)blockIdx.x * GS_MAXSTRIPS;
+    const int      my_colour = ( tx & 1 ) | ( ( tyg & 1 ) << 1 );
+    uint32_t       parity = 0;
+    // Most tiles fit as they are: one sub-tile, and its run table tells so without looking at the columns.
+    if ( threadIdx.x == 0 )
+        desc[ 0 ] = make_uint2( 0u, GS_LAST_STRIP );   // until the sub-tile turns out to own pairs (same thread, program order)
+    if ( !gs_pairs_subtile( T, rec_a, mcol, pv_out, cell_start, G, dt, cx0, cx1, cx0, cx1, cy0, tx, tyg, my_colour, parity, desc, GS_LAST_STRIP, PR, err_flags,
+                            D, (uint32_t)L.strip_limit ) )
+        return;
+    // A tile whose staged particles exceed the limit is cut into column strips, which this CTA runs one after the other.
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );
+    __syncthreads();
     gs_column_sums( T.colp, cell_start, G, c0, c1, cy0, GS_THREADS );
     const uint32_t total = T.colp[ c1 - c0 ] - T.colp[ 0 ];
-    uint2         *desc  = PR.desc + (size_t)blockIdx.x * GS_MAXSTRIPS;
-    if ( total == 0 ) {
-        if ( threadIdx.x == 0 )
-            desc[ 0 ] = make_uint2( 0u, GS_LAST_STRIP );
-        return;
-    }
-    uint32_t parity = 0;
-    int      strip  = 0;
+    int            strip = 0;
     for ( int sx = cx0; sx < cx1; strip++ ) {
         const int      ex   = gs_strip_end( T.colp, total, sx, cx1, c0, c1, (uint32_t)L.strip_limit );
         const uint32_t last = ex >= cx1 ? GS_LAST_STRIP : 0u;
         if ( threadIdx.x == 0 )
-            desc[ strip ] = make_uint2( 0u, last );   // until the sub-tile turns out to own pairs (same thread, program order)
-        gs_pairs_subtile( T, rec_a, mcol, pv_out, cell_start, G, dt, sx, ex, cx0, cx1, cy0, tx, tyg, ( tx & 1 ) | ( ( tyg & 1 ) << 1 ), parity,
-                          desc + strip, last, PR, err_flags, D );
+            desc[ strip ] = make_uint2( 0u, last );
+        if ( gs_pairs_subtile( T, rec_a, mcol, pv_out, cell_start, G, dt, sx, ex, cx0, cx1, cy0, tx, tyg, my_colour, parity, desc + strip, last, PR, err_flags, D,
+                               (uint32_t)GS_CAP ) &&
+             threadIdx.x == 0 )
+            atomicOr( err_flags, GS_ERR_CAP );   // a one-column strip that still does not fit: this mode has no generic path
         sx = ex;
     }
 }
