@@ -126,6 +126,9 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *   "gs_wc"    "resolve"=3: tile width in cells (0 = from the particle density, default).  Part of the pair order: the
  *              ranks of a multi-GPU field must all use the same value
  *   "gs_dump"  "resolve"=3: 1 = every substep also dumps the pairs it resolves (ppc_debug_hot_pairs); test hook
+ *   "gs_strip" "resolve"=3: staged particles above which a tile is cut into column strips (0 = the kernel's capacity, default)
+ *   "defer_state"  1 = the first pass of a substep writes only cell keys and the sorting gather applies the integrate + wall
+ *              pass to the record it moves (default: 16 bytes per particle less traffic); 0 = the first pass writes the state
  *   "collide"  0 = auto (shared-memory tile kernel with fine x-bins), 1 = global-memory thread-per-particle kernel,
  *              3 = shared-memory tile kernel scanning the whole 3x3 neighbourhood
  *   "slab_strict"  slab mode: 1 = ppc_slab_begin fails (-2) when the substep just finished was not exact (default); 0 = it only

@@ -52,6 +52,7 @@ struct Store {
     bool     col_valid     = false;   // set[cur].col holds the colours of the latest particlesUpdate
     int      opt_sort = 0, opt_stash = 1, opt_resolve = 1, opt_collide = 0, opt_wave_passes = 0, opt_wave_mode = 1, opt_slab_strict = 1;   // resolve: 0 off, 1 sequential-equivalent, 2 Jacobi, 3 tile Gauss-Seidel
     int      opt_nb_lo_rows = 0, opt_nb_hi_rows = 0;   // slab mode: cell rows the lower / upper neighbour owns (0: not told)
+    int      opt_defer_state = 1;   // K1 writes keys only and the gather applies the integrate + wall pass (0: K1 writes the state, as round 1 did)
     int      opt_gs_wc = 0, opt_gs_dump = 0, opt_gs_strip = 0;   // tile width of the "resolve"=3 kernel (0: from the particle density); dump the pairs it resolves
     // pending particlesUpdate (fused into the next collisions check)
     bool  pending = false;
@@ -70,6 +71,7 @@ struct Store {
     uint32_t    *api_ids = nullptr;   // slab mode: global indices of the copied-back particles
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
+    bool         hist_clean = false;   // cell_count is all zeros (the counting-sort scatter counts it back down): K1 need not clear it
     size_t       cells_cap = 0;
     uint32_t    *scratch = nullptr;
     size_t       scratch_words = 0;
@@ -450,6 +452,7 @@ static void ensure_cells( Store *st, size_t cells ) {
     st->cells_cap  = cells + 1 + cells / 8;
     st->cell_count = dev_alloc<uint32_t>( st->cells_cap );
     st->cell_start = dev_alloc<uint32_t>( st->cells_cap );
+    st->hist_clean = false;
 }
 
 static Store *new_store( const struct Particles_t *p, bool owns_host ) {
@@ -577,8 +580,10 @@ static unsigned auto_download_mask( const Store *st ) {
 // ---- the substep ----------------------------------------------------------------------------------------------
 static void launch_integrate( Store *st, const StepParams &P ) {
     StageTimer T( st, ST_INTEGRATE );
+    if ( P.do_walls_keys && P.do_histogram && !st->hist_clean )
+        PPC_CK( cudaMemsetAsync( st->cell_count, 0, st->cells_cap * sizeof( uint32_t ), st->stream ) );
     if ( P.do_walls_keys && P.do_histogram )
-        PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( (size_t)P.grid.cells + 1 ) * sizeof( uint32_t ), st->stream ) );
+        st->hist_clean = false;
     PPC_LAUNCH( k_integrate_walls_keys, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->cell_count,
                 st->n, P );
 }
@@ -612,7 +617,8 @@ static ParticleSet offset_view( const ParticleSet &S, const size_t first ) {
     return ParticleSet{ S.pv + first, S.rm + first, S.gid + first, S.key + first, S.col + first };
 }
 
-static void grid_stage( Store *st, const size_t n, const size_t bins, const int cols, const size_t first = 0, const uint32_t unranked_cell = 0xffffffffu ) {
+static void grid_stage( Store *st, const size_t n, const size_t bins, const int cols, const size_t first = 0, const uint32_t unranked_cell = 0xffffffffu,
+                        const StepParams *deferred = nullptr ) {
     const ParticleSet  A = offset_view( st->set[ st->cur ], first );   // input: n slots starting at `first`
     const ParticleSet &B = st->set[ st->cur ^ 1 ];
     {
@@ -627,18 +633,21 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
             const int where = radix_sort_pairs( st->sort_keys_a, st->slot_of, st->sort_keys_b, st->sort_vals_b, true, n,
                                                 bits_for( (uint32_t)bins ), st->scratch, st->stream );
             slot_of         = where ? st->sort_vals_b : st->slot_of;
-        } else {
-            PPC_CK( cudaMemsetAsync( st->cell_count, 0, bins * sizeof( uint32_t ), st->stream ) );
+        } else {   // counts the histogram back down to zero
             PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, st->cell_count, st->cell_start,
                         st->slot_of, n );
+            st->hist_clean = true;
         }
     }
     {
         StageTimer T( st, ST_GATHER );                                                 // K6
         const bool gs = st->opt_resolve == 3;   // also leave the records the tile kernel stages
+        StepParams P  = {};
+        if ( deferred )
+            P = *deferred;   // K1 kept the integrated, wall-constrained state to itself: the gather repeats it on the record it moves
         PPC_LAUNCH( k_canonical_gather, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A, B, slot_of, st->cell_start, n,
                     st->col_valid ? 1 : 0, unranked_cell, gs ? st->rec_a : (float4 *)nullptr, gs ? st->gs_mcol : (uint16_t *)nullptr,
-                    (uint32_t)cols );
+                    (uint32_t)cols, P );
     }
     st->cur ^= 1;   // B is now the sorted, pre-resolve state
 }
@@ -892,6 +901,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     P.wall_w        = (float)(int)W;
     P.wall_h        = (float)(int)H;
     P.grid          = G;
+    P.defer_state   = st->opt_defer_state ? 1 : 0;   // K1 writes keys only; the gather applies the integrate + wall pass to what it moves
     if ( st->pending )
         st->col_valid = st->pending_colour;
     st->pending     = false;
@@ -899,7 +909,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
     launch_integrate( st, P );                                                         // K1 (+K3 histogram)
     if ( st->opt_resolve == 3 )
         ensure_gs_buffers( st );
-    grid_stage( st, n, G.cells, G.cols );
+    grid_stage( st, n, G.cells, G.cols, 0, 0xffffffffu, P.defer_state ? &P : nullptr );
     st->grid       = G;
     st->grid_valid = true;
     resolve_stage( st, n, G, dt );
@@ -1177,6 +1187,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_strip = (int)value;
     else if ( !strcmp( name, "gs_dump" ) )
         st->opt_gs_dump = (int)value;
+    else if ( !strcmp( name, "defer_state" ) )
+        st->opt_defer_state = (int)value;
     else
         return -1;
     return 0;

@@ -20,13 +20,15 @@ struct StepParams {
     int   do_colour;      // reference src/particles_solver.c:31-39 (only on substeps whose result is drawn)
     int   do_walls_keys;  // reference src/particles_solver.c:207-228 and :280-291
     int   do_histogram;   // count particles per cell key (off in slab mode: the window's histogram is built after the exchange)
+    int   defer_state;    // K1 writes only the key (and the colour): k_canonical_gather repeats the integrate + wall pass on the record it
+                          // moves anyway and writes the result once (16 B per particle less written here, the same 16 B read there either way)
     float wall_w, wall_h; // (float)(int)window_width / height
     GridDims grid;
 };
 
 // ---- K1: integrate + wall-constrain + cell key + warp-aggregated cell histogram ------------------------------
 // One thread per storage slot; 128-bit load/store of (p_x, p_y, v_x, v_y).  Algorithmic traffic: 20 B read
-// (pv + radius; mass only when colouring) + 16 B write + 4 B key.
+// (pv + radius; mass only when colouring) + 4 B key (+ 16 B write unless the gather applies the state, P.defer_state).
 __global__ void __launch_bounds__( STREAM_THREADS ) k_integrate_walls_keys( ParticleSet S, uint32_t *__restrict__ cell_count, const size_t n,
                                                                             const StepParams P ) {
     const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
@@ -48,7 +50,8 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_integrate_walls_keys( Part
             key          = (uint32_t)( cy * P.grid.cols + cx );   // reference :291
             S.key[ k ]   = key;
         }
-        S.pv[ k ] = s;
+        if ( !P.defer_state )
+            S.pv[ k ] = s;
     }
     if ( P.do_walls_keys && P.do_histogram ) {   // whole warp arrives here: lanes of one cell elect a leader that adds their count
         const unsigned peers = __match_any_sync( 0xffffffffu, key );
@@ -80,7 +83,9 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_max_radius( const float2 *
 // ---- K5: counting-sort scatter ------------------------------------------------------------------------------
 // slot_of[pos] = storage slot that lands at sorted position pos; positions inside a cell are handed out by a
 // warp-aggregated atomic, so the order inside a cell is arbitrary here and fixed by k_canonical_gather.
-__global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32_t *__restrict__ key, uint32_t *__restrict__ cell_fill,
+// The atomic counts the cell's own histogram entry DOWN: when the scatter is done the histogram is all zeros again, which is
+// what the next substep's K1 needs -- no separate fill counters, no clearing pass over the cell table (two per substep before).
+__global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32_t *__restrict__ key, uint32_t *__restrict__ cell_count,
                                                                     const uint32_t *__restrict__ cell_start, uint32_t *__restrict__ slot_of,
                                                                     const size_t n ) {
     const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
@@ -91,7 +96,7 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
     const unsigned leader = (unsigned)( __ffs( peers ) - 1 );
     uint32_t       base   = 0;
     if ( valid && lane == leader )
-        base = atomicAdd( &cell_fill[ c ], (uint32_t)__popc( peers ) );
+        base = atomicSub( &cell_count[ c ], (uint32_t)__popc( peers ) ) - (uint32_t)__popc( peers );
     base = __shfl_sync( peers, base, leader );
     if ( valid )
         slot_of[ cell_start[ c ] + base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) ) ] = (uint32_t)k;
@@ -108,7 +113,8 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
                                                                         const uint32_t *__restrict__ slot_of,
                                                                         const uint32_t *__restrict__ cell_start, const size_t n,
                                                                         const int move_colour, const uint32_t unranked_cell,
-                                                                        float4 *__restrict__ rec_a, uint16_t *__restrict__ mcol, const uint32_t cols ) {
+                                                                        float4 *__restrict__ rec_a, uint16_t *__restrict__ mcol, const uint32_t cols,
+                                                                        const StepParams P ) {
     const size_t pos = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     if ( pos >= n )
         return;
@@ -123,8 +129,13 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_canonical_gather( const Pa
         for ( uint32_t q = b; q < e; q++ )
             rank += ( In.gid[ slot_of[ q ] ] < g ) ? 1u : 0u;
     const uint32_t dst = b + rank;
-    const float4   s4  = In.pv[ src ];
+    float4         s4  = In.pv[ src ];
     const float2   a2  = In.rm[ src ];
+    if ( P.defer_state ) {   // K1 computed exactly this to find the key and kept it to itself
+        if ( P.do_integrate )
+            integrate( s4.x, s4.y, s4.z, s4.w, P.dt_update );
+        walls( s4.x, s4.y, s4.z, s4.w, a2.x, P.wall_w, P.wall_h );
+    }
     if ( rec_a ) {
         const uint32_t cx = c - ( c / cols ) * cols;
         rec_a[ dst ] = make_float4( s4.x, s4.y, a2.x, __uint_as_float( g ) );

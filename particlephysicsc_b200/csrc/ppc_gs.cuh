@@ -92,6 +92,7 @@ constexpr uint32_t GS_HDR_UNITS = ( 2 * ( GS_R + 2 ) + 1 + 3 ) / 4;   // 21 word
 constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u, GS_ERR_CHUNK = 8u;
 static_assert( GS_CAP <= 1024, "T.ord holds a staged index in 10 bits" );
 static_assert( GS_BINS * 4 <= GS_POOL * 4, "the bin counters alias the contact pool" );
+static_assert( GS_CAP + ( GS_R + 2 ) * 2 * GS_MC_PAD <= GS_POOL, "the mass/column words land in pool_aux" );
 static_assert( GS_BINS % GS_THREADS == 0, "bins per thread" );
 
 struct GsSmem {
@@ -101,7 +102,8 @@ struct GsSmem {
     uint16_t pool_aux[ GS_POOL ];   // level of an entry that stands for a pair this sub-tile owns
     uint16_t fend[ GS_BINS ];       // end (exclusive) of fine bin f = row * GS_NB + bin in perm; its begin is fend[f - 1]
     uint16_t perm[ GS_CAP ];        // staged indices sorted by (staged row, fine bin)
-    uint16_t mc[ GS_CAP + ( GS_R + 2 ) * 2 * GS_MC_PAD ];   // mass byte | cell column byte << 8, row by row from 16-byte boundaries
+    uint8_t  colb[ GS_CAP ];        // cell column byte of every staged particle
+    uint8_t  massb[ GS_CAP ];       // mass byte (:141-142)
     uint16_t head[ GS_CAP ];        // first contact entry of a centre particle
     uint8_t  lvl[ GS_CAP ];         // level of the latest pair of every staged particle
     uint16_t ord[ GS_CAP ];         // centre particle t: staged index [9:0] | staged row << 10
@@ -181,10 +183,16 @@ __device__ __forceinline__ int gs_strip_end( const uint32_t *colp, const uint32_
                                              const uint32_t limit ) {
     if ( total <= limit )
         return cx1;
-    int ex = sx + 1;
-    while ( ex < cx1 && colp[ min( ex + 2, c1 ) - c0 ] - colp[ max( sx - 1, c0 ) - c0 ] <= limit )
-        ex++;
-    return ex;
+    // the first end that cannot grow any further; the test is monotone in the end, so a warp tries 32 ends at once (every warp of the
+    // CTA, or the one warp of k_gs_resolve, computes the same value; all their lanes are here)
+    const uint32_t below = colp[ max( sx - 1, c0 ) - c0 ];
+    for ( int ex = sx + 1;; ex += 32 ) {
+        const int      e  = ex + (int)( threadIdx.x & 31u );
+        const bool     ok = e < cx1 && colp[ min( e + 2, c1 ) - c0 ] - below <= limit;
+        const unsigned m  = __ballot_sync( 0xffffffffu, ok );
+        if ( m != 0xffffffffu )
+            return ex + __ffs( (int)~m ) - 1;
+    }
 }
 
 // Run table of a sub-tile: staged row j = 0 .. GS_R+1 is grid row cy0 - 1 + j, columns [c0, c1); centre = columns [cx0, cx1) of rows
@@ -238,6 +246,8 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
     const int c0 = max( cx0 - 1, 0 ), c1 = min( cx1 + 1, G.cols );      // staged columns [c0, c1)
     const int ncol = c1 - c0, nb = ncol * GS_F;
     uint32_t *cnt32 = reinterpret_cast<uint32_t *>( T.pool_val );       // bin counters / cursors while binning (pool unused then)
+    uint16_t *mcland = T.pool_aux;   // where the bulk copies put the mass/column words, row by row from 16-byte boundaries (pool_aux is not used
+                                     // before the levels are assigned); the binning pass below spreads them into colb / massb
     __syncthreads();                                                    // shared memory may still be in use by the previous strip
 
     // Run table and staging by warp 0, one lane per staged row: row j = 0 .. GS_R+1 is grid row cy0 - 1 + j, columns [c0, c1); centre =
@@ -291,7 +301,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             __syncwarp();
             if ( len ) {
                 tma_load_1d( &T.a[ s_inc - len ], rec_a + g0, len * 16u, reinterpret_cast<uint64_t *>( &T.mbar ) );
-                tma_load_1d( &T.mc[ m_inc - mclen ], mcol + ( g0 - lead ), mclen * 2u, reinterpret_cast<uint64_t *>( &T.mbar ) );
+                tma_load_1d( &mcland[ m_inc - mclen ], mcol + ( g0 - lead ), mclen * 2u, reinterpret_cast<uint64_t *>( &T.mbar ) );
             }
         }
 #endif
@@ -331,13 +341,10 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             j++;
         const uint32_t g = T.run_g0[ j ] + ( t - T.run_s0[ j ] );
         T.a[ t ] = rec_a[ g ];
-        T.mc[ T.mc_s0[ j ] + ( t - T.run_s0[ j ] ) ] = mcol[ g ];
+        mcland[ T.mc_s0[ j ] + ( t - T.run_s0[ j ] ) ] = mcol[ g ];
     }
     __syncthreads();
 #endif
-    // mass/column word of staged particle t in staged row j
-#define GS_MC( t, j ) T.mc[ T.mc_s0[ j ] + ( ( t ) - T.run_s0[ j ] ) ]
-
     // ---- histogram of (row, fine bin); largest radius ----
     const float x0 = __fmul_rn( (float)c0, G.cell_size ), inv_w = __fdiv_rn( (float)GS_F, G.cell_size );
     float       rmax = 0.0f;
@@ -348,6 +355,9 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         const float4 p = T.a[ t ];
         rmax           = fmaxf( rmax, p.z );
         atomicAdd( &cnt32[ j * GS_NB + gs_fine_bin( p.x, x0, inv_w, nb ) ], 1u );
+        const uint32_t w = mcland[ T.mc_s0[ j ] + ( t - T.run_s0[ j ] ) ];
+        T.colb[ t ]  = (uint8_t)( w >> 8 );
+        T.massb[ t ] = (uint8_t)w;
     }
 #pragma unroll
     for ( int d = 16; d > 0; d >>= 1 )
@@ -414,7 +424,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         const uint32_t self = T.run_s0[ j ] + ( gk - T.run_g0[ j ] );          // staged index
         const float4   me4  = T.a[ self ];
         const float    x = me4.x, y = me4.y, r = me4.z;
-        const int      mycol = (int)( GS_MC( self, j ) >> 8 );
+        const int      mycol = (int)T.colb[ self ];
         const int      gy    = cy0 - 1 + j;
         const float    reach = __fadd_rn( __fadd_rn( r, R ), 0.02f );
         const int      b_lo  = gs_fine_bin( __fsub_rn( x, reach ), x0, inv_w, nb ), b_hi = gs_fine_bin( __fadd_rn( x, reach ), x0, inv_w, nb );
@@ -461,7 +471,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                 continue;
             const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
             if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
-                const int dc = (int)(int8_t)( ( (uint32_t)GS_MC( s, jr ) >> 8 ) - (uint32_t)mycol );
+                const int dc = (int)(int8_t)( (uint32_t)T.colb[ s ] - (uint32_t)mycol );
                 if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
                     continue;
                 const uint32_t at = atomicAdd( &T.pool_n, 1u );
@@ -504,7 +514,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                     continue;
                 const float d2 = __fadd_rn( __fmul_rn( dx, dx ), __fmul_rn( dy, dy ) );
                 if ( d2 <= __fmul_rn( rs, rs ) && s != self ) {   // :360-362
-                    const int dc = (int)(int8_t)( ( (uint32_t)GS_MC( s, jr ) >> 8 ) - (uint32_t)mycol );
+                    const int dc = (int)(int8_t)( (uint32_t)T.colb[ s ] - (uint32_t)mycol );
                     if ( dc < -1 || dc > 1 )   // two columns apart: outside the reference's 3x3 scan (:331-340)
                         continue;
                     const uint32_t at = atomicAdd( &T.pool_n, 1u );
@@ -558,8 +568,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         const float4   me4  = T.a[ self ];
         const float    x = me4.x, y = me4.y, r = me4.z;
         const uint32_t gid   = __float_as_uint( me4.w );
-        const uint32_t mcw   = GS_MC( self, j );
-        const int      mycol = (int)( mcw >> 8 );
+        const int      mycol = (int)T.colb[ self ];
         const uint32_t head  = T.head[ self ];
         float X = x, Y = y;
         {
@@ -572,7 +581,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                 const uint32_t s = v & 0x7ffu, g = __float_as_uint( T.a[ s ].w );
                 return g < gid ? g : 0x80000000u | ( ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) << 11 ) | ( 2047u - s );
             };
-            const float wme      = T.inv_lut[ mcw & 0xffu ];
+            const float wme      = T.inv_lut[ T.massb[ self ] ];
             const bool  row_last = ( j == GS_R ), row_first = ( j == 1 );
             const int   my_gc    = c0 + ( ( mycol - c0 ) & 0xff );   // this particle's grid column
 #pragma unroll 1
@@ -596,7 +605,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                 const float4   c     = T.a[ s ];
                 const uint32_t cg    = __float_as_uint( c.w );
                 const bool     me_lo = gid < cg;
-                const float    wq    = T.inv_lut[ GS_MC( s, j + d ) & 0xffu ];
+                const float    wq    = T.inv_lut[ T.massb[ s ] ];
                 {   // position push, operands selected by role (lo = the pair's i), :145-156
                     const PushTerms P = push_terms( contact_geom( me_lo ? x : c.x, me_lo ? y : c.y, me_lo ? r : c.z, me_lo ? c.x : x, me_lo ? c.y : y,
                                                                   me_lo ? c.z : r, dt ), me_lo ? wme : wq, me_lo ? wq : wme );
@@ -876,7 +885,6 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             }
         }
     }
-#undef GS_MC
     return false;
 }
 

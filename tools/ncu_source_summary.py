@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line summary of one kernel from an ncu report captured with --import-source on (needs -lineinfo).
 
-    python tools/ncu_source_summary.py gpurun_out/prof.ncu-rep [top] [sort: samp|inst]
+    python tools/ncu_source_summary.py gpurun_out/prof.ncu-rep [top] [sort: samp|inst] [kernel name (first launch of it)]
 Prints, per CUDA source line: share of executed warp instructions, share of stall samples, average active threads.
 """
 import csv
@@ -13,7 +13,8 @@ import sys
 def main():
     rep, top = sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 40
     key = sys.argv[3] if len(sys.argv) > 3 else "samp"
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    sel = ["--kernel-name", sys.argv[4], "--launch-count", "1"] if len(sys.argv) > 4 else []
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + sel, capture_output=True, text=True).stdout
     hdr, lines, fname = None, [], ""
     for r in csv.reader(io.StringIO(out)):
         if not r:
