@@ -90,6 +90,13 @@ struct Store {
     uint32_t    *h_gs_flag = nullptr;                       // pinned copy of gs_flags[0] after the narrow phase of the current substep
     cudaEvent_t  ev_gs = nullptr;
     unsigned long long gs_fallbacks = 0;                    // substeps the tile kernel could not hold and the exact resolve ran instead
+    uint32_t     gs_pairs_per_tile = 0;                     // owned pairs per tile (with pairs or not) of the last settled substep: sizes k_gs_resolve's slices
+    int          opt_gs_slice = 0;                          // pair records per slice of k_gs_resolve (0: from gs_pairs_per_tile)
+    size_t       gs_tiles = 0;
+    bool         gs_pending = false;                        // the verdict of the last "resolve"=3 substep has not been looked at yet (gs_settle)
+    size_t       gs_pending_n = 0;                          // ... and what the exact resolve needs if the verdict is "did not fit"
+    GridDims     gs_pending_grid = {};
+    float        gs_pending_dt = 0.0f;
     WaveBuffers  wave = {};          // sequential-equivalent resolve (allocated on first use)
     WaveRecs     recs = {};          // packed records of the event-driven rounds
     int          events_grid = 0;
@@ -480,11 +487,14 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
 }
 
 // Find the device mirror of a caller's struct; adopt arrays we did not allocate (a harness that filled its own).
+static void gs_settle( Store *st );
 static Store *store_of( struct Particles_t *p ) {
     for ( Store *st : g_stores )
         if ( st->host_key == p->mass ) {
             PPC_CK( cudaSetDevice( st->device ) );   // several stores on several GPUs in one process (or a host framework that
-            return st;                               // switches devices between calls): always work on this store's device
+            if ( st->gs_pending )                    // switches devices between calls): always work on this store's device
+                gs_settle( st );                     // every entry point sees a state whose last substep is settled
+            return st;
         }
     Store *st     = new_store( p, false );
     st->dirty_all = true;
@@ -671,8 +681,9 @@ static int gs_tile_width( const Store *st, const size_t n, const GridDims &G ) {
     return wc < 2 ? 2 : ( wc > wc_max ? wc_max : wc );   // >= 2 cells, so tiles of one colour touch disjoint particles
 }
 
-// Returns true when the field did not fit and the caller must run the exact resolve on the (restored) sorted state instead.
-static bool resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
+// The verdict "every sub-tile fit" is looked at by gs_settle, a substep late at most: the host queues the velocity kernels and
+// returns, so it is never more than one narrow phase behind the GPU and the GPU never waits for it.
+static void resolve_gs( Store *st, const size_t n, const GridDims &G, const float dt ) {
     if ( !st->gs_attr_set ) {
         PPC_CK( cudaFuncSetAttribute( k_gs_pairs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof( GsSmem ) ) );
         st->gs_attr_set = true;
@@ -703,10 +714,16 @@ static bool resolve_gs( Store *st, const size_t n, const GridDims &G, const floa
     // Did every sub-tile fit the kernel's shared-memory capacities?  The answer travels to the host behind the narrow phase; the
     // velocity kernels are queued meanwhile and do nothing if it is no, so the GPU never waits for the host.
     if ( !st->h_gs_flag ) {
-        PPC_CK( cudaHostAlloc( (void **)&st->h_gs_flag, sizeof( uint32_t ), cudaHostAllocDefault ) );
+        PPC_CK( cudaHostAlloc( (void **)&st->h_gs_flag, 3 * sizeof( uint32_t ), cudaHostAllocDefault ) );
         PPC_CK( cudaEventCreateWithFlags( &st->ev_gs, cudaEventDisableTiming ) );
     }
-    PPC_CK( cudaMemcpyAsync( st->h_gs_flag, st->gs_flags, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_gs_flag, st->gs_flags, 3 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );   // flag, -, record units handed out
+    st->gs_tiles = tiles;
+    // dense fields (a thousand pairs and more per tile) stream their records in long slices; dilute ones keep the CTA small
+    const int slice = st->opt_gs_slice > 0 ? st->opt_gs_slice : ( st->gs_pairs_per_tile >= 600u ? 512 : ( st->gs_pairs_per_tile >= 100u ? 256 : 64 ) );
+    L.slice_log2    = 4;
+    while ( L.slice_log2 < 10 && ( 1 << ( L.slice_log2 + 1 ) ) <= slice )
+        L.slice_log2++;   // 16 .. 1024 records, a power of two
     PPC_CK( cudaEventRecord( st->ev_gs, st->stream ) );
     {
         StageTimer T( st, ST_WAVEFRONT );     // velocity impulses: tiles of one colour at a time
@@ -717,30 +734,53 @@ static bool resolve_gs( Store *st, const size_t n, const GridDims &G, const floa
             const int nty = ( tiles_y - L.ty_start + 1 ) / 2;
             if ( L.ntx <= 0 || nty <= 0 )
                 continue;
-            PPC_LAUNCH( k_gs_resolve, (unsigned)( L.ntx * nty ), GSB_THREADS, 0, st->stream, (const uint16_t *)st->gs_mcol, st->set[ st->cur ].pv, L, PR,
+            PPC_LAUNCH( k_gs_resolve, (unsigned)( L.ntx * nty ), GSB_THREADS, ( (size_t)GSB_NBUF << L.slice_log2 ) * sizeof( uint4 ), st->stream, (const uint16_t *)st->gs_mcol, st->set[ st->cur ].pv, L, PR,
                         (const uint32_t *)st->gs_flags );
         }
     }
+    st->gs_pending      = true;
+    st->gs_pending_n    = n;
+    st->gs_pending_grid = G;
+    st->gs_pending_dt   = dt;
+}
+
+static void resolve_exact( Store *st, const size_t n, const GridDims &G, const float dt, const int mode );
+
+// Look at the verdict of the last "resolve"=3 substep; called before anything else touches the state (the next substep, a copy-back,
+// an exporter ...: store_of and collide_step).  Nothing has been queued behind that substep's velocity kernels yet.
+static void gs_settle( Store *st ) {
+    if ( !st->gs_pending )
+        return;
+    st->gs_pending = false;
     PPC_CK( cudaEventSynchronize( st->ev_gs ) );
+    if ( st->gs_tiles )
+        st->gs_pairs_per_tile = (uint32_t)( st->h_gs_flag[ 2 ] / st->gs_tiles );   // (units include the chunk headers: fine for a threshold)
     if ( *st->h_gs_flag == 0u )
-        return false;
+        return;
     if ( st->slab )    // a rank cannot fall back on its own: the single-GPU run it must equal would have done so for the whole field
-        return false;  // (the flag stays set; the next synchronising call reports it)
-    // Some sub-tile overflowed (a region far denser than the rest: an impact front, a clump of overlapping particles).  This substep
+        return;        // (the flag stays set; the next synchronising call reports it)
+    // Some sub-tile overflowed (a region far denser than the rest: an impact front, a clump of overlapping particles).  That substep
     // runs on the exact resolve instead -- for the WHOLE field, so the result is a function of the state alone: positions back to what
-    // the pair search saw (the velocities are untouched: the velocity kernels above saw the flag), then the reference's order.
+    // the pair search saw (the velocities are untouched: the velocity kernels saw the flag and did nothing), then the reference's order.
+    const size_t n = st->gs_pending_n;
     st->gs_fallbacks++;
     PPC_CK( cudaMemsetAsync( st->gs_flags, 0, sizeof( uint32_t ), st->stream ) );
     PPC_LAUNCH( k_rec_to_positions, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, st->set[ st->cur ].pv, n );
-    return true;
+    resolve_exact( st, n, st->gs_pending_grid, st->gs_pending_dt, 1 );
 }
 
 static void resolve_stage( Store *st, const size_t n, const GridDims &G, const float dt ) {
-    if ( st->opt_resolve == 3 && !resolve_gs( st, n, G, dt ) )
-        return;
+    if ( st->opt_resolve == 3 )
+        resolve_gs( st, n, G, dt );
+    else
+        resolve_exact( st, n, G, dt, st->opt_resolve );
+}
+
+// mode: the "resolve" option (1 exact wavefront, 2 Jacobi, 0 none)
+static void resolve_exact( Store *st, const size_t n, const GridDims &G, const float dt, const int mode ) {
     ParticleSet &S = st->set[ st->cur ], &O = st->set[ st->cur ^ 1 ];
-    if ( st->opt_resolve ) {
-        const bool jacobi = st->opt_resolve == 2;
+    if ( mode ) {
+        const bool jacobi = mode == 2;
         if ( !jacobi ) {
             ensure_wave_buffers( st );
             PPC_CK( cudaMemsetAsync( st->wave.counters, 0, 3 * sizeof( uint32_t ), st->stream ) );
@@ -872,6 +912,7 @@ static void resolve_stage( Store *st, const size_t n, const GridDims &G, const f
 
 // One collisions check (reference src/particles_solver.c:197-393), with the pending particlesUpdate fused in.
 static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
+    gs_settle( st );   // the previous substep's verdict, before this one queues anything
     const size_t n = st->n;
     if ( n < 2 ) {   // reference :204-205: not even the wall pass runs
         flush_pending_update( st );
@@ -1187,6 +1228,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_strip = (int)value;
     else if ( !strcmp( name, "gs_dump" ) )
         st->opt_gs_dump = (int)value;
+    else if ( !strcmp( name, "gs_slice" ) )
+        st->opt_gs_slice = (int)value;
     else if ( !strcmp( name, "defer_state" ) )
         st->opt_defer_state = (int)value;
     else

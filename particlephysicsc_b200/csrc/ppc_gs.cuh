@@ -68,12 +68,16 @@ namespace ppc {
 #ifndef PPC_GSB_THREADS
 #define PPC_GSB_THREADS 128
 #endif
-#ifndef PPC_GSB_SLICE
-#define PPC_GSB_SLICE 256  // pair records per slice of the chunk k_gs_resolve streams through shared memory
-#endif
+#ifndef PPC_GSB_NBUF
+#define PPC_GSB_NBUF 2     // slices of the record chunk in flight in k_gs_resolve.  The slice length is chosen per launch (GsLaunch::slice,
+#endif                     // dynamic shared memory): measured on the 16M pile 0.81 / 0.74 ms with 256 / 512 records per slice (a short slice
+                           // lasts about two levels, less than the latency of the copy that refills its buffer), but 0.24 / 0.32 ms on the
+                           // dilute uniform field, whose tiles own a few dozen pairs and want many resident CTAs instead; deeper rings
+                           // (3, 4, 6, 8 buffers) cost more residency than the latency they hide on both
 constexpr int      GS_THREADS  = PPC_GS_THREADS;
 constexpr int      GSB_THREADS = PPC_GSB_THREADS;
-constexpr int      GSB_SLICE   = PPC_GSB_SLICE;
+constexpr int      GSB_NBUF    = PPC_GSB_NBUF;
+static_assert( GSB_NBUF >= 2 && GSB_NBUF <= 8, "ring of slice buffers" );
 constexpr int      GS_R        = TILE_R;              // centre rows per tile
 constexpr int      GS_CAP      = PPC_GS_CAP;
 constexpr int      GS_POOL     = PPC_GS_POOL;
@@ -117,7 +121,7 @@ struct GsSmem {
     uint32_t wsum[ 32 ], wsum2[ 32 ];
     uint32_t colp[ GS_MAXC + 2 ];   // column sums of cell_start over the staged rows (strip planning)
     uint32_t bcount[ GS_BUCKETS ];  // pairs per level, then running begin / end of each level in the record chunk
-    uint32_t rmax_bits, pool_n, err, chunk_base, n_buckets, phase_mask;
+    uint32_t rmax_bits, pool_n, err, chunk_base, n_buckets, phase_mask, n_owned;
     unsigned long long mbar;
 };
 
@@ -131,6 +135,7 @@ struct GsLaunch {
     int ntx;         // k_gs_resolve: tiles of this colour per tile row
     int ty_start;    // k_gs_resolve: first local tile row of this colour
     int strip_limit; // staged particles (strip + halo) above which a tile is cut into strips, and which a strip may hold (<= GS_CAP)
+    int slice_log2;  // k_gs_resolve: log2 of the pair records per slice of a chunk (dynamic shared memory: GSB_NBUF * slice * 16 bytes)
 };
 
 // Pair records of one substep: one chunk per sub-tile, allocated with one atomic add, in units of 16 bytes:
@@ -843,6 +848,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             }
             T.chunk_base = base;
             T.n_buckets  = n_used;
+            T.n_owned    = n_pairs;
             *desc_slot   = base != 0xffffffffu ? make_uint2( base + 1u, n_pairs | ( n_used << 16 ) | last_flag ) : make_uint2( 0u, last_flag );
         }
         __syncthreads();
@@ -864,11 +870,10 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         return false;   // no pair, or no room
     {
         uint4         *rec = PR.chunks + T.chunk_base + GS_HDR_UNITS + ( T.n_buckets * 2u + 15u ) / 16u;
-        const uint32_t n_entries = min( T.pool_n, (uint32_t)GS_POOL );
-        for ( uint32_t e = threadIdx.x; e < n_entries; e += GS_THREADS ) {
-            const uint32_t v = T.pool_val[ e ];
-            if ( !( v & 0x8000u ) )
-                continue;
+        // one thread per owned pair: seg lists exactly the entries that stand for one (every lane has work, unlike a sweep over the pool)
+        const uint32_t n_owned = T.n_owned;
+        for ( uint32_t k = threadIdx.x; k < n_owned; k += GS_THREADS ) {
+            const uint32_t e = seg[ k ], v = T.pool_val[ e ];
             const uint32_t a = T.pool_next[ e ], q = v & 0x7ffu;
             const float4   A = T.a[ a ], Q = T.a[ q ];
             const bool     a_lo = __float_as_uint( A.w ) < __float_as_uint( Q.w );   // lo = the lower API index = the reference's i
@@ -932,10 +937,9 @@ __global__ void __launch_bounds__( GS_THREADS, PPC_GS_MINBLOCKS ) k_gs_pairs( co
 // k_gs_resolve: the velocity impulses of the pairs a sub-tile owns, bucket by bucket (one launch per tile colour).
 // ====================================================================================================================
 // A sub-tile's records are one contiguous chunk, read front to back: the TMA streams it through shared memory in slices of
-// GSB_SLICE records, two slices in flight, so a record is never waited for at HBM latency.  CTAs are small (the pairs of a bucket
+// GSB_SLICE records, GSB_NBUF slices in flight, so a record is never waited for at HBM latency.  CTAs are small (the pairs of a bucket
 // are a few dozen) and hold little shared memory, so many tiles are resident per SM and their dependent steps interleave.
 struct GsbSmem {
-    uint4    recs[ 2 ][ GSB_SLICE ];         // two slices of the record chunk
     float2   v[ GS_CAP ];                    // current velocity of every staged particle
     uint8_t  m[ GS_CAP ];                    // mass byte (:141-142)
     uint8_t  dirty[ GS_CAP ];                // an impulse changed this particle's velocity
@@ -943,18 +947,20 @@ struct GsbSmem {
     float    inv_lut[ 256 ];                 // 1 / (float)k, the inverse masses of :146-147
     uint32_t run[ 2 * ( GS_R + 2 ) + 1 + 3 ];   // run table of the sub-tile, as k_gs_pairs left it: run_g0[GS_R + 2], run_s0[GS_R + 3]
     uint2    desc;
-    unsigned long long mbar[ 2 ];
+    unsigned long long mbar[ GSB_NBUF ];
 };
 
 __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *__restrict__ mcol, float4 *pv, const GsLaunch L, const GsPairs PR,
                                                                 const uint32_t *__restrict__ err_flags ) {
     __shared__ __align__( 16 ) GsbSmem T;
+    extern __shared__ __align__( 16 ) uint4 gsb_recs[];   // ring of GSB_NBUF slices of the record chunk, L.slice records each
+    const uint32_t SL = (uint32_t)L.slice_log2, GSB_SLICE = 1u << SL;
     if ( *err_flags )   // some sub-tile did not fit: the host runs the exact resolve for this substep instead
         return;
     const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
     const int tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;   // ty: tile row inside this grid
     const uint2 *desc = PR.desc + ( (size_t)ty * L.tiles_x + tx ) * GS_MAXSTRIPS;
-    uint32_t     parity[ 2 ] = { 0u, 0u };
+    uint32_t     parity = 0u;   // bit i: phase of the barrier of ring buffer i
     bool         ready = false;
     for ( int strip = 0;; strip++ ) {
         __syncthreads();   // shared memory may still be in use by the previous strip
@@ -962,36 +968,84 @@ __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *_
             T.desc = desc[ strip ];
         __syncthreads();
         const uint2 d = T.desc;
-        if ( d.x != 0 ) {
-            if ( !ready ) {   // first sub-tile with pairs (most tiles of a dilute field never get here)
-                if ( threadIdx.x == 0 ) {
-                    mbar_init( reinterpret_cast<uint64_t *>( &T.mbar[ 0 ] ), 1u );
-                    mbar_init( reinterpret_cast<uint64_t *>( &T.mbar[ 1 ] ), 1u );
+        const uint32_t n_pairs = d.y & 0xffffu, n_used = ( d.y >> 16 ) & 0x7fffu;
+        if ( d.x != 0 && n_pairs <= (uint32_t)GSB_THREADS ) {
+            // A sub-tile with a handful of pairs (every sub-tile of a dilute field): one thread per pair, everything straight from
+            // global memory -- its record, the two velocities when its level comes up -- instead of staging the velocities of a
+            // thousand particles for a few dozen impulses.  Same pairs, same levels, same arithmetic.
+            const uint4 *chunk = PR.chunks + ( d.x - 1u );
+            const uint4 *rec   = chunk + GS_HDR_UNITS + ( n_used * 2u + 15u ) / 16u;
+            if ( threadIdx.x < 2 * ( GS_R + 2 ) + 1 )
+                T.run[ threadIdx.x ] = reinterpret_cast<const uint32_t *>( chunk )[ threadIdx.x ];
+            for ( uint32_t b = threadIdx.x; b < n_used; b += GSB_THREADS )
+                T.bend[ b ] = reinterpret_cast<const uint16_t *>( chunk + GS_HDR_UNITS )[ b ];
+            const bool mine = threadIdx.x < n_pairs;
+            uint4      r    = make_uint4( 0u, 0u, 0u, 0u );
+            if ( mine )
+                r = rec[ threadIdx.x ];
+            __syncthreads();
+            const uint32_t *run_g0 = T.run, *run_s0 = T.run + ( GS_R + 2 );
+            uint32_t my_level = 0xffffffffu, slot_lo = 0, slot_hi = 0;
+            float    wlo = 0.0f, whi = 0.0f;
+            if ( mine ) {
+                my_level = 0;
+                while ( my_level < n_used && threadIdx.x >= T.bend[ my_level ] )
+                    my_level++;
+                const uint32_t lo = r.x & 0x7ffu, hi = ( r.x >> 11 ) & 0x7ffu;
+                int jl = 0, jh = 0;
+                while ( jl < GS_R + 1 && lo >= run_s0[ jl + 1 ] )
+                    jl++;
+                while ( jh < GS_R + 1 && hi >= run_s0[ jh + 1 ] )
+                    jh++;
+                slot_lo = run_g0[ jl ] + ( lo - run_s0[ jl ] );
+                slot_hi = run_g0[ jh ] + ( hi - run_s0[ jh ] );
+                wlo     = __fdiv_rn( 1.0f, (float)( mcol[ slot_lo ] & 0xffu ) );   // :141-142, :146-147
+                whi     = __fdiv_rn( 1.0f, (float)( mcol[ slot_hi ] & 0xffu ) );
+            }
+            for ( uint32_t b = 0; b < n_used; b++ ) {
+                if ( my_level == b ) {
+                    float2 *pl = reinterpret_cast<float2 *>( pv + slot_lo ) + 1, *ph = reinterpret_cast<float2 *>( pv + slot_hi ) + 1;
+                    float2  ul = __ldcg( pl ), uh = __ldcg( ph );
+                    ContactGeom C;
+                    C.nx = __uint_as_float( r.y ), C.ny = __uint_as_float( r.z ), C.vbias = __uint_as_float( r.w ), C.raw = 0.0f, C.corrected = 0.0f;
+                    const ImpulseTerms I = impulse_terms( C, wlo, whi, ul.x, ul.y, uh.x, uh.y );   // :158-190
+                    if ( I.impulse ) {
+                        ul.x = __fadd_rn( ul.x, I.dvx_lo );
+                        ul.y = __fadd_rn( ul.y, I.dvy_lo );
+                        uh.x = __fsub_rn( uh.x, I.dvx_hi );
+                        uh.y = __fsub_rn( uh.y, I.dvy_hi );
+                        __stcg( pl, ul );
+                        __stcg( ph, uh );
+                    }
                 }
+                if ( b + 1 < n_used )
+                    __syncthreads();   // the next level reads what this one wrote (same CTA: the barrier orders the global accesses)
+            }
+        } else if ( d.x != 0 ) {
+            if ( !ready ) {   // first sub-tile with many pairs
+                if ( threadIdx.x < GSB_NBUF )
+                    mbar_init( reinterpret_cast<uint64_t *>( &T.mbar[ threadIdx.x ] ), 1u );
                 for ( int i = threadIdx.x; i < 256; i += GSB_THREADS )
                     T.inv_lut[ i ] = __fdiv_rn( 1.0f, (float)i );
                 ready = true;
             }
-            const uint32_t n_pairs = d.y & 0xffffu, n_used = ( d.y >> 16 ) & 0x7fffu;
             const uint4   *chunk   = PR.chunks + ( d.x - 1u );
             const uint4   *rec     = chunk + GS_HDR_UNITS + ( n_used * 2u + 15u ) / 16u;
-            const uint32_t n_slices = ( n_pairs + GSB_SLICE - 1 ) / GSB_SLICE;
+            const uint32_t n_slices = ( n_pairs + GSB_SLICE - 1 ) >> SL;
             if ( threadIdx.x < 2 * ( GS_R + 2 ) + 1 )
                 T.run[ threadIdx.x ] = reinterpret_cast<const uint32_t *>( chunk )[ threadIdx.x ];
             for ( uint32_t b = threadIdx.x; b < n_used; b += GSB_THREADS )
                 T.bend[ b ] = reinterpret_cast<const uint16_t *>( chunk + GS_HDR_UNITS )[ b ];
             __syncthreads();   // run table; the barriers initialised
             auto load_slice = [ & ]( const uint32_t i ) {   // one thread
-                const uint32_t count = min( (uint32_t)GSB_SLICE, n_pairs - i * GSB_SLICE );
+                const uint32_t count = min( GSB_SLICE, n_pairs - ( i << SL ) );
                 fence_proxy_async();
-                mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar[ i & 1u ] ), count * 16u );
-                tma_load_1d( T.recs[ i & 1u ], rec + (size_t)i * GSB_SLICE, count * 16u, reinterpret_cast<uint64_t *>( &T.mbar[ i & 1u ] ) );
+                mbar_arrive_expect_tx( reinterpret_cast<uint64_t *>( &T.mbar[ i % GSB_NBUF ] ), count * 16u );
+                tma_load_1d( gsb_recs + ( ( i % GSB_NBUF ) << SL ), rec + ( (size_t)i << SL ), count * 16u, reinterpret_cast<uint64_t *>( &T.mbar[ i % GSB_NBUF ] ) );
             };
-            if ( threadIdx.x == 0 ) {
-                load_slice( 0u );
-                if ( n_slices > 1 )
-                    load_slice( 1u );
-            }
+            if ( threadIdx.x == 0 )
+                for ( uint32_t i = 0; i < (uint32_t)GSB_NBUF && i < n_slices; i++ )
+                    load_slice( i );
             const uint32_t *run_g0 = T.run, *run_s0 = T.run + ( GS_R + 2 );
             // current velocities (earlier sub-tiles may have changed them) and mass bytes of the staged particles, row by row so
             // that the loads of a row are independent of each other and many are in flight
@@ -1009,13 +1063,14 @@ __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *_
             uint32_t k = 0, b = 0;
 #pragma unroll 1
             while ( k < n_pairs ) {
-                const uint32_t slice = k / GSB_SLICE, s_end = min( ( slice + 1u ) * GSB_SLICE, n_pairs );
+                const uint32_t slice = k >> SL, s_end = min( ( slice + 1u ) << SL, n_pairs );
                 const uint32_t b_end = T.bend[ b ], seg_end = min( b_end, s_end );
-                if ( k == slice * GSB_SLICE ) {   // first record of a slice: it must have landed
-                    mbar_wait( reinterpret_cast<uint64_t *>( &T.mbar[ slice & 1u ] ), parity[ slice & 1u ] );
-                    parity[ slice & 1u ] ^= 1u;
+                const uint32_t ring = slice % GSB_NBUF;
+                if ( k == slice << SL ) {   // first record of a slice: it must have landed
+                    mbar_wait( reinterpret_cast<uint64_t *>( &T.mbar[ ring ] ), ( parity >> ring ) & 1u );
+                    parity ^= 1u << ring;
                 }
-                const uint4 *buf = T.recs[ slice & 1u ] - (size_t)slice * GSB_SLICE;
+                const uint4 *buf = gsb_recs + ( ring << SL ) - ( (size_t)slice << SL );
 #pragma unroll 1
                 for ( uint32_t q = k + threadIdx.x; q < seg_end; q += GSB_THREADS ) {
                     const uint4    r  = buf[ q ];
@@ -1036,8 +1091,8 @@ __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *_
                     }
                 }
                 __syncthreads();
-                if ( seg_end == s_end && slice + 2u < n_slices && threadIdx.x == 0 )
-                    load_slice( slice + 2u );   // the slice just finished frees its buffer
+                if ( seg_end == s_end && slice + GSB_NBUF < n_slices && threadIdx.x == 0 )
+                    load_slice( slice + GSB_NBUF );   // the slice just finished frees its buffer
                 k = seg_end;
                 if ( k == b_end )
                     b++;

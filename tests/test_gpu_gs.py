@@ -146,6 +146,27 @@ def test_an_overfull_tile_runs_that_substep_on_the_exact_resolve(oracle):
     p.Free()
 
 
+def test_performance_options_do_not_change_the_result():
+    """The slice length of k_gs_resolve's record stream ("gs_slice") and who applies the integrate + wall pass ("defer_state": the
+    sorting gather, or the first pass as in round 1) are performance choices: same bits whatever they are set to."""
+    sc = scenes.polydisperse_pile(60000, seed=131, vmax=5.0)
+    want = None
+    for opts in ({}, {"gs_slice": 64}, {"gs_slice": 512}, {"defer_state": 0}):
+        p = gs_store(state_from_scene(sc))
+        for k, v in opts.items():
+            p.set_option(k, v)
+        for _ in range(6):
+            p.Update(DT)
+            p.CollisionsCheck_Grid(sc.W, sc.H, DT)
+        got = gpu_state(p)
+        assert p.gs_fallbacks() == 0
+        p.Free()
+        if want is None:
+            want = got
+        else:
+            assert_state_bits(got, want, f"options {opts}")
+
+
 # ---- statistics against the compiled reference ----------------------------------------------------------------------
 def _reference_runs(sc, steps, dt):
     from oracle import oracle as om
