@@ -170,7 +170,7 @@ def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float =
     value = n * steps / dt
     sample = (f"{n} particles of the same generator and density ({sc.W}x{sc.H} box), {warmup} untimed + {steps} timed substeps, "
               f"1 thread of {os.cpu_count()} host cores (the reference is single-threaded)")
-    return value, dt / steps * 1e3, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample}
+    return value, dt / steps * 1e3, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "particles": n}
 
 
 def run_reference(args, rank: int):
@@ -179,7 +179,12 @@ def run_reference(args, rank: int):
     value, ms, base = time_reference_cpu(args.workload, args.steps, args.warmup, budget_s=170.0)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][1], "sample": base["sample"]},
+            "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][1], "sample": base["sample"],
+                                            "full_field": base["particles"] == WORKLOADS[args.workload][0],
+                                            "note": "the reference's CPU solver, one thread (it has no threads); the field is the full workload when "
+                                                    "(steps + warmup) substeps of it fit ~170 s (one 16M-particle substep takes ~16 s), else the largest "
+                                                    "power-of-two sample of the same generator and density that does (the full 16M-particle substep of "
+                                                    "tests/test_gpu_parity.py runs at ~1.0 M particle-substeps/s on the same host, the 2^20 sample at ~0.9 M)"},
             "cpu_baseline": base, "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)

@@ -123,10 +123,14 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *                  bit-exact, velocities agree with the reference as well as the reference agrees with itself under a
  *                  reordering of its list; one fused kernel, no dependency rounds,
  *              2 = Jacobi (one pass, diverges in dense packings), 0 = walls + grid only
+ *              The environment variable PPC_RESOLVE (0..3) sets the initial value of every store created afterwards: for programs
+ *              that only call the reference's six entry points.
  *   "gs_wc"    "resolve"=3: tile width in cells (0 = from the particle density, default).  Part of the pair order: the
  *              ranks of a multi-GPU field must all use the same value
  *   "gs_dump"  "resolve"=3: 1 = every substep also dumps the pairs it resolves (ppc_debug_hot_pairs); test hook
  *   "gs_strip" "resolve"=3: staged particles above which a tile is cut into column strips (0 = the kernel's capacity, default)
+ *   "cell_ranks"   1 = the histogram pass also leaves every particle's rank inside its cell, so the counting sort places the
+ *              particles without a second round of atomics (default); 0 = the scatter hands the positions out itself
  *   "defer_state"  1 = the first pass of a substep writes only cell keys and the sorting gather applies the integrate + wall
  *              pass to the record it moves (default: 16 bytes per particle less traffic); 0 = the first pass writes the state
  *   "collide"  0 = auto (shared-memory tile kernel with fine x-bins), 1 = global-memory thread-per-particle kernel,

@@ -71,6 +71,8 @@ struct Store {
     uint32_t    *api_ids = nullptr;   // slab mode: global indices of the copied-back particles
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
+    bool         ranks_valid = false;  // K1 of this substep left per-cell ranks in sort_keys_a
+    int          opt_cell_ranks = 1;   // 0: the scatter hands out the positions inside a cell with its own atomics (round 1)
     bool         hist_clean = false;   // cell_count is all zeros (the counting-sort scatter counts it back down): K1 need not clear it
     size_t       cells_cap = 0;
     uint32_t    *scratch = nullptr;
@@ -482,6 +484,15 @@ static Store *new_store( const struct Particles_t *p, bool owns_host ) {
         st->h_active_dma[ k ] = 0;
     st->h_active[ 1 ] = st->h_active[ 2 ] = st->h_active[ 3 ] = st->h_active[ 4 ] = 0;
     resize_particle_arrays( st, p->size, 0 );
+    // A program that only knows the reference's six entry points (main.c, examples/headless_scene.c) chooses the resolve from outside
+    if ( const char *e = getenv( "PPC_RESOLVE" ) ) {
+        const int v = atoi( e );
+        if ( v < 0 || v > 3 ) {
+            fprintf( stderr, "particlephysicsc_b200: PPC_RESOLVE=%s (expected 0..3)\n", e );
+            abort();
+        }
+        st->opt_resolve = v;
+    }
     g_stores.push_back( st );
     return st;
 }
@@ -594,8 +605,11 @@ static void launch_integrate( Store *st, const StepParams &P ) {
         PPC_CK( cudaMemsetAsync( st->cell_count, 0, st->cells_cap * sizeof( uint32_t ), st->stream ) );
     if ( P.do_walls_keys && P.do_histogram )
         st->hist_clean = false;
+    // counting-sort mode: K1 also leaves every particle's rank inside its cell (in the radix engine's idle key buffer)
+    uint32_t *ranks = ( P.do_walls_keys && P.do_histogram && st->opt_sort == 0 && st->opt_cell_ranks ) ? st->sort_keys_a : nullptr;
+    st->ranks_valid = ranks != nullptr;
     PPC_LAUNCH( k_integrate_walls_keys, div_up( st->n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, st->set[ st->cur ], st->cell_count,
-                st->n, P );
+                st->n, P, ranks );
 }
 
 // particlesUpdate on its own (no collisions check follows, or the host wants to look at the result).
@@ -643,6 +657,11 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
             const int where = radix_sort_pairs( st->sort_keys_a, st->slot_of, st->sort_keys_b, st->sort_vals_b, true, n,
                                                 bits_for( (uint32_t)bins ), st->scratch, st->stream );
             slot_of         = where ? st->sort_vals_b : st->slot_of;
+        } else if ( st->ranks_valid && first == 0 ) {   // K1 ranked the particles inside their cells: no atomics here
+            PPC_LAUNCH( k_cell_place, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, (const uint32_t *)st->sort_keys_a, st->cell_count,
+                        st->cell_start, st->slot_of, n );
+            st->hist_clean  = true;
+            st->ranks_valid = false;
         } else {   // counts the histogram back down to zero
             PPC_LAUNCH( k_cell_scatter, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, st->cell_count, st->cell_start,
                         st->slot_of, n );
@@ -1230,6 +1249,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_dump = (int)value;
     else if ( !strcmp( name, "gs_slice" ) )
         st->opt_gs_slice = (int)value;
+    else if ( !strcmp( name, "cell_ranks" ) )
+        st->opt_cell_ranks = (int)value;
     else if ( !strcmp( name, "defer_state" ) )
         st->opt_defer_state = (int)value;
     else
@@ -1532,7 +1553,7 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     P.wall_w = st->slab_wall_w, P.wall_h = st->slab_wall_h, P.grid = st->slab_world;
     if ( n ) {
         StageTimer T( st, ST_INTEGRATE );
-        PPC_LAUNCH( k_integrate_walls_keys, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->cell_count, n, P );
+        PPC_LAUNCH( k_integrate_walls_keys, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->cell_count, n, P, (uint32_t *)nullptr );
     }
     st->col_valid = colour != 0;
     {

@@ -29,8 +29,10 @@ struct StepParams {
 // ---- K1: integrate + wall-constrain + cell key + warp-aggregated cell histogram ------------------------------
 // One thread per storage slot; 128-bit load/store of (p_x, p_y, v_x, v_y).  Algorithmic traffic: 20 B read
 // (pv + radius; mass only when colouring) + 4 B key (+ 16 B write unless the gather applies the state, P.defer_state).
+// With cell_rank given, every particle also keeps what its cell's counter read when it was counted: its (arbitrary but unique) rank
+// inside the cell, so the counting sort needs no second round of atomics (k_cell_place).
 __global__ void __launch_bounds__( STREAM_THREADS ) k_integrate_walls_keys( ParticleSet S, uint32_t *__restrict__ cell_count, const size_t n,
-                                                                            const StepParams P ) {
+                                                                            const StepParams P, uint32_t *__restrict__ cell_rank ) {
     const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     const bool     valid = k < n;
     const unsigned lane  = threadIdx.x & 31u;
@@ -54,9 +56,16 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_integrate_walls_keys( Part
             S.pv[ k ] = s;
     }
     if ( P.do_walls_keys && P.do_histogram ) {   // whole warp arrives here: lanes of one cell elect a leader that adds their count
-        const unsigned peers = __match_any_sync( 0xffffffffu, key );
-        if ( valid && lane == (unsigned)( __ffs( peers ) - 1 ) )
-            atomicAdd( &cell_count[ key ], (uint32_t)__popc( peers ) );
+        const unsigned peers  = __match_any_sync( 0xffffffffu, key );
+        const unsigned leader = (unsigned)( __ffs( peers ) - 1 );
+        uint32_t       base   = 0;
+        if ( valid && lane == leader )
+            base = atomicAdd( &cell_count[ key ], (uint32_t)__popc( peers ) );
+        if ( cell_rank ) {
+            base = __shfl_sync( 0xffffffffu, base, leader );
+            if ( valid )
+                cell_rank[ k ] = base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) );
+        }
     }
 }
 
@@ -100,6 +109,20 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_cell_scatter( const uint32
     base = __shfl_sync( peers, base, leader );
     if ( valid )
         slot_of[ cell_start[ c ] + base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) ) ] = (uint32_t)k;
+}
+
+// K5 when K1 left ranks: sorted position = cell start + rank, no atomics.  The particle of rank 0 clears its cell's histogram entry
+// (every non-empty cell has exactly one), so the histogram is all zeros again for the next substep.
+__global__ void __launch_bounds__( STREAM_THREADS ) k_cell_place( const uint32_t *__restrict__ key, const uint32_t *__restrict__ cell_rank,
+                                                                  uint32_t *__restrict__ cell_count, const uint32_t *__restrict__ cell_start,
+                                                                  uint32_t *__restrict__ slot_of, const size_t n ) {
+    const size_t k = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    if ( k >= n )
+        return;
+    const uint32_t c = key[ k ], r = cell_rank[ k ];
+    slot_of[ cell_start[ c ] + r ] = (uint32_t)k;
+    if ( r == 0 )
+        cell_count[ c ] = 0u;
 }
 
 // ---- K6: canonicalise + gather ------------------------------------------------------------------------------

@@ -91,6 +91,7 @@ constexpr int      GS_BUCKETS  = 256;                 // levels a sub-tile's pai
 constexpr int      GS_MAXSTRIPS = 64;                 // descriptor slots per tile (a strip is at least one column, a tile <= 62)
 constexpr int      GS_MC_PAD   = 8;                   // mass/column words are copied from an 8-element (16-byte) boundary
 constexpr uint32_t GS_NONE     = 0xffffu;
+constexpr int      GS_FEW      = 256;                 // contact entries up to which a sub-tile takes the few-contacts path to its levels
 constexpr uint32_t GS_LAST_STRIP = 0x80000000u;
 constexpr uint32_t GS_HDR_UNITS = ( 2 * ( GS_R + 2 ) + 1 + 3 ) / 4;   // 21 words
 constexpr uint32_t GS_ERR_CAP = 1u, GS_ERR_POOL = 2u, GS_ERR_DEPTH = 4u, GS_ERR_CHUNK = 8u;
@@ -295,6 +296,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             T.err       = 0u;
             T.pool_n    = 0u;
             T.phase_mask = 0u;
+            T.n_owned    = 0u;
         }
         if ( j < 4 )
             T.kcnt[ j ] = 0u;
@@ -670,7 +672,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
     constexpr uint32_t SEG_CAP = ( sizeof( T.fend ) + sizeof( T.perm ) ) / sizeof( uint16_t );
     // phase of the pairs a cell lists under direction code d * 3 + dc: class by the direction as seen from the base cell, parity of
     // the base cell's whole-field column (east) or row (the southward classes)
-    auto phase_of = [ & ]( const uint32_t code ) -> uint32_t {
+    auto phase_at = [ & ]( const uint32_t code, const int xj, const int xc ) -> uint32_t {   // (xj, xc): staged cell of the listing particle
         const int  dj = (int)( code / 3u ) - 1, dcl = (int)( code % 3u ) - 1;
         const bool fwd = dj > 0 || ( dj == 0 && dcl >= 0 );                    // this cell is the base
         const int  bj = fwd ? xj : xj + dj, bc = fwd ? xc : xc + dcl;          // base cell
@@ -679,6 +681,56 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         const int  par = cls == 1 ? ( ( c0 + bc ) & 1 ) : ( ( row_g0 + bj ) & 1 );
         return cls == 0 ? 0u : (uint32_t)( 2 * cls - 1 + par );
     };
+    auto phase_of = [ & ]( const uint32_t code ) -> uint32_t { return phase_at( code, xj, xc ); };
+    const bool few = T.pool_n <= (uint32_t)GS_FEW;
+    if ( few ) {
+        // ---- a sub-tile with a handful of contacts (every sub-tile of a dilute field): the same order and levels without the per-cell machinery ----
+        // Every owned pair gets the key {phase, listing particle, position in its list}: pairs of one phase that share a particle belong
+        // to one cell pair, whose order is exactly (particle, position); pairs that share none may come in any order.  Rank by
+        // counting, then one thread assigns the levels in rank order.
+        uint32_t *skey = reinterpret_cast<uint32_t *>( T.fend + GS_CAP );       // behind `order` (GS_CAP 16-bit words), inside fend
+        uint16_t *sent = T.fend + GS_CAP + 2 * GS_FEW;
+        static_assert( ( GS_CAP + 3 * GS_FEW ) * 2 <= (int)sizeof( T.fend ), "keys and entry numbers of the few-contacts path live in fend" );
+        for ( uint32_t u = threadIdx.x; u < with_contacts; u += GS_THREADS ) {
+            const uint32_t ov = order[ u ], self = ov & 0x3ffu;
+            const int      pj = (int)( ov >> 10 ), pc = ( (int)T.colb[ self ] - c0 ) & 0xff;
+            uint32_t       pos = 0;
+            for ( uint32_t e = T.head[ self ]; e != GS_NONE; pos++ ) {
+                const uint32_t nxt = T.pool_next[ e ], v = T.pool_val[ e ];
+                if ( v & 0x8000u ) {
+                    const uint32_t at = atomicAdd( &T.n_owned, 1u );
+                    skey[ at ] = ( phase_at( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ), pj, pc ) << 20 ) | ( self << 10 ) | ( pos < 1023u ? pos : 1023u );
+                    sent[ at ] = (uint16_t)e;
+                    T.pool_next[ e ] = (uint16_t)self;   // the entry remembers its anchor where its link was
+                }
+                e = nxt;
+            }
+        }
+        __syncthreads();
+        const uint32_t P = T.n_owned;
+        for ( uint32_t i = threadIdx.x; i < P; i += GS_THREADS ) {
+            const uint32_t k = skey[ i ];
+            uint32_t       rank = 0;
+            for ( uint32_t o = 0; o < P; o++ )
+                rank += skey[ o ] < k ? 1u : 0u;
+            seg[ rank ] = sent[ i ];   // (`order` is dead: every list has been walked)
+        }
+        __syncthreads();
+        if ( threadIdx.x == 0 )
+            for ( uint32_t r = 0; r < P; r++ ) {
+                const uint32_t e = seg[ r ], a = T.pool_next[ e ], q = T.pool_val[ e ] & 0x7ffu;
+                uint32_t       lv = max( (uint32_t)T.lvl[ a ], (uint32_t)T.lvl[ q ] ) + 1u;
+                if ( lv >= (uint32_t)GS_BUCKETS ) {
+                    T.err = GS_ERR_DEPTH;
+                    lv    = GS_BUCKETS - 1;
+                }
+                T.lvl[ a ]      = (uint8_t)lv;
+                T.lvl[ q ]      = (uint8_t)lv;
+                T.pool_aux[ e ] = (uint16_t)lv;
+                T.bcount[ lv ]++;
+            }
+        __syncthreads();
+    } else {
     // (a) this cell's pairs per direction code: nine 7-bit counters in one word
     unsigned long long cnt = 0ull;
     uint32_t           mine = 0;
@@ -790,6 +842,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         }
         __syncthreads();
     }
+    }   // (the per-cell path)
     if ( T.err ) {
         if ( threadIdx.x == 0 ) {
             atomicOr( err_flags, T.err );
