@@ -53,7 +53,7 @@ def test_reference_arm_line_shape(monkeypatch, capsys):
     sys.path.insert(0, ROOT)
     import json
     import bench
-    base = {"value": 1.0e5, "unit": bench.UNIT, "cores": 1, "kind": "reference", "sample": "stub"}
+    base = {"value": 1.0e5, "unit": bench.UNIT, "cores": 1, "kind": "reference", "sample": "stub", "particles": 1 << 20}
     monkeypatch.setattr(bench, "time_reference_cpu", lambda *a, **k: (1.0e5, 10.0, base))
 
     class A:
@@ -62,6 +62,6 @@ def test_reference_arm_line_shape(monkeypatch, capsys):
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["unit"] == bench.UNIT
     assert line["e2e"] == {"value": 1.0e5, "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert line["cpu_baseline"]["kind"] == "reference" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "reference" and line["higher_is_better"] is True and line["config"]["full_field"] is False
     bench.run_reference(A, 1)   # other ranks print nothing
     assert capsys.readouterr().out == ""
