@@ -129,6 +129,10 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *              ranks of a multi-GPU field must all use the same value
  *   "gs_dump"  "resolve"=3: 1 = every substep also dumps the pairs it resolves (ppc_debug_hot_pairs); test hook
  *   "gs_strip" "resolve"=3: staged particles above which a tile is cut into column strips (0 = the kernel's capacity, default)
+ *   "gs_merge" "resolve"=3: 1 = the velocity passes of the four tile colours run in ONE launch, a tile starting as soon as its
+ *              neighbouring tiles of lower colour are done; 0 = one launch per colour (default: measured within 3 % of each
+ *              other either way).  "gs_slice": records per slice of
+ *              the velocity kernel's record stream (0 = chosen from the pair density).  Neither changes any result
  *   "cell_ranks"   1 = the histogram pass also leaves every particle's rank inside its cell, so the counting sort places the
  *              particles without a second round of atomics (default); 0 = the scatter hands the positions out itself
  *   "defer_state"  1 = the first pass of a substep writes only cell keys and the sorting gather applies the integrate + wall

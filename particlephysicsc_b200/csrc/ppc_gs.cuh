@@ -137,6 +137,12 @@ struct GsLaunch {
     int ty_start;    // k_gs_resolve: first local tile row of this colour
     int strip_limit; // staged particles (strip + halo) above which a tile is cut into strips, and which a strip may hold (<= GS_CAP)
     int slice_log2;  // k_gs_resolve: log2 of the pair records per slice of a chunk (dynamic shared memory: GSB_NBUF * slice * 16 bytes)
+    // k_gs_resolve, all four colours in ONE launch (merged != 0): CTAs take tickets; ticket t runs tile number t of the colour-major
+    // list (col_begin[c] <= t < col_begin[c + 1]: colour c) once its neighbouring tiles of lower colour have reported done
+    int      merged, tiles_y;
+    int      col_ntx[ 4 ], col_ty_start[ 4 ];
+    uint32_t col_begin[ 5 ];
+    uint32_t epoch;   // value of a done[] word that means "done in THIS substep" (the words are never cleared)
 };
 
 // Pair records of one substep: one chunk per sub-tile, allocated with one atomic add, in units of 16 bytes:
@@ -1004,14 +1010,44 @@ struct GsbSmem {
 };
 
 __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *__restrict__ mcol, float4 *pv, const GsLaunch L, const GsPairs PR,
-                                                                const uint32_t *__restrict__ err_flags ) {
+                                                                const uint32_t *__restrict__ err_flags, uint32_t *__restrict__ ticket,
+                                                                uint32_t *done ) {
     __shared__ __align__( 16 ) GsbSmem T;
+    __shared__ uint32_t s_ticket;
     extern __shared__ __align__( 16 ) uint4 gsb_recs[];   // ring of GSB_NBUF slices of the record chunk, L.slice records each
     const uint32_t SL = (uint32_t)L.slice_log2, GSB_SLICE = 1u << SL;
     if ( *err_flags )   // some sub-tile did not fit: the host runs the exact resolve for this substep instead
         return;
-    const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
-    const int tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;   // ty: tile row inside this grid
+    int tx, ty;   // ty: tile row inside this grid
+    if ( L.merged ) {
+        // Tickets are handed out in colour-major order and a CTA only ever waits for tiles of LOWER colour, i.e. for lower tickets,
+        // whose CTAs are already running: no deadlock whatever order the hardware starts CTAs in.
+        if ( threadIdx.x == 0 )
+            s_ticket = atomicAdd( ticket, 1u );
+        __syncthreads();
+        const uint32_t t = s_ticket;
+        // (selected with constant indices: a dynamically indexed kernel parameter would be copied to local memory)
+        const int      c = t >= L.col_begin[ 3 ] ? 3 : ( t >= L.col_begin[ 2 ] ? 2 : ( t >= L.col_begin[ 1 ] ? 1 : 0 ) );
+        const uint32_t i = t - ( c == 3 ? L.col_begin[ 3 ] : ( c == 2 ? L.col_begin[ 2 ] : ( c == 1 ? L.col_begin[ 1 ] : 0u ) ) );
+        const unsigned ntx = (unsigned)( c == 3 ? L.col_ntx[ 3 ] : ( c == 2 ? L.col_ntx[ 2 ] : ( c == 1 ? L.col_ntx[ 1 ] : L.col_ntx[ 0 ] ) ) );
+        const int      ty0 = c == 3 ? L.col_ty_start[ 3 ] : ( c == 2 ? L.col_ty_start[ 2 ] : ( c == 1 ? L.col_ty_start[ 1 ] : L.col_ty_start[ 0 ] ) );
+        const int      bx = (int)( i % ntx ), by = (int)( i / ntx );
+        tx = 2 * bx + ( c & 1 ), ty = 2 * by + ty0;
+        if ( threadIdx.x < 8 ) {   // one lane per neighbouring tile
+            const int k = (int)threadIdx.x, ddx = k < 3 ? k - 1 : ( k == 3 ? -1 : ( k == 4 ? 1 : k - 6 ) ), ddy = k < 3 ? -1 : ( k < 5 ? 0 : 1 );
+            const int nx = tx + ddx, ny = ty + ddy;
+            if ( nx >= 0 && nx < L.tiles_x && ny >= 0 && ny < L.tiles_y && ( ( nx & 1 ) | ( ( ( L.ty_first + ny ) & 1 ) << 1 ) ) < c ) {
+                const volatile uint32_t *flag = done + (size_t)ny * L.tiles_x + nx;
+                while ( *flag != L.epoch )
+                    __nanosleep( 100 );
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    } else {
+        const int bx = (int)( blockIdx.x % (unsigned)L.ntx ), by = (int)( blockIdx.x / (unsigned)L.ntx );
+        tx = 2 * bx + ( L.colour & 1 ), ty = 2 * by + L.ty_start;
+    }
     const uint2 *desc = PR.desc + ( (size_t)ty * L.tiles_x + tx ) * GS_MAXSTRIPS;
     uint32_t     parity = 0u;   // bit i: phase of the barrier of ring buffer i
     bool         ready = false;
@@ -1160,6 +1196,12 @@ __global__ void __launch_bounds__( GSB_THREADS ) k_gs_resolve( const uint16_t *_
         }
         if ( d.y & GS_LAST_STRIP )
             break;
+    }
+    if ( L.merged ) {   // everything this tile wrote is visible before its flag is
+        __threadfence();
+        __syncthreads();
+        if ( threadIdx.x == 0 )
+            *( (volatile uint32_t *)( done + (size_t)ty * L.tiles_x + tx ) ) = L.epoch;
     }
 }
 
