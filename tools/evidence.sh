@@ -14,12 +14,12 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --settle 8 --steps 2 --warmup 3 --no-other-configs --no-cpu-baseline > $O/${TAG}_ncu_launches_bench.log 2>&1
 for w in pile16m uniform16m; do
     timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
-        --log-file $O/${TAG}_ncu_traffic_$w.csv python tools/profile_substeps.py --workload $w --resolve 3 --settle 8 --steps 2 > $O/${TAG}_ncu_traffic_$w.log 2>&1
+        --log-file $O/${TAG}_ncu_traffic_$w.csv python tools/profile_substeps.py --workload $w --resolve 3 --settle 64 --steps 2 > $O/${TAG}_ncu_traffic_$w.log 2>&1
 done
 if [ "$2" = "full" ]; then
     for w in pile16m uniform16m; do
-        timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gs_ --launch-skip 45 --launch-count 5 -o $O/${TAG}_full_$w -f \
-            python tools/profile_substeps.py --workload $w --resolve 3 --settle 8 --steps 2 > $O/${TAG}_full_$w.log 2>&1
+        timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gs_ --launch-skip 325 --launch-count 5 -o $O/${TAG}_full_$w -f \
+            python tools/profile_substeps.py --workload $w --resolve 3 --settle 64 --steps 2 > $O/${TAG}_full_$w.log 2>&1
     done
 fi
 ls -la $O | grep ${TAG}_

@@ -91,7 +91,7 @@ def main():
     traffic_path = os.path.join(P, f"{out}_traffic.json")
     traffic = {"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per substep and stage (bytes; a stage launched several times per substep is summed), "
                            "last substep of `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum python tools/profile_substeps.py "
-                           "--workload W --resolve 3 --settle 8 --steps 2`; tables in " + out + "_substep_<workload>.txt. bench.py copies the dominant "
+                           "--workload W --resolve 3 --settle 64 --steps 2` (the field relaxed as in bench.py); tables in " + out + "_substep_<workload>.txt. bench.py copies the dominant "
                            "kernel's figure into roofline.traffic and whole_substep into roofline_substep.traffic."}
     for w in ("pile16m", "uniform16m", "slab32m"):
         src = os.path.join(G, f"{tag}_ncu_traffic_{w}.csv")
@@ -123,7 +123,7 @@ def main():
         open(os.path.join(P, f"{out}_ncu_full_{w}.csv"), "w").write(s)
         s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_gs_sections.py"), rep], capture_output=True, text=True).stdout
         open(os.path.join(P, f"{out}_ncu_sections_k_gs_pairs_{w}.txt"), "w").write(s)
-        s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), rep, "40", "inst"], capture_output=True, text=True).stdout
+        s = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_source_summary.py"), rep, "40", "inst", "k_gs_pairs"], capture_output=True, text=True).stdout
         open(os.path.join(P, f"{out}_ncu_source_k_gs_pairs_{w}.txt"), "w").write(s)
     print("written:", sorted(x for x in os.listdir(P) if x.startswith(out + "_")))
 

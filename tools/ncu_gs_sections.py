@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Shares of k_gs_pairs by phase (line ranges found from the comment markers of ppc_gs.cuh): python tools/ncu_gs_sections.py rep"""
+"""Shares of k_gs_pairs by phase (line ranges found from the comment markers of ppc_gs.cuh): python tools/ncu_gs_sections.py rep [kernel]"""
 import collections, os, subprocess, sys
 rep = sys.argv[1]
 here = os.path.dirname(os.path.abspath(__file__))
@@ -10,7 +10,8 @@ for i, l in enumerate(src, 1):
     if t.startswith("// ---- ") or t.startswith("// (a)") or t.startswith("// (b)") or t.startswith("// (c)") or t.startswith("// exclusive scan of the level") \
             or t.startswith("__global__") or t.startswith("__device__ __forceinline__ void gs_pairs_subtile"):
         marks.append((i, t[:70]))
-out = subprocess.run([sys.executable, os.path.join(here, "ncu_source_summary.py"), rep, "100000", "inst"], capture_output=True, text=True).stdout
+kernel = sys.argv[2] if len(sys.argv) > 2 else "k_gs_pairs"   # the first launch of this kernel in the report
+out = subprocess.run([sys.executable, os.path.join(here, "ncu_source_summary.py"), rep, "100000", "inst", kernel], capture_output=True, text=True).stdout
 agg = collections.OrderedDict((n, [0, 0, 0]) for _, n in marks)
 agg["ppc_math.cuh"] = [0, 0, 0]
 agg["other files"] = [0, 0, 0]
