@@ -21,18 +21,21 @@
 //  2. A pair belongs to the sub-tile (tile, strip) holding both particles, else to the EARLIER of the two sub-tiles
 //     (lower colour; inside a tile the lower strip).  The owner applies the impulse to both particles; what it did to a
 //     halo particle is in global memory before that particle's own sub-tile runs.
-//  3. Inside a sub-tile, nine phases: pairs inside one cell; pairs with the east neighbour cell, base column even / odd;
-//     with the south, south-east, south-west neighbour, base row even / odd.  The cell pairs of one phase are disjoint.
-//  4. Inside a cell pair: by anchor particle (ascending index), then by position in the anchor's contact list.
+//  3. Inside a sub-tile the pairs are EDGE-COLOURED greedily: they are visited in a fixed order -- nine phases of disjoint cell
+//     pairs (pairs inside one cell; pairs with the east neighbour cell, base column even / odd; with the south, south-east,
+//     south-west neighbour, base row even / odd); inside a cell pair by listing particle (ascending index), then by position in
+//     its contact list -- and each takes the lowest pair-colour (0..31) that no earlier pair has used at either of its particles.
+//  4. The sub-tile's pairs fire colour by colour.  Pairs of one colour share no particle, so their mutual order is immaterial.
+//     (Round 2 first fired them by "level" = 1 + the level of the previous pair of either particle in the visiting order: the
+//     same passes, but ~14 dependent steps per sub-tile of a dense pile where the colouring needs ~8.)
 //
 // Execution.  Positions do not depend on velocities, so the work splits into two kernels:
 //   k_gs_pairs   (all tiles at once)  stages a tile and its halo, finds the contacts of every centre particle, adds its
 //                position pushes in the reference's order, and writes the pairs the sub-tile owns as 16-byte records
-//                {particle numbers, unit normal, Baumgarte term} into one contiguous chunk per sub-tile, sorted by
-//                LEVEL = 1 + the level of the previous pair of either particle in the order above.  Pairs of one level share no particle.
-//   k_gs_resolve (one launch per colour)  loads the current velocities of a sub-tile and its halo, then fires the records
-//                level by level, one thread per pair, and writes back what changed.  Each particle receives its impulses
-//                in exactly the order of 3. and 4., so the result is the sequential one.
+//                {particle numbers, unit normal, Baumgarte term} into one contiguous chunk per sub-tile, sorted by pair-colour.
+//   k_gs_resolve (one launch per tile colour)  loads the current velocities of a sub-tile and its halo, then fires the records
+//                colour by colour, one thread per pair, and writes back what changed: the sequential pass 2 of the reference
+//                over the pair list in the order (tile colour, sub-tile, pair-colour).
 //
 // Data movement: the canonical gather (ppc_grid.cuh) leaves, besides the ordinary sorted state, one 16-byte record
 // {x, y, radius, API index} and one 16-bit word {mass byte, cell column byte} per particle in sorted order, so the GS_R + 2
@@ -87,7 +90,7 @@ constexpr int      GS_MAXC     = 64;                  // staged columns (centre 
 constexpr int      GS_NB       = GS_MAXC * GS_F;      // fine bins per staged row
 constexpr int      GS_BINS     = ( GS_R + 2 ) * GS_NB;
 constexpr int      GS_STRIP_LIMIT = GS_CAP;           // staged particles (strip + halo) a strip may hold
-constexpr int      GS_BUCKETS  = 256;                 // levels a sub-tile's pairs may span (level 0 is unused)
+constexpr int      GS_BUCKETS  = 64;                  // buckets of the record chunk: colour + 1 of a pair (32 colours; bucket 0 is unused)
 constexpr int      GS_MAXSTRIPS = 64;                 // descriptor slots per tile (a strip is at least one column, a tile <= 62)
 constexpr int      GS_MC_PAD   = 8;                   // mass/column words are copied from an 8-element (16-byte) boundary
 constexpr uint32_t GS_NONE     = 0xffffu;
@@ -110,7 +113,6 @@ struct GsSmem {
     uint8_t  colb[ GS_CAP ];        // cell column byte of every staged particle
     uint8_t  massb[ GS_CAP ];       // mass byte (:141-142)
     uint16_t head[ GS_CAP ];        // first contact entry of a centre particle
-    uint8_t  lvl[ GS_CAP ];         // level of the latest pair of every staged particle
     uint16_t ord[ GS_CAP ];         // centre particle t: staged index [9:0] | staged row << 10
     uint16_t perm2[ GS_CAP ];       // centre particle t: rank inside its class of contact count
     uint8_t  kk[ GS_CAP ];          // centre particle t: number of contacts (saturating)
@@ -340,7 +342,6 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         T.inv_lut[ threadIdx.x ] = __fdiv_rn( 1.0f, (float)threadIdx.x );
     for ( uint32_t t = threadIdx.x; t < staged; t += GS_THREADS ) {
         T.head[ t ] = (uint16_t)GS_NONE;
-        T.lvl[ t ]  = 0;
     }
     for ( int b = threadIdx.x; b < GS_BUCKETS; b += GS_THREADS )
         T.bcount[ b ] = 0u;
@@ -571,6 +572,12 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             order[ ( k <= 2u ? n2 : ( k <= 4u ? n1 : ( k <= 7u ? n0 : 0u ) ) ) + T.perm2[ t ] ] = T.ord[ t ];
     }
     __syncthreads();
+    // colours in use at every staged particle (bit c: a pair of colour c of this sub-tile touches it); lives where ord / perm2 were
+    uint32_t *used = reinterpret_cast<uint32_t *>( T.ord );
+    static_assert( sizeof( T.ord ) + sizeof( T.perm2 ) >= GS_CAP * sizeof( uint32_t ) && offsetof( GsSmem, perm2 ) == offsetof( GsSmem, ord ) + sizeof( T.ord ) &&
+                       offsetof( GsSmem, ord ) % 4 == 0, "the colour masks alias ord + perm2" );
+    for ( uint32_t t = threadIdx.x; t < staged; t += GS_THREADS )
+        used[ t ] = 0u;
 
     // ---- one thread per centre particle with contacts: list into the reference's order, position pushes, who owns each pair ----
     for ( uint32_t u = threadIdx.x; u < with_contacts; u += GS_THREADS ) {
@@ -662,10 +669,10 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
     }
 
     // ---- the pairs this sub-tile owns, as records sorted by LEVEL ----
-    // The ORDER of the pairs is the nine phases of disjoint cell pairs described in the header.  Their EXECUTION (k_gs_resolve)
-    // is levelled: level(pair) = 1 + max(level of the previous pair of either particle in that order), a cheap integer pass
-    // done here; the pairs of one level share no particle and fire together, and every particle still receives its impulses in
-    // exactly the order of the phases.  A dense packing has ~70 (phase, position) steps per sub-tile but only ~15 levels.
+    // ("level" = pair-colour + 1 from here on.)  The pairs are VISITED in the nine phases of disjoint cell pairs described in the
+    // header and each takes the lowest colour free at both its particles, a cheap integer pass done here; the pairs of one colour
+    // share no particle and fire together in k_gs_resolve.  A dense packing has ~70 (phase, position) steps per sub-tile, ~14
+    // levels under list scheduling of that order, and ~8 colours.
     // One thread per staged cell (the host bounds the tile width accordingly).  All pairs of a cell pair are listed by particles
     // of ONE cell with ONE direction code (the base cell when it is inside the sub-tile, else the other one): ascending particle,
     // list order -- the order inside the cell pair.
@@ -725,13 +732,14 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         if ( threadIdx.x == 0 )
             for ( uint32_t r = 0; r < P; r++ ) {
                 const uint32_t e = seg[ r ], a = T.pool_next[ e ], q = T.pool_val[ e ] & 0x7ffu;
-                uint32_t       lv = max( (uint32_t)T.lvl[ a ], (uint32_t)T.lvl[ q ] ) + 1u;
-                if ( lv >= (uint32_t)GS_BUCKETS ) {
+                const uint32_t ua = used[ a ], uq = used[ q ], taken = ua | uq;
+                uint32_t       lv = (uint32_t)__ffs( (int)~taken );   // 1 + the lowest colour neither particle has used yet
+                if ( lv == 0u ) {   // 32 colours in use around this pair
                     T.err = GS_ERR_DEPTH;
-                    lv    = GS_BUCKETS - 1;
+                    lv    = 32u;
                 }
-                T.lvl[ a ]      = (uint8_t)lv;
-                T.lvl[ q ]      = (uint8_t)lv;
+                used[ a ]       = ua | ( 1u << ( lv - 1u ) );
+                used[ q ]       = uq | ( 1u << ( lv - 1u ) );
                 T.pool_aux[ e ] = (uint16_t)lv;
                 T.bcount[ lv ]++;
             }
@@ -835,13 +843,14 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             for ( uint32_t k = kb; k < ke; k++ ) {
                 const uint32_t e = seg[ k ];
                 const uint32_t a = T.pool_next[ e ], q = T.pool_val[ e ] & 0x7ffu;
-                uint32_t       lv = max( (uint32_t)T.lvl[ a ], (uint32_t)T.lvl[ q ] ) + 1u;
-                if ( lv >= (uint32_t)GS_BUCKETS ) {
+                const uint32_t ua = used[ a ], uq = used[ q ], taken = ua | uq;
+                uint32_t       lv = (uint32_t)__ffs( (int)~taken );   // 1 + the lowest colour neither particle has used yet
+                if ( lv == 0u ) {   // 32 colours in use around this pair
                     T.err = GS_ERR_DEPTH;
-                    lv    = GS_BUCKETS - 1;
+                    lv    = 32u;
                 }
-                T.lvl[ a ]      = (uint8_t)lv;
-                T.lvl[ q ]      = (uint8_t)lv;
+                used[ a ]       = ua | ( 1u << ( lv - 1u ) );
+                used[ q ]       = uq | ( 1u << ( lv - 1u ) );
                 T.pool_aux[ e ] = (uint16_t)lv;
                 atomicAdd( &T.bcount[ lv ], 1u );
             }

@@ -212,19 +212,39 @@ def test_thousand_substeps_within_one_percent_of_the_reference(oracle, phi, seed
 
 
 def test_thousand_substeps_on_the_dense_pile_within_the_references_own_spread(oracle):
-    n, steps, dt = 20000, 1000, 1.0 / 1152.0
+    """A chaotic, energy-injecting state: the bar is the reference's own sensitivity to its pair order,
+    measured in this same test (kinetic energy of the reference with its list reversed / shuffled against the reference as built:
+    1-17 % on this pile, largest in the first few hundred substeps and itself erratic from checkpoint to checkpoint, so the bar at
+    a checkpoint is the largest value seen up to it; tests/order_sensitivity.py, profiles/r02_order_sensitivity.txt)."""
+    from oracle import oracle as om
+    if not om.reference_available():
+        pytest.skip("oracle/_ref/libref.so not built")
+    n, dt, checkpoints = 20000, 1.0 / 1152.0, (100, 250, 500, 1000)
+    sensitivity = 0.0   # largest deviation of the reordered reference from the reference as built seen so far in this run
     sc = scenes.polydisperse_pile(n, seed=104, vmax=5.0)
     p = gs_store(state_from_scene(sc))
-    p.run_substeps(sc.W, sc.H, dt, steps)
-    got = gpu_state(p)
-    print(f"\ndense pile: {p.gs_fallbacks()} of {steps} substeps fell back to the exact resolve (a sub-tile overflowed the tile kernel)")
-    assert p.gs_fallbacks() < steps // 4
+    R = om.Reference()
+    refs = {label: state_from_scene(sc) for label in ("as built", "reversed", "shuffled")}
+    done = 0
+    for upto in checkpoints:
+        p.run_substeps(sc.W, sc.H, dt, upto - done)
+        got = gpu_state(p)
+        assert np.isfinite(got.px).all() and np.isfinite(got.py).all() and np.isfinite(got.vx).all() and np.isfinite(got.vy).all()
+        for label, mode in (("as built", 0), ("reversed", 1), ("shuffled", 2)):
+            R.set_pair_order(mode, 7)
+            try:
+                for _ in range(upto - done):
+                    R.substep(refs[label], sc.W, sc.H, dt)
+            finally:
+                R.set_pair_order(0)
+        done = upto
+        dev, spread = _report(oracle, sc, got, refs, f"dense pile, {upto} substeps")
+        sensitivity = max(sensitivity, spread["reversed"]["ke"], spread["shuffled"]["ke"])
+        assert dev["ke"] <= sensitivity, (f"substep {upto}: kinetic energy off by {100 * dev['ke']:.2f}%, more than the reference moves under a "
+                                          f"reordering of its own pair list anywhere in this run ({100 * sensitivity:.2f}%)")
+    print(f"\ndense pile: {p.gs_fallbacks()} of {done} substeps fell back to the exact resolve (a sub-tile overflowed the tile kernel)")
+    assert p.gs_fallbacks() < done // 4
     p.Free()
-    assert np.isfinite(got.px).all() and np.isfinite(got.py).all() and np.isfinite(got.vx).all() and np.isfinite(got.vy).all()
-    dev, spread = _report(oracle, sc, got, _reference_runs(sc, steps, dt), f"dense pile, {steps} substeps")
-    worst = max(spread["reversed"]["ke"], spread["shuffled"]["ke"])
-    # a chaotic, energy-injecting state: the bar is the reference's own sensitivity to its pair order
-    assert dev["ke"] <= 2.0 * worst + 0.01, f"kinetic energy off by {100 * dev['ke']:.2f}%, the reference's own spread is {100 * worst:.2f}%"
 
 
 def test_sixteen_million_pile_stays_finite_for_a_thousand_substeps():

@@ -48,8 +48,8 @@ def test_order_is_a_permutation_and_positions_are_the_references(oracle, make, w
 
 def test_order_follows_the_documented_rule_on_a_hand_made_field(oracle):
     """Four particles in a row across a tile border, wc = 2: tile 0 = columns 0-1 (colour 0), tile 1 = columns 2-3 (colour 1).
-    Pairs: (0,1) inside tile 0, (1,2) across the border -> owned by tile 0, (2,3) inside tile 1.  East-neighbour pairs run
-    base-column-even first: (0,1) has base column 0, (1,2) base column 1, so tile 0 runs (0,1) then (1,2); tile 1 then (2,3)."""
+    Pairs: (0,1) inside tile 0, (1,2) across the border -> owned by tile 0, (2,3) inside tile 1.  East-neighbour pairs are visited
+    base-column-even first (and here the greedy pair-colours follow the visiting order): (0,1) has base column 0, (1,2) base column 1, so tile 0 runs (0,1) then (1,2); tile 1 then (2,3)."""
     from oracle.oracle import State
     n = 4
     x = np.array([11.0, 13.5, 25.5, 37.0], np.float32)   # cells 0, 1, 2, 3 at cell size 12; overlapping neighbours (r = 6... see radius)
@@ -66,6 +66,27 @@ def test_order_follows_the_documented_rule_on_a_hand_made_field(oracle):
     # with the border between cells 0|1 instead (wc = 1 is not allowed on the device, but the rule is the same): wc = 3 puts
     # cells 0-2 in tile 0 and cell 3 in tile 1 (colour 1): (2,3) crosses, owned by tile 0, base column 2 (even) -> before (1,2)
     perm = oracle.tilegs_order(res["pairs"], dict(keys=res["keys"], cell_start=res["cell_start"], cols=cols, rows=rows), n, 3, 8, 921)
+    assert [pairs[k] for k in perm] == [[0, 1], [2, 3], [1, 2]]
+
+
+def test_pairs_run_by_greedy_colour_not_in_visiting_order(oracle):
+    """Pairs are VISITED in the nine phases and take the lowest pair-colour free at both particles; they RUN colour by colour.
+    One tile (wc = 4): particles 0, 1, 2 in cells 0, 1, 2 of one row, particle 3 in the cell south of cell 2.  Visiting order:
+    (0,1) [east, base column 0] colour 0; (1,2) [east, base column 1]: particle 1 has used colour 0 -> colour 1; (2,3) [south]:
+    particle 2 has used colour 1 only, particle 3 nothing -> colour 0.  So (2,3) runs BEFORE (1,2) although it is visited later
+    (list scheduling of the visiting order would have needed three dependent steps here, the colouring needs two)."""
+    from oracle.oracle import State
+    n = 4
+    x = np.array([11.0, 13.5, 25.5, 25.5], np.float32)
+    y = np.array([30.0, 30.0, 30.0, 41.0], np.float32)
+    r = np.array([1.5, 6.0, 6.0, 6.0], np.float32)
+    s = State(x, y, np.zeros(n, np.float32), np.zeros(n, np.float32), np.full(n, 5.0, np.float32), r, np.zeros((n, 4), np.uint8))
+    oracle.set_tilegs(4, 8, 921)
+    res = oracle.collisions_check_grid(s.copy(), 200, 100, DT, mode=0, want_grid=True)
+    pairs = res["pairs"].tolist()
+    assert pairs == [[0, 1], [1, 2], [2, 3]]
+    cs, cols, rows = oracle.grid_dims(s, 200, 100)
+    perm = oracle.tilegs_order(res["pairs"], dict(keys=res["keys"], cell_start=res["cell_start"], cols=cols, rows=rows), n, 4, 8, 921)
     assert [pairs[k] for k in perm] == [[0, 1], [2, 3], [1, 2]]
 
 
