@@ -133,6 +133,7 @@ void ppc_run_substeps( struct Particles_t *p, uint16_t window_width, uint16_t wi
  *              neighbouring tiles of lower colour are done; 0 = one launch per colour (default: measured within 3 % of each
  *              other either way).  "gs_slice": records per slice of
  *              the velocity kernel's record stream (0 = chosen from the pair density).  Neither changes any result
+ *   "scan_single"  1 = the cell-start table is scanned in one launch (decoupled look-back; default); 0 = reduce / scan / apply
  *   "cell_ranks"   1 = the histogram pass also leaves every particle's rank inside its cell, so the counting sort places the
  *              particles without a second round of atomics (default); 0 = the scatter hands the positions out itself
  *   "defer_state"  1 = the first pass of a substep writes only cell keys and the sorting gather applies the integrate + wall

@@ -71,6 +71,10 @@ struct Store {
     uint32_t    *api_ids = nullptr;   // slab mode: global indices of the copied-back particles
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
+    int          opt_scan_single = 1;  // cell-start scan in one launch (decoupled look-back); 0: reduce / scan / apply (three launches)
+    unsigned long long *scan_desc = nullptr;   // [0]: ticket counter, [1..]: tile descriptors of the single-pass scan
+    size_t       scan_desc_cap = 0;
+    uint32_t     scan_epoch = 0;
     bool         ranks_valid = false;  // K1 of this substep left per-cell ranks in sort_keys_a
     int          opt_cell_ranks = 1;   // 0: the scatter hands out the positions inside a cell with its own atomics (round 1)
     bool         hist_clean = false;   // cell_count is all zeros (the counting-sort scatter counts it back down): K1 need not clear it
@@ -654,7 +658,24 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
     const ParticleSet &B = st->set[ st->cur ^ 1 ];
     {
         StageTimer T( st, ST_SCAN );                                                   // K4 cell-start table
-        exclusive_scan( st->cell_count, st->cell_start, bins + 1, st->scratch, st->stream );
+        if ( st->opt_scan_single ) {   // one launch (decoupled look-back)
+            const size_t tiles = div_up( bins + 1, SCAN_TILE );
+            if ( tiles + 1 > st->scan_desc_cap ) {
+                PPC_CK( cudaStreamSynchronize( st->stream ) );
+                cudaFree( st->scan_desc );
+                st->scan_desc_cap = tiles + 1 + tiles / 8;
+                st->scan_desc     = dev_alloc<unsigned long long>( st->scan_desc_cap + 1 );
+                PPC_CK( cudaMemsetAsync( st->scan_desc, 0, ( st->scan_desc_cap + 1 ) * sizeof( unsigned long long ), st->stream ) );
+                st->scan_epoch = 0;
+            }
+            if ( ++st->scan_epoch >= ( 1u << 30 ) ) {   // the epoch field is 30 bits: start over on clean descriptors
+                PPC_CK( cudaMemsetAsync( st->scan_desc, 0, ( st->scan_desc_cap + 1 ) * sizeof( unsigned long long ), st->stream ) );
+                st->scan_epoch = 1;
+            }
+            exclusive_scan_single_pass( st->cell_count, st->cell_start, bins + 1, st->scan_desc + 1, reinterpret_cast<uint32_t *>( st->scan_desc ),
+                                        st->scan_epoch, st->stream );
+        } else
+            exclusive_scan( st->cell_count, st->cell_start, bins + 1, st->scratch, st->stream );
     }
     const uint32_t *slot_of = st->slot_of;
     {
@@ -1080,6 +1101,7 @@ extern "C" void particlesFree( struct Particles_t *particles ) {
         free_particle_arrays( st );
         cudaFree( st->cell_count );
         cudaFree( st->cell_start );
+        cudaFree( st->scan_desc );
         cudaFree( st->d_word );
         cudaFree( st->slab_counts );
         if ( st->h_slab )
@@ -1280,6 +1302,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_merge = (int)value;
     else if ( !strcmp( name, "gs_slice" ) )
         st->opt_gs_slice = (int)value;
+    else if ( !strcmp( name, "scan_single" ) )
+        st->opt_scan_single = (int)value;
     else if ( !strcmp( name, "cell_ranks" ) )
         st->opt_cell_ranks = (int)value;
     else if ( !strcmp( name, "defer_state" ) )

@@ -105,7 +105,7 @@ static_assert( GS_BINS % GS_THREADS == 0, "bins per thread" );
 
 struct GsSmem {
     float4   a[ GS_CAP ];           // x, y, radius, API index (bits), in storage order
-    uint16_t pool_val[ GS_POOL ];   // contact entry: partner [10:0], row offset + 1 [12:11], column offset + 1 [14:13], anchored [15]
+    uint16_t pool_val[ GS_POOL ];   // contact entry: partner [10:0], scan-cell code 3 (row offset + 1) + column offset + 1 [14:11], anchored [15]
     uint16_t pool_next[ GS_POOL ];  // next entry of the same particle; the two arrays double as 32-bit bin counters during binning
     uint16_t pool_aux[ GS_POOL ];   // level of an entry that stands for a pair this sub-tile owns
     uint16_t fend[ GS_BINS ];       // end (exclusive) of fine bin f = row * GS_NB + bin in perm; its begin is fend[f - 1]
@@ -490,7 +490,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                     continue;
                 const uint32_t at = atomicAdd( &T.pool_n, 1u );
                 if ( at < (uint32_t)GS_POOL ) {
-                    T.pool_val[ at ]  = (uint16_t)( s | ( (uint32_t)d << 11 ) | ( (uint32_t)( dc + 1 ) << 13 ) );
+                    T.pool_val[ at ]  = (uint16_t)( s | ( (uint32_t)( d * 3 + dc + 1 ) << 11 ) );
                     T.pool_next[ at ] = (uint16_t)GS_NONE;
                     if ( tail == GS_NONE )
                         head = at;
@@ -533,7 +533,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                         continue;
                     const uint32_t at = atomicAdd( &T.pool_n, 1u );
                     if ( at < (uint32_t)GS_POOL ) {
-                        T.pool_val[ at ]  = (uint16_t)( s | ( (uint32_t)d << 11 ) | ( (uint32_t)( dc + 1 ) << 13 ) );
+                        T.pool_val[ at ]  = (uint16_t)( s | ( (uint32_t)( d * 3 + dc + 1 ) << 11 ) );
                         T.pool_next[ at ] = (uint16_t)GS_NONE;
                         if ( tail == GS_NONE )
                             head = at;
@@ -599,7 +599,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             // staged numbers of one cell ascending with the index.
             auto sort_key = [ & ]( const uint32_t v ) -> uint32_t {
                 const uint32_t s = v & 0x7ffu, g = __float_as_uint( T.a[ s ].w );
-                return g < gid ? g : 0x80000000u | ( ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) << 11 ) | ( 2047u - s );
+                return g < gid ? g : 0x80000000u | ( v & 0x7800u ) | ( 2047u - s );   // the scan-cell code sits in the entry where the key wants it
             };
             const float wme      = T.inv_lut[ T.massb[ self ] ];
             const bool  row_last = ( j == GS_R ), row_first = ( j == 1 );
@@ -621,7 +621,8 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                 if ( best != e )
                     T.pool_val[ best ] = T.pool_val[ e ];
                 const uint32_t s     = v & 0x7ffu;
-                const int      d     = (int)( ( v >> 11 ) & 3u ) - 1, dc = (int)( ( v >> 13 ) & 3u ) - 1;   // partner's cell relative to mine
+                const uint32_t code  = ( v >> 11 ) & 15u, code3 = ( code * 11u ) >> 5;                  // code / 3 for 0..8
+                const int      d     = (int)code3 - 1, dc = (int)( code - 3u * code3 ) - 1;                  // partner's cell relative to mine
                 const float4   c     = T.a[ s ];
                 const uint32_t cg    = __float_as_uint( c.w );
                 const bool     me_lo = gid < cg;
@@ -712,7 +713,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
                 const uint32_t nxt = T.pool_next[ e ], v = T.pool_val[ e ];
                 if ( v & 0x8000u ) {
                     const uint32_t at = atomicAdd( &T.n_owned, 1u );
-                    skey[ at ] = ( phase_at( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ), pj, pc ) << 20 ) | ( self << 10 ) | ( pos < 1023u ? pos : 1023u );
+                    skey[ at ] = ( phase_at( ( v >> 11 ) & 15u, pj, pc ) << 20 ) | ( self << 10 ) | ( pos < 1023u ? pos : 1023u );
                     sent[ at ] = (uint16_t)e;
                     T.pool_next[ e ] = (uint16_t)self;   // the entry remembers its anchor where its link was
                 }
@@ -754,7 +755,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
         for ( uint32_t e = T.head[ a ]; e != GS_NONE; e = T.pool_next[ e ] ) {
             const uint32_t v = T.pool_val[ e ];
             if ( v & 0x8000u ) {
-                cnt += 1ull << ( 7u * ( ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u ) ) );
+                cnt += 1ull << ( 7u * ( ( v >> 11 ) & 15u ) );
                 mine++;
             }
         }
@@ -816,7 +817,7 @@ __device__ __forceinline__ bool gs_pairs_subtile( GsSmem &T, const float4 *__res
             for ( uint32_t e = T.head[ a ]; e != GS_NONE; ) {
                 const uint32_t nxt = T.pool_next[ e ], v = T.pool_val[ e ];
                 if ( v & 0x8000u ) {
-                    const uint32_t code = ( ( v >> 11 ) & 3u ) * 3u + ( ( v >> 13 ) & 3u );
+                    const uint32_t code = ( v >> 11 ) & 15u;
                     seg[ seg_base + ( (uint32_t)( pre >> ( 7u * code ) ) & 127u ) + ( (uint32_t)( cur >> ( 7u * code ) ) & 127u ) ] = (uint16_t)e;
                     cur += 1ull << ( 7u * code );
                     T.pool_next[ e ] = (uint16_t)a;

@@ -137,6 +137,103 @@ __global__ void __launch_bounds__( SCAN_THREADS ) k_scan_apply( const uint32_t *
     }
 }
 
+// ---- single-pass variant: decoupled look-back --------------------------------------------------------------------------
+// One launch, one read and one write of the array.  CTAs take tile numbers from a ticket counter (so a CTA only ever waits for tiles
+// whose CTAs are already running), publish their tile's sum, and find their exclusive prefix by looking back over the published
+// descriptors of the preceding tiles, 32 at a time: sums are added up until a tile is met that already knows its inclusive prefix.
+// A descriptor is ONE 64-bit word {value, epoch << 2 | state}: written and read whole, so no fence is needed between value and flag,
+// and never cleared: the epoch (a counter of launches on this descriptor array) tells this launch's words from stale ones.
+constexpr uint32_t SCAN_AGGREGATE = 1u, SCAN_INCLUSIVE = 2u;
+
+__global__ void __launch_bounds__( SCAN_THREADS ) k_scan_lookback( const uint32_t *in, uint32_t *out, const size_t n, unsigned long long *desc,
+                                                                   uint32_t *ticket, const uint32_t epoch, const uint32_t tiles ) {
+    __shared__ uint32_t sh[ 16 ];
+    __shared__ uint32_t s_tile, s_prefix;
+    if ( threadIdx.x == 0 )
+        s_tile = atomicAdd( ticket, 1u );
+    __syncthreads();
+    const uint32_t tile  = s_tile;
+    const size_t   first = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    uint32_t       item[ SCAN_ITEMS ];
+    scan_load_items( in, n, first, item );
+    uint32_t s = 0;
+#pragma unroll
+    for ( int q = 0; q < SCAN_ITEMS; q++ )
+        s += item[ q ];
+    uint32_t total;
+    uint32_t run = block_exclusive_scan( s, sh, total );
+    volatile unsigned long long *vd = desc;
+    const unsigned long long     tag = (unsigned long long)( epoch << 2 ) << 32;
+    if ( threadIdx.x < 32 ) {
+        const unsigned lane = threadIdx.x;
+        if ( lane == 0 ) {
+            vd[ tile ] = tag | ( (unsigned long long)( tile == 0 ? SCAN_INCLUSIVE : SCAN_AGGREGATE ) << 32 ) | total;
+            if ( tile == tiles - 1 )
+                *ticket = 0u;   // every ticket of this launch has been taken: ready for the next one
+        }
+        uint32_t prefix = 0;
+        if ( tile != 0 ) {
+            int base = (int)tile - 1;
+            for ( ;; ) {
+                const int          p = base - (int)lane;
+                unsigned long long d;
+                do {   // a tile before the first one counts as "inclusive prefix 0"
+                    d = p >= 0 ? vd[ p ] : ( tag | ( (unsigned long long)SCAN_INCLUSIVE << 32 ) );
+                } while ( __any_sync( 0xffffffffu, ( d >> 34 ) != (unsigned long long)epoch || ( ( d >> 32 ) & 3u ) == 0u ) );
+                const unsigned incl = __ballot_sync( 0xffffffffu, ( ( d >> 32 ) & 3u ) == SCAN_INCLUSIVE );
+                const unsigned stop = incl ? (unsigned)( __ffs( (int)incl ) - 1 ) : 31u;   // nearest tile that knows its inclusive prefix
+                uint32_t       v    = lane <= stop ? (uint32_t)d : 0u;
+#pragma unroll
+                for ( int k = 16; k > 0; k >>= 1 )
+                    v += __shfl_xor_sync( 0xffffffffu, v, k );
+                prefix += v;
+                if ( incl )
+                    break;
+                base -= 32;
+            }
+            if ( lane == 0 )
+                vd[ tile ] = tag | ( (unsigned long long)SCAN_INCLUSIVE << 32 ) | ( prefix + total );
+        }
+        if ( lane == 0 )
+            s_prefix = prefix;
+    }
+    __syncthreads();
+    run += s_prefix;
+    if ( first + SCAN_ITEMS <= n ) {
+        uint4 *p = reinterpret_cast<uint4 *>( out + first );
+#pragma unroll
+        for ( int q = 0; q < SCAN_ITEMS / 4; q++ ) {
+            uint4 v;
+            v.x = run;
+            run += item[ 4 * q ];
+            v.y = run;
+            run += item[ 4 * q + 1 ];
+            v.z = run;
+            run += item[ 4 * q + 2 ];
+            v.w = run;
+            run += item[ 4 * q + 3 ];
+            p[ q ] = v;
+        }
+    } else {
+#pragma unroll
+        for ( int q = 0; q < SCAN_ITEMS; q++ ) {
+            if ( first + q < n )
+                out[ first + q ] = run;
+            run += item[ q ];
+        }
+    }
+}
+
+// desc: div_up(n, SCAN_TILE) 64-bit words, zero-filled when allocated; ticket: one zero-initialised word; epoch: 1, 2, 3 ... per call
+// on this descriptor array (below 2^30).
+static inline void exclusive_scan_single_pass( const uint32_t *in, uint32_t *out, size_t n, unsigned long long *desc, uint32_t *ticket,
+                                               uint32_t epoch, cudaStream_t s ) {
+    if ( n == 0 )
+        return;
+    const unsigned tiles = div_up( n, SCAN_TILE );
+    PPC_LAUNCH( k_scan_lookback, tiles, SCAN_THREADS, 0, s, in, out, n, desc, ticket, epoch, tiles );
+}
+
 // Number of uint32 words of scratch exclusive_scan needs for n elements.
 static inline size_t scan_scratch_words( size_t n ) { return div_up( n, SCAN_TILE ) + 1; }
 

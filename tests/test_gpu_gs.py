@@ -149,10 +149,10 @@ def test_an_overfull_tile_runs_that_substep_on_the_exact_resolve(oracle):
 def test_performance_options_do_not_change_the_result():
     """The slice length of k_gs_resolve's record stream ("gs_slice"), one launch for the four tile colours or four ("gs_merge"), who applies the integrate + wall pass ("defer_state": the
     sorting gather, or the first pass as in round 1) and who hands out the positions inside a cell ("cell_ranks": the histogram
-    pass, or the scatter's own atomics) are performance choices: same bits whatever they are set to."""
+    pass, or the scatter's own atomics), one launch or three for the cell-start scan ("scan_single") are performance choices: same bits whatever they are set to."""
     sc = scenes.polydisperse_pile(60000, seed=131, vmax=5.0)
     want = None
-    for opts in ({}, {"gs_slice": 64}, {"gs_slice": 512}, {"gs_merge": 1}, {"defer_state": 0}, {"cell_ranks": 0}, {"defer_state": 0, "cell_ranks": 0}):
+    for opts in ({}, {"gs_slice": 64}, {"gs_slice": 512}, {"gs_merge": 1}, {"scan_single": 0}, {"defer_state": 0}, {"cell_ranks": 0}, {"defer_state": 0, "cell_ranks": 0}):
         p = gs_store(state_from_scene(sc))
         for k, v in opts.items():
             p.set_option(k, v)
