@@ -98,6 +98,29 @@ def test_hot_pairs_of_the_exact_path_equal_the_reference_pair_set(oracle):
             p.Free()
 
 
+@pytest.mark.parametrize("phi", [0.05, 0.40, 0.80])
+def test_density_sweep_points_match_their_models(oracle, phi):
+    """BASELINE configs[4] (packing-density sweep 5 %-80 %), at test size: the exact resolve against the reference's sequential
+    order and the tile Gauss-Seidel resolve against its CPU model, bit for bit, at both ends and the middle of the sweep (the same
+    generator bench.py's other_configs.density_sweep_16m times at 16M particles)."""
+    sc = scenes.uniform_random(30000, 2.0, phi, seed=0x5EED0005, vmax=0.0)
+    for resolve in (1, 3):
+        ref = state_from_scene(sc)
+        p = gpu_store(ref)
+        p.set_option("resolve", resolve)
+        for step in range(4):
+            before = p.gs_fallbacks() if resolve == 3 else 0
+            p.Update(DT)
+            p.CollisionsCheck_Grid(sc.W, sc.H, DT)
+            fell_back = resolve == 3 and p.gs_fallbacks() != before   # (a substep that does not fit the tile kernel runs on the exact resolve)
+            if resolve == 3:
+                par = p.gs_params()
+                oracle.set_tilegs(par["wc"], par["tile_r"], par["strip_limit"])
+            oracle.substep(ref, sc.W, sc.H, DT, 0 if ( resolve == 1 or fell_back ) else 3, False)
+            assert_state_bits(gpu_state(p), ref, f"area fraction {phi}, resolve={resolve}, substep {step}, fell back: {fell_back}")
+        p.Free()
+
+
 def test_tiny_and_degenerate_fields(oracle):
     for n in (2, 3, 17):
         sc = scenes.uniform_random(n, 5.0, 0.6, seed=420 + n, vmax=10.0)
