@@ -71,6 +71,8 @@ struct Store {
     uint32_t    *api_ids = nullptr;   // slab mode: global indices of the copied-back particles
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
+    int          opt_slab_fused = 1;   // slab mode: one fused first pass (k_slab_integrate) instead of K1 + count + pack + localize sweeps over the owned particles
+    bool         slab_fused_now = false;   // this substep's ppc_slab_begin ran the fused pass
     int          opt_scan_single = 1;  // cell-start scan in one launch (decoupled look-back); 0: reduce / scan / apply (three launches)
     unsigned long long *scan_desc = nullptr;   // [0]: ticket counter, [1..]: tile descriptors of the single-pass scan
     size_t       scan_desc_cap = 0;
@@ -685,9 +687,9 @@ static void grid_stage( Store *st, const size_t n, const size_t bins, const int 
             const int where = radix_sort_pairs( st->sort_keys_a, st->slot_of, st->sort_keys_b, st->sort_vals_b, true, n,
                                                 bits_for( (uint32_t)bins ), st->scratch, st->stream );
             slot_of         = where ? st->sort_vals_b : st->slot_of;
-        } else if ( st->ranks_valid && first == 0 ) {   // K1 ranked the particles inside their cells: no atomics here
-            PPC_LAUNCH( k_cell_place, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, (const uint32_t *)st->sort_keys_a, st->cell_count,
-                        st->cell_start, st->slot_of, n );
+        } else if ( st->ranks_valid ) {   // the first pass ranked the particles inside their cells: no atomics here
+            PPC_LAUNCH( k_cell_place, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, A.key, (const uint32_t *)( st->sort_keys_a + first ),
+                        st->cell_count, st->cell_start, st->slot_of, n );
             st->hist_clean  = true;
             st->ranks_valid = false;
         } else {   // counts the histogram back down to zero
@@ -1302,6 +1304,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_merge = (int)value;
     else if ( !strcmp( name, "gs_slice" ) )
         st->opt_gs_slice = (int)value;
+    else if ( !strcmp( name, "slab_fused" ) )
+        st->opt_slab_fused = (int)value;
     else if ( !strcmp( name, "scan_single" ) )
         st->opt_scan_single = (int)value;
     else if ( !strcmp( name, "cell_ranks" ) )
@@ -1606,12 +1610,31 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     StepParams   P = {};
     P.do_integrate = 1, P.dt_update = time_step, P.do_colour = colour ? 1 : 0, P.do_walls_keys = 1, P.do_histogram = 0;
     P.wall_w = st->slab_wall_w, P.wall_h = st->slab_wall_h, P.grid = st->slab_world;
-    if ( n ) {
+    st->slab_fused_now = st->opt_slab_fused != 0 && st->opt_sort == 0;
+    if ( st->slab_fused_now ) {
+        // One pass over the owned particles: integrate, walls, window-local key + histogram + rank, neighbour counts and pack lists
+        const SlabRows &R      = st->slab_rows;
+        const int       row_lo = R.own_begin - R.halo > 0 ? R.own_begin - R.halo : 0;
+        const int       row_hi = R.own_end + R.halo < st->slab_world.rows ? R.own_end + R.halo : st->slab_world.rows;
+        const size_t    bins   = (size_t)st->slab_world.cols * (size_t)( row_hi - row_lo ) + 1;   // + the drop bin
+        ensure_cells( st, bins );
         StageTimer T( st, ST_INTEGRATE );
-        PPC_LAUNCH( k_integrate_walls_keys, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->cell_count, n, P, (uint32_t *)nullptr );
-    }
-    st->col_valid = colour != 0;
-    {
+        PPC_CK( cudaMemsetAsync( st->slab_counts, 0, 8 * sizeof( uint32_t ), st->stream ) );
+        if ( !st->hist_clean )
+            PPC_CK( cudaMemsetAsync( st->cell_count, 0, st->cells_cap * sizeof( uint32_t ), st->stream ) );
+        st->hist_clean = false;
+        if ( n )
+            PPC_LAUNCH( k_slab_integrate, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, n, P, R, row_lo, row_hi, (uint32_t)( bins - 1 ),
+                        st->cell_count, st->sort_keys_a + st->own_first, st->slab_counts, st->sort_keys_b, st->sort_vals_b );
+        PPC_CK( cudaMemcpyAsync( st->h_slab, st->slab_counts, 4 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+        PPC_CK( cudaStreamSynchronize( st->stream ) );
+        st->col_valid = colour != 0;
+    } else {
+        if ( n ) {
+            StageTimer T( st, ST_INTEGRATE );
+            PPC_LAUNCH( k_integrate_walls_keys, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->cell_count, n, P, (uint32_t *)nullptr );
+        }
+        st->col_valid = colour != 0;
         StageTimer T( st, ST_SLAB );
         PPC_CK( cudaMemsetAsync( st->slab_counts, 0, 8 * sizeof( uint32_t ), st->stream ) );
         if ( n )
@@ -1643,7 +1666,15 @@ extern "C" int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_h
             PPC_CK( cudaMemcpyAsync( hi, st->h_slab + 1, sizeof( uint32_t ), cudaMemcpyHostToDevice, st->stream ) );
         lo += 1, hi += 1;
     }
-    if ( n && ( st->h_slab[ 0 ] || st->h_slab[ 1 ] ) )
+    if ( st->slab_fused_now ) {   // the first pass listed the slots to send
+        const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
+        if ( st->h_slab[ 0 ] )
+            PPC_LAUNCH( k_slab_pack_list, div_up( st->h_slab[ 0 ], STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, (const uint32_t *)st->sort_keys_b,
+                        (size_t)st->h_slab[ 0 ], lo );
+        if ( st->h_slab[ 1 ] )
+            PPC_LAUNCH( k_slab_pack_list, div_up( st->h_slab[ 1 ], STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, (const uint32_t *)st->sort_vals_b,
+                        (size_t)st->h_slab[ 1 ], hi );
+    } else if ( n && ( st->h_slab[ 0 ] || st->h_slab[ 1 ] ) )
         PPC_LAUNCH( k_slab_pack, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, offset_view( st->set[ st->cur ], st->own_first ), n,
                     st->slab_rows, lo, hi, st->slab_counts + 4 );
     return 0;
@@ -1689,10 +1720,19 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
             PPC_CK( cudaMemcpyAsync( st->h_slab + 3, recv_lo, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
         if ( with_header && n_hi )
             PPC_CK( cudaMemcpyAsync( st->h_slab + 7, recv_hi, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
-        PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
-        if ( n_loc )
-            PPC_LAUNCH( k_slab_localize, div_up( n_loc, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key, n_loc, G.cols, row_lo, row_hi, G.cells,
-                        st->cell_count );
+        if ( st->slab_fused_now ) {   // the owned particles already carry local keys and ranks and are in the histogram: only what arrived is left
+            const size_t n_rec = n_lo + n_hi;
+            if ( n_rec )
+                PPC_LAUNCH( k_slab_localize, div_up( n_rec, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key + st->n_own, n_rec, G.cols, row_lo, row_hi,
+                            G.cells, st->cell_count, st->sort_keys_a + st->own_first + st->n_own );
+            st->ranks_valid = true;
+        } else {
+            PPC_CK( cudaMemsetAsync( st->cell_count, 0, ( bins + 1 ) * sizeof( uint32_t ), st->stream ) );
+            if ( n_loc )
+                PPC_LAUNCH( k_slab_localize, div_up( n_loc, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V.key, n_loc, G.cols, row_lo, row_hi, G.cells,
+                            st->cell_count, (uint32_t *)nullptr );
+            st->ranks_valid = false;
+        }
     }
     if ( n_loc )
         grid_stage( st, n_loc, bins, G.cols, st->own_first, G.cells );

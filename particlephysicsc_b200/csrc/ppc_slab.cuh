@@ -102,6 +102,78 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_pack( const ParticleS
     }
 }
 
+// ---- the fused first pass of a slab substep ---------------------------------------------------------------------------------
+// K1 of the single-GPU path (integrate, colour, walls, cell key: same float operations, ppc_math.cuh) over the owned particles,
+// and in the same pass everything that used to be three more sweeps over them: which neighbour each particle goes to (counts +
+// the two lists of slots to pack, instead of k_slab_count and a k_slab_pack over all owned particles), its key LOCAL to the window
+// and the window's histogram (instead of k_slab_localize over the owned particles), and its rank inside its cell (so that the
+// counting sort places it without atomics, k_cell_place).
+__global__ void __launch_bounds__( STREAM_THREADS ) k_slab_integrate( ParticleSet S, const size_t n, const StepParams P, const SlabRows R, const int row_lo,
+                                                                      const int row_hi, const uint32_t drop, uint32_t *__restrict__ cell_count,
+                                                                      uint32_t *__restrict__ cell_rank, uint32_t *__restrict__ counts,
+                                                                      uint32_t *__restrict__ list_lo, uint32_t *__restrict__ list_hi ) {
+    const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    const bool     valid = k < n;
+    const unsigned lane  = threadIdx.x & 31u;
+    uint32_t       lk    = 0xffffffffu;
+    unsigned       t     = 0;
+    bool           lost  = false;
+    if ( valid ) {
+        float4       s = S.pv[ k ];
+        const float2 a = S.rm[ k ];
+        integrate( s.x, s.y, s.z, s.w, P.dt_update );
+        if ( P.do_colour )
+            S.col[ k ] = energy_colour( s.z, s.w, a.y );
+        walls( s.x, s.y, s.z, s.w, a.x, P.wall_w, P.wall_h );
+        const int cx = cell_coord( s.x, P.grid.cell_size, P.grid.cols );   // P.grid: the WHOLE field's grid
+        const int cy = cell_coord( s.y, P.grid.cell_size, P.grid.rows );
+        t            = slab_targets( R, cy, lost );
+        lk           = ( cy >= row_lo && cy < row_hi ) ? (uint32_t)( ( cy - row_lo ) * P.grid.cols + cx ) : drop;
+        S.key[ k ]   = lk;
+        S.pv[ k ]    = s;
+    }
+    const unsigned lo = __ballot_sync( 0xffffffffu, t & 1u ), hi = __ballot_sync( 0xffffffffu, t & 2u ), ls = __ballot_sync( 0xffffffffu, lost );
+    if ( lo | hi | ls ) {   // rare: only warps near a border
+        uint32_t base_lo = 0, base_hi = 0;
+        if ( lane == 0 ) {
+            if ( lo )
+                base_lo = atomicAdd( &counts[ 0 ], (uint32_t)__popc( lo ) );
+            if ( hi )
+                base_hi = atomicAdd( &counts[ 1 ], (uint32_t)__popc( hi ) );
+            if ( ls )
+                atomicAdd( &counts[ 2 ], (uint32_t)__popc( ls ) );
+        }
+        base_lo = __shfl_sync( 0xffffffffu, base_lo, 0 );
+        base_hi = __shfl_sync( 0xffffffffu, base_hi, 0 );
+        const unsigned below = ( 1u << lane ) - 1u;
+        if ( t & 1u )
+            list_lo[ base_lo + (uint32_t)__popc( lo & below ) ] = (uint32_t)k;
+        if ( t & 2u )
+            list_hi[ base_hi + (uint32_t)__popc( hi & below ) ] = (uint32_t)k;
+    }
+    const unsigned peers  = __match_any_sync( 0xffffffffu, lk );
+    const unsigned leader = (unsigned)( __ffs( peers ) - 1 );
+    uint32_t       base   = 0;
+    if ( valid && lane == leader )
+        base = atomicAdd( &cell_count[ lk ], (uint32_t)__popc( peers ) );
+    base = __shfl_sync( 0xffffffffu, base, leader );
+    if ( valid )
+        cell_rank[ k ] = base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) );
+}
+
+// the records of the listed slots -> one send buffer (order inside a buffer is arbitrary: the receiver sorts by (key, gid))
+__global__ void __launch_bounds__( STREAM_THREADS ) k_slab_pack_list( const ParticleSet S, const uint32_t *__restrict__ list, const size_t count,
+                                                                      SlabRec *__restrict__ send ) {
+    const size_t i = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    if ( i >= count )
+        return;
+    const uint32_t k = list[ i ];
+    SlabRec        r;
+    const float2   a = S.rm[ k ];
+    r.pv = S.pv[ k ], r.radius = a.x, r.mass = a.y, r.gid = S.gid[ k ], r.col = S.col[ k ];
+    send[ i ] = r;
+}
+
 // received records -> storage slots [first, first + capacity), with their global cell key (:280-291, same float operations
 // as K1).  With a header (fixed-size messages: record 0 holds the number of records that follow) the slots past that number
 // get a key beyond every window, which the sort puts into the drop bin.
@@ -130,8 +202,10 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_append( const Particl
 }
 
 // global key -> key local to the window [row_lo, row_hi) (or the drop bin `drop`), and the histogram of those (K3)
+// (with cell_rank: also the rank of every particle inside its cell, as the fused first pass leaves it for the owned particles)
 __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_localize( uint32_t *__restrict__ key, const size_t n, const int cols, const int row_lo,
-                                                                     const int row_hi, const uint32_t drop, uint32_t *__restrict__ cell_count ) {
+                                                                     const int row_hi, const uint32_t drop, uint32_t *__restrict__ cell_count,
+                                                                     uint32_t *__restrict__ cell_rank ) {
     const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
     const bool     valid = k < n;
     const unsigned lane  = threadIdx.x & 31u;
@@ -142,9 +216,16 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_localize( uint32_t *_
         lk                = ( cy >= row_lo && cy < row_hi ) ? g - (uint32_t)row_lo * (uint32_t)cols : drop;
         key[ k ]          = lk;
     }
-    const unsigned peers = __match_any_sync( 0xffffffffu, lk );
-    if ( valid && lane == (unsigned)( __ffs( peers ) - 1 ) )
-        atomicAdd( &cell_count[ lk ], (uint32_t)__popc( peers ) );
+    const unsigned peers  = __match_any_sync( 0xffffffffu, lk );
+    const unsigned leader = (unsigned)( __ffs( peers ) - 1 );
+    uint32_t       base   = 0;
+    if ( valid && lane == leader )
+        base = atomicAdd( &cell_count[ lk ], (uint32_t)__popc( peers ) );
+    if ( cell_rank ) {
+        base = __shfl_sync( 0xffffffffu, base, leader );
+        if ( valid )
+            cell_rank[ k ] = base + (uint32_t)__popc( peers & ( ( 1u << lane ) - 1u ) );
+    }
 }
 
 // After the resolve: did the inexactness mark (ST_TAINT) reach an owned particle, and how many rows did it travel?  A contact
