@@ -173,6 +173,18 @@ def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float =
     return value, dt / steps * 1e3, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "particles": n}
 
 
+def nccl_options():
+    """NCCL's own stream at high priority: the neighbour exchange of the slab decomposition runs beside the interior integrate
+    pass (slab.slab_step), and the few CTAs of its transfer kernels must not queue behind that pass's hundred thousand."""
+    try:
+        from torch.distributed import ProcessGroupNCCL
+        o = ProcessGroupNCCL.Options()
+        o.is_high_priority_stream = True
+        return o
+    except Exception:
+        return None
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -288,7 +300,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
     n_per_gpu, descr = WORKLOADS[args.workload]
     n = n_per_gpu
     sc = make_scene(args.workload, n, seed_offset=0x100 * rank)
@@ -476,7 +488,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=nccl_options())
     dev = torch.device("cuda", local_rank)
     # weak scaling: BASELINE configs[3], every rank generates its own slab; strong scaling: one of the single-GPU fields
     # (e.g. the 16M pile), generated identically on every rank and cut into slabs of equal particle count

@@ -190,6 +190,7 @@ const char        *ppc_version( void );
  * The field is cut into slabs of whole cell rows, one store (one process, one GPU) per slab.  A substep is
  *     ppc_slab_begin   integrate + walls of the owned particles; how many records go to each neighbour
  *     ppc_slab_pack    write those records (32 bytes each) into two device buffers of the caller
+ *     ppc_slab_interior  (optional) the part of the integrate pass that cannot produce records, while the buffers travel
  *     -- the caller moves the buffers to the neighbouring ranks (NCCL send/recv, or a device copy in one process) --
  *     ppc_slab_finish  take the received records in, build the grid over owned + ghost rows, narrow phase, resolve
  * The particles of a window's outermost ghost row miss their outward contacts; the resolve marks them and everything that
@@ -218,6 +219,11 @@ int ppc_slab_begin( struct Particles_t *p, float time_step, int colour, uint64_t
 /* with_header: messages of a fixed, agreed size -- record 0 of each buffer holds the number of records that follow, so the
  * receiver needs no count in advance (ppc_slab_finish then takes the buffers' CAPACITIES and reports the counts received) */
 int ppc_slab_pack( struct Particles_t *p, void *send_lo, void *send_hi /* device buffers of send_counts (+1) records */, int with_header );
+/* Optional, between ppc_slab_pack and ppc_slab_finish: ppc_slab_begin integrates only the owned particles near the borders (the
+ * ones that can end up in a message); this queues the rest on the store's stream.  A host that starts the transfer of the packed
+ * buffers on ANOTHER stream (after an event recorded behind ppc_slab_pack) and then calls this overlaps the transfer with most of
+ * the integrate pass; ppc_slab_finish calls it itself if the host did not. */
+int ppc_slab_interior( struct Particles_t *p );
 /* returns the number of owned particles after the substep */
 int64_t ppc_slab_finish( struct Particles_t *p, float time_step, const void *recv_lo, uint64_t n_lo, const void *recv_hi, uint64_t n_hi,
                          int with_header, uint64_t received[ 2 ] /* may be NULL */ );

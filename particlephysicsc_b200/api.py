@@ -63,7 +63,7 @@ EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_
                      "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_hot_pairs", "ppc_debug_gs_params", "ppc_gs_fallbacks", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
-SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_gs_halo", "ppc_gs_auto_tile_width", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_download_async", "ppc_slab_info",
+SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_gs_halo", "ppc_gs_auto_tile_width", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_interior", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_download_async", "ppc_slab_info",
                 "ppc_slab_debug_pairs"]
 SNAPSHOT_SYMBOLS = ["ppc_snapshot_write", "ppc_snapshot_read"]
 
@@ -129,6 +129,7 @@ def load_library() -> C.CDLL:
     L.ppc_slab_init.restype = C.c_int
     L.ppc_slab_begin.argtypes, L.ppc_slab_begin.restype = [PP, C.c_float, C.c_int, C.POINTER(C.c_uint64)], C.c_int
     L.ppc_slab_pack.argtypes, L.ppc_slab_pack.restype = [PP, C.c_void_p, C.c_void_p, C.c_int], C.c_int
+    L.ppc_slab_interior.argtypes, L.ppc_slab_interior.restype = [PP], C.c_int
     L.ppc_slab_finish.argtypes = [PP, C.c_float, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
     L.ppc_slab_finish.restype = C.c_int64
     L.ppc_slab_download.argtypes, L.ppc_slab_download.restype = [PP, u32p, C.c_uint], C.c_int

@@ -72,6 +72,12 @@ struct Store {
     uint32_t    *slot_of = nullptr, *sort_keys_b = nullptr, *sort_vals_b = nullptr, *sort_keys_a = nullptr;
     uint32_t    *cell_count = nullptr, *cell_start = nullptr;
     int          opt_slab_fused = 1;   // slab mode: one fused first pass (k_slab_integrate) instead of K1 + count + pack + localize sweeps over the owned particles
+    int          opt_slab_overlap = 1; // slab mode: the fused first pass does the border slots first, the interior while the records travel
+    size_t       slab_band_lo = 0, slab_band_hi = 0;   // owned slots (relative to own_first) of the rows 2 * halo from either border, at the last grid build
+    size_t       slab_int_first = 0, slab_int_count = 0;   // interior part of the current substep's first pass, still to be launched
+    StepParams   slab_int_P = {};
+    int          slab_int_row_lo = 0, slab_int_row_hi = 0;
+    uint32_t     slab_int_drop = 0;
     bool         slab_fused_now = false;   // this substep's ppc_slab_begin ran the fused pass
     int          opt_scan_single = 1;  // cell-start scan in one launch (decoupled look-back); 0: reduce / scan / apply (three launches)
     unsigned long long *scan_desc = nullptr;   // [0]: ticket counter, [1..]: tile descriptors of the single-pass scan
@@ -1304,6 +1310,8 @@ extern "C" int ppc_set_option( struct Particles_t *p, const char *name, long lon
         st->opt_gs_merge = (int)value;
     else if ( !strcmp( name, "gs_slice" ) )
         st->opt_gs_slice = (int)value;
+    else if ( !strcmp( name, "slab_overlap" ) )
+        st->opt_slab_overlap = (int)value;
     else if ( !strcmp( name, "slab_fused" ) )
         st->opt_slab_fused = (int)value;
     else if ( !strcmp( name, "scan_single" ) )
@@ -1623,9 +1631,19 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
         if ( !st->hist_clean )
             PPC_CK( cudaMemsetAsync( st->cell_count, 0, st->cells_cap * sizeof( uint32_t ), st->stream ) );
         st->hist_clean = false;
-        if ( n )
-            PPC_LAUNCH( k_slab_integrate, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, n, P, R, row_lo, row_hi, (uint32_t)( bins - 1 ),
-                        st->cell_count, st->sort_keys_a + st->own_first, st->slab_counts, st->sort_keys_b, st->sort_vals_b );
+        // Border slots first (within 2 * halo rows of a border at the last grid build; everything before the first grid build): their
+        // counts are what the host waits for, and their records can travel while ppc_slab_interior integrates the rest.
+        size_t b_lo = n, b_hi = n;   // owned slots [0, b_lo) and [b_hi, n) are the border parts
+        if ( st->opt_slab_overlap && st->grid_valid && ( R.has_lo || R.has_hi ) && st->slab_band_lo <= st->slab_band_hi && st->slab_band_hi <= n )
+            b_lo = R.has_lo ? st->slab_band_lo : 0, b_hi = R.has_hi ? st->slab_band_hi : n;
+        st->slab_int_first = b_lo, st->slab_int_count = b_hi > b_lo ? b_hi - b_lo : 0;
+        st->slab_int_P = P, st->slab_int_row_lo = row_lo, st->slab_int_row_hi = row_hi, st->slab_int_drop = (uint32_t)( bins - 1 );
+        const size_t parts[ 2 ][ 2 ] = { { 0, b_lo < n ? b_lo : n }, { b_hi, b_hi < n ? n - b_hi : 0 } };
+        for ( int part = 0; part < 2; part++ )
+            if ( parts[ part ][ 1 ] )
+                PPC_LAUNCH( k_slab_integrate, div_up( parts[ part ][ 1 ], STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, parts[ part ][ 0 ],
+                            parts[ part ][ 1 ], P, R, row_lo, row_hi, (uint32_t)( bins - 1 ), st->cell_count, st->sort_keys_a + st->own_first,
+                            st->slab_counts, st->sort_keys_b, st->sort_vals_b, 0 );
         PPC_CK( cudaMemcpyAsync( st->h_slab, st->slab_counts, 4 * sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
         PPC_CK( cudaStreamSynchronize( st->stream ) );
         st->col_valid = colour != 0;
@@ -1649,6 +1667,27 @@ extern "C" int ppc_slab_begin( struct Particles_t *p, float time_step, int colou
     send_counts[ 0 ] = st->h_slab[ 0 ];
     send_counts[ 1 ] = st->h_slab[ 1 ];
     st->pre_valid    = false;
+    return 0;
+}
+
+// The rest of the fused first pass: the owned particles that cannot reach a send zone.  Called by the host once the packed records
+// are on their way (so the transfer overlaps this pass), or by ppc_slab_finish if the host did not.
+static void slab_interior( Store *st ) {
+    if ( !st->slab_int_count )
+        return;
+    StageTimer T( st, ST_INTEGRATE );
+    const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
+    PPC_LAUNCH( k_slab_integrate, div_up( st->slab_int_count, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, V, st->slab_int_first, st->slab_int_count,
+                st->slab_int_P, st->slab_rows, st->slab_int_row_lo, st->slab_int_row_hi, st->slab_int_drop, st->cell_count,
+                st->sort_keys_a + st->own_first, st->slab_counts, st->sort_keys_b, st->sort_vals_b, 1 );
+    st->slab_int_count = 0;
+}
+
+extern "C" int ppc_slab_interior( struct Particles_t *p ) {
+    Store *st = store_of( p );
+    if ( !st->slab )
+        return -1;
+    slab_interior( st );
     return 0;
 }
 
@@ -1706,6 +1745,7 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     ensure_scratch( st, radix_scratch_words( n_loc ) + scan_scratch_words( bins + 1 ) + scan_scratch_words( n_loc + 1 ) + 64 );
     if ( st->opt_resolve == 3 )
         ensure_gs_buffers( st );
+    slab_interior( st );   // (if the host has not started it already)
     const ParticleSet V = offset_view( st->set[ st->cur ], st->own_first );
     {
         StageTimer T( st, ST_SLAB );
@@ -1748,7 +1788,18 @@ extern "C" int64_t ppc_slab_finish( struct Particles_t *p, float time_step, cons
     // end of the first owned row / begin of the last owned row (taint scan, below)
     PPC_CK( cudaMemcpyAsync( st->h_slab + 8, st->cell_start + c_own0 + G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaMemcpyAsync( st->h_slab + 9, st->cell_start + c_own1 - G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    // first slot of the rows 2 * halo inside either border: what the next substep's first pass treats as border / interior
+    const int    band_lo_row = R.own_begin + 2 * R.halo < R.own_end ? R.own_begin + 2 * R.halo : R.own_end;
+    const int    band_hi_row = R.own_end - 2 * R.halo > R.own_begin ? R.own_end - 2 * R.halo : R.own_begin;
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 10, st->cell_start + (size_t)( band_lo_row - row_lo ) * G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 11, st->cell_start + (size_t)( band_hi_row - row_lo ) * G.cols, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
+    PPC_CK( cudaMemcpyAsync( st->h_slab + 12, st->slab_counts + 2, sizeof( uint32_t ), cudaMemcpyDeviceToHost, st->stream ) );
     PPC_CK( cudaStreamSynchronize( st->stream ) );
+    if ( st->h_slab[ 12 ] ) {   // (the interior part of the first pass reports here)
+        fprintf( stderr, "particlephysicsc_b200: %u particles moved more than the %d halo rows in one substep\n", st->h_slab[ 12 ], R.halo );
+        abort();
+    }
+    st->slab_band_lo = st->h_slab[ 10 ] - st->h_slab[ 4 ], st->slab_band_hi = st->h_slab[ 11 ] - st->h_slab[ 4 ];
     const size_t n_work = st->h_slab[ 6 ];
     if ( received )
         received[ 0 ] = st->h_slab[ 3 ], received[ 1 ] = st->h_slab[ 7 ];

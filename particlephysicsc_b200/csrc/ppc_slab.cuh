@@ -108,12 +108,18 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_pack( const ParticleS
 // the two lists of slots to pack, instead of k_slab_count and a k_slab_pack over all owned particles), its key LOCAL to the window
 // and the window's histogram (instead of k_slab_localize over the owned particles), and its rank inside its cell (so that the
 // counting sort places it without atomics, k_cell_place).
-__global__ void __launch_bounds__( STREAM_THREADS ) k_slab_integrate( ParticleSet S, const size_t n, const StepParams P, const SlabRows R, const int row_lo,
-                                                                      const int row_hi, const uint32_t drop, uint32_t *__restrict__ cell_count,
-                                                                      uint32_t *__restrict__ cell_rank, uint32_t *__restrict__ counts,
-                                                                      uint32_t *__restrict__ list_lo, uint32_t *__restrict__ list_hi ) {
-    const size_t   k     = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
-    const bool     valid = k < n;
+// The pass runs over the slots [first, first + count) of the owned particles.  `interior`: these slots lay more than 2 * halo rows
+// from both borders at the last grid build, so none of them can reach a send zone without moving more than `halo` rows in one
+// substep -- which is the fatal "lost" condition anyway: the border slots are done first and their records are on the wire while
+// this (much larger) part is still being integrated.
+__global__ void __launch_bounds__( STREAM_THREADS ) k_slab_integrate( ParticleSet S, const size_t first, const size_t count, const StepParams P,
+                                                                      const SlabRows R, const int row_lo, const int row_hi, const uint32_t drop,
+                                                                      uint32_t *__restrict__ cell_count, uint32_t *__restrict__ cell_rank,
+                                                                      uint32_t *__restrict__ counts, uint32_t *__restrict__ list_lo,
+                                                                      uint32_t *__restrict__ list_hi, const int interior ) {
+    const size_t   t_in  = (size_t)blockIdx.x * STREAM_THREADS + threadIdx.x;
+    const size_t   k     = first + t_in;
+    const bool     valid = t_in < count;
     const unsigned lane  = threadIdx.x & 31u;
     uint32_t       lk    = 0xffffffffu;
     unsigned       t     = 0;
@@ -128,6 +134,10 @@ __global__ void __launch_bounds__( STREAM_THREADS ) k_slab_integrate( ParticleSe
         const int cx = cell_coord( s.x, P.grid.cell_size, P.grid.cols );   // P.grid: the WHOLE field's grid
         const int cy = cell_coord( s.y, P.grid.cell_size, P.grid.rows );
         t            = slab_targets( R, cy, lost );
+        if ( interior && t ) {   // came from deep inside the slab into a send zone: more than `halo` rows in one substep
+            lost = true;
+            t    = 0;
+        }
         lk           = ( cy >= row_lo && cy < row_hi ) ? (uint32_t)( ( cy - row_lo ) * P.grid.cols + cx ) : drop;
         S.key[ k ]   = lk;
         S.pv[ k ]    = s;
