@@ -173,6 +173,26 @@ def time_reference_cpu(workload: str, steps: int, warmup: int, budget_s: float =
     return value, dt / steps * 1e3, {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample, "particles": n}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank on the CPU cores next to its GPU (what `numactl` / the launcher's binding does on a production node), BEFORE
+    the pinned host arrays are allocated: the frame copy-back of 8 ranks then writes 8 node-local buffers instead of crossing
+    the socket interconnect.  Returns what was done, for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "no CPU affinity reported for this GPU"
+        os.sched_setaffinity(0, cpus)
+        return f"{len(cpus)} cores near GPU {local_rank}"
+    except Exception as e:   # no NVML, a container without the call: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def nccl_options():
     """NCCL's own stream at high priority: the neighbour exchange of the slab decomposition runs beside the interior integrate
     pass (slab.slab_step), and the few CTAs of its transfer kernels must not queue behind that pass's hundred thousand."""
@@ -485,6 +505,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
     from particlephysicsc_b200 import api, scenes, slab
 
     dist = None
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else "not requested"
     torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
@@ -700,7 +721,7 @@ def run_slab(args, rank: int, world: int, local_rank: int):
                              "parallel efficiency = value / (n_gpus x this)"),
                     "parallel_efficiency": value / (world * ref_value),
                     "e2e": None if ref_e2e is None else {"value": ref_e2e, "unit": UNIT, "parallel_efficiency": e2e_value / (world * ref_e2e)}},
-                "equivalence": equivalence,
+                "equivalence": equivalence, "host_binding_rank0": numa,
                 "cpu_baseline": None,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 12.0 * n_down / SUBSTEPS_PER_FRAME,
                         "note": "8 slab substeps, then the owned particles' p_x, p_y, colors copied to the host arrays (asynchronously: a frame's "
@@ -731,6 +752,7 @@ def main():
     ap.add_argument("--settle-halo", type=int, default=40, help="slab32m: ghost rows while the random field relaxes")
     ap.add_argument("--halo-margin", type=int, default=3, help="slab32m: rows added to the halo the measured travel of the inexactness mark requires")
     ap.add_argument("--no-scaling-reference", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-GPU: do not bind each rank to the CPU cores next to its GPU")
     ap.add_argument("--no-equivalence", action="store_true", help="skip the N-slabs == one-GPU digest check that precedes the timing")
     ap.add_argument("--replicas", action="store_true", help="with --gpus N and a single-GPU workload: N independent copies instead of N slabs of one field")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (ppc_set_option), e.g. collide=3")
