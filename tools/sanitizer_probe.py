@@ -17,7 +17,8 @@ DT = 1.0 / 144.0 / 8.0
 def main():
     for sc in (scenes.polydisperse_pile(30000, seed=1, vmax=5.0), scenes.uniform_random(30000, 2.0, 0.5, seed=2, vmax=100.0),
                scenes.uniform_random(20000, 1.0, 0.4, seed=3, vmax=50.0)):
-        for opts in ({}, {"wave_mode": 0}, {"collide": 3}, {"collide": 1}):
+        for opts in ({}, {"wave_mode": 0}, {"collide": 3}, {"collide": 1}, {"resolve": 3}, {"resolve": 3, "gs_wc": 3}, {"resolve": 3, "gs_merge": 1},
+                     {"resolve": 3, "scan_single": 0, "cell_ranks": 0, "defer_state": 0}):
             p = api.Particles(sc.n)
             p.set_sync_policy(api.PPC_SYNC_MANUAL)
             for k, v in opts.items():
