@@ -19,6 +19,9 @@
 /* The B200 library's frame copy-back moves what the draw loop reads (p_x, p_y, colors); velocities come on request.  The symbol is
  * weak so that this file still links against the reference's own objects, where the host arrays ARE the state. */
 extern void ppc_download( struct Particles_t *p, unsigned mask ) __attribute__( ( weak ) );
+/* With PPC_RESOLVE=3 in the environment (the fast resolve): how many substeps the library ran on the exact path
+ * because a tile did not fit (particles are spawned ten at a time on one spot here) */
+extern unsigned long long ppc_gs_fallbacks( struct Particles_t *p ) __attribute__( ( weak ) );
 
 static uint64_t g_state = 0x5EED0001ull;
 static uint64_t next_u64( void ) {
@@ -62,6 +65,8 @@ int main( int argc, char **argv ) {
     }
     printf( "frames %d particles %zu size %zu  sum_x %.6f sum_y %.6f ke %.6f  %.3f s  %.3e particle-substeps/s\n", frames, particles.length,
             particles.size, sx, sy, ke, secs, particle_steps / secs );
+    if ( ppc_gs_fallbacks && getenv( "PPC_RESOLVE" ) )
+        printf( "PPC_RESOLVE=%s: %llu of %d substeps ran on the exact resolve instead\n", getenv( "PPC_RESOLVE" ), ppc_gs_fallbacks( &particles ), frames );
     particlesFree( &particles );
     return 0;
 }

@@ -1035,6 +1035,7 @@ static void collide_step( Store *st, uint16_t W, uint16_t H, float dt ) {
 }
 
 static void download( Store *st, struct Particles_t *p, unsigned mask, bool async = false ) {
+    gs_settle( st );   // (the frame copy-back inside particlesCollisionsCheck_Grid comes here without passing store_of again)
     flush_pending_update( st );
     const size_t n = st->n < p->length ? st->n : p->length;
     if ( n && mask ) {

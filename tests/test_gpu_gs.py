@@ -191,6 +191,40 @@ def test_performance_options_do_not_change_the_result():
             assert_state_bits(got, want, f"options {opts}")
 
 
+def test_frame_copy_back_follows_a_substep_that_fell_back(oracle):
+    """The reference's own calling pattern (main.c: no harness calls, the default sync policy copies the frame back inside
+    particlesCollisionsCheck_Grid) with "resolve"=3 on a field whose clumps do not fit the tile kernel: the verdict of the narrow
+    phase is looked at before the copy-back, the substep runs on the exact resolve, and the host arrays hold its result."""
+    n, W, H = 6000, 2000, 2000
+    rng = scenes.Stream(122)
+    s = State.empty(n)
+    cx, cy = rng.unit(12) * (W - 400) + 200, rng.unit(12) * (H - 400) + 200      # 12 clumps of 500 particles within 90 px
+    k = np.arange(n) % 12
+    s.px[:] = cx[k] + (rng.unit(n) - 0.5) * 90
+    s.py[:] = cy[k] + (rng.unit(n) - 0.5) * 90
+    s.vx[:] = (rng.unit(n) - 0.5) * 100
+    s.vy[:] = (rng.unit(n) - 0.5) * 100
+    s.mass[:] = rng.ints(n, 5, 10)
+    s.radius[:] = 1.5 + rng.unit(n) * 4.5
+    ref = s.copy()
+    p = gpu_store(s, policy=api.PPC_SYNC_FRAME)
+    p.set_option("resolve", 3)
+    fell = []
+    for step in range(4):
+        p.Update(DT)
+        p.CollisionsCheck_Grid(W, H, DT)                 # ... and the frame is on the host when this returns
+        got_x, got_y = p.array("p_x").copy(), p.array("p_y").copy()
+        fell.append(p.gs_fallbacks())
+        fell_back = fell[-1] != (fell[-2] if len(fell) > 1 else 0)
+        par = p.gs_params()
+        oracle.set_tilegs(par["wc"], par["tile_r"], par["strip_limit"])
+        oracle.substep(ref, W, H, DT, 0 if fell_back else 3, False)
+        assert_bits_equal(got_x, ref.px, f"substep {step}: p_x as copied back (fell back: {fell_back})")
+        assert_bits_equal(got_y, ref.py, f"substep {step}: p_y as copied back (fell back: {fell_back})")
+    assert fell[0] == 1, "the clumps were meant to overflow the tile kernel in the first substep"
+    p.Free()
+
+
 # ---- statistics against the compiled reference ----------------------------------------------------------------------
 def _reference_runs(sc, steps, dt):
     from oracle import oracle as om
