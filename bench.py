@@ -478,6 +478,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                            "resolve": RESOLVE_NAMES.get(args.resolve, str(args.resolve)),
                            "resolve_option": args.resolve,
                            "gs_substeps_that_fell_back_to_the_exact_resolve": p.gs_fallbacks() if args.resolve == 3 else None,
+                           "gs_fallback_reasons": p.gs_fallback_reasons() if args.resolve == 3 else None,
                            "l2": "state is %.0f MB per GPU, larger than the 126 MB L2; no flush between steps" % (28.0 * n / 1e6),
                            "parallelism": "independent replicas" if world > 1 else "single GPU"},
                 "roofline": roofline,

@@ -171,6 +171,10 @@ int     ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] );
  * does not fit (a region far denser than the rest of the field) is run on the exact resolve instead, for the whole field, so
  * the result stays a function of the state alone.  Returns how many substeps of this store did that. */
 unsigned long long ppc_gs_fallbacks( struct Particles_t *p );
+/* ... by cause (one substep may have several): [0] a one-column strip of a tile holds more particles than shared memory takes,
+ * [1] more contacts in one sub-tile than its contact pool holds, [2] more than 127 owned contacts in one cell or more than 32
+ * pair-colours around one pair, [3] the pair-record buffer is full */
+void    ppc_gs_fallback_reasons( struct Particles_t *p, unsigned long long out[ 4 ] );
 /* last sequential-equivalent resolve: rounds = depth of the reference's pair dependency graph, visits = particle visits */
 int     ppc_debug_wave_stats( struct Particles_t *p, unsigned long long *rounds, unsigned long long *visits );
 

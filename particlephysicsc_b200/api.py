@@ -60,7 +60,7 @@ REFERENCE_SYMBOLS = ["particlesCreate", "particlesFree", "particlesAddParticle",
                      "particlesCollisionsCheck_Grid"]
 EXTENSION_SYMBOLS = ["ppc_set_device", "ppc_set_sync_policy", "ppc_set_download_mask", "ppc_request_colors", "ppc_host_modified",
                      "ppc_download", "ppc_download_async", "ppc_download_wait", "ppc_synchronize", "ppc_run_substeps", "ppc_set_option", "ppc_debug_grid_info", "ppc_debug_keys",
-                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_hot_pairs", "ppc_debug_gs_params", "ppc_gs_fallbacks", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
+                     "ppc_debug_sorted_order", "ppc_debug_cell_start", "ppc_debug_pairs", "ppc_debug_hot_pairs", "ppc_debug_gs_params", "ppc_gs_fallbacks", "ppc_gs_fallback_reasons", "ppc_debug_wave_stats", "ppc_stream", "ppc_kernel_launches",
                      "ppc_profile", "ppc_profile_stages", "ppc_profile_stage_name", "ppc_profile_read", "ppc_profile_reset",
                      "ppc_version"]
 SLAB_SYMBOLS = ["ppc_grid_dims", "ppc_slab_gs_halo", "ppc_gs_auto_tile_width", "ppc_slab_init", "ppc_slab_begin", "ppc_slab_pack", "ppc_slab_interior", "ppc_slab_finish", "ppc_slab_download", "ppc_slab_download_async", "ppc_slab_info",
@@ -109,6 +109,7 @@ def load_library() -> C.CDLL:
     L.ppc_debug_hot_pairs.argtypes, L.ppc_debug_hot_pairs.restype = [PP, i32p, C.c_size_t], C.c_int64
     L.ppc_debug_gs_params.argtypes, L.ppc_debug_gs_params.restype = [PP, C.POINTER(C.c_int)], C.c_int
     L.ppc_gs_fallbacks.argtypes, L.ppc_gs_fallbacks.restype = [PP], C.c_ulonglong
+    L.ppc_gs_fallback_reasons.argtypes, L.ppc_gs_fallback_reasons.restype = [PP, C.POINTER(C.c_ulonglong)], None
     L.ppc_debug_wave_stats.argtypes = [PP, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.ppc_debug_wave_stats.restype = C.c_int
     L.ppc_stream.argtypes, L.ppc_stream.restype = [PP], C.c_void_p
@@ -288,6 +289,12 @@ class Particles:
     def gs_fallbacks(self) -> int:
         """Substeps on which "resolve"=3 ran the exact resolve instead because a sub-tile overflowed the tile kernel."""
         return int(self.lib.ppc_gs_fallbacks(C.byref(self.s)))
+
+    def gs_fallback_reasons(self) -> dict:
+        """... by cause (a substep may have several)."""
+        out = (C.c_ulonglong * 4)()
+        self.lib.ppc_gs_fallback_reasons(C.byref(self.s), out)
+        return dict(strip_over_capacity=int(out[0]), contact_pool_full=int(out[1]), cell_or_colour_limit=int(out[2]), record_buffer_full=int(out[3]))
 
     def wave_stats(self):
         """(rounds, particle visits) of the last sequential-equivalent resolve."""

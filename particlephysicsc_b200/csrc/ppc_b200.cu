@@ -112,6 +112,7 @@ struct Store {
     uint32_t     gs_epoch = 0;
     int          opt_gs_slice = 0;                          // pair records per slice of k_gs_resolve (0: from gs_pairs_per_tile)
     size_t       gs_tiles = 0;
+    unsigned long long gs_fallback_reason[ 4 ] = { 0, 0, 0, 0 };   // ... by cause: GS_ERR_CAP, _POOL, _DEPTH, _CHUNK
     bool         gs_pending = false;                        // the verdict of the last "resolve"=3 substep has not been looked at yet (gs_settle)
     size_t       gs_pending_n = 0;                          // ... and what the exact resolve needs if the verdict is "did not fit"
     GridDims     gs_pending_grid = {};
@@ -841,6 +842,9 @@ static void gs_settle( Store *st ) {
     // the pair search saw (the velocities are untouched: the velocity kernels saw the flag and did nothing), then the reference's order.
     const size_t n = st->gs_pending_n;
     st->gs_fallbacks++;
+    for ( int b = 0; b < 4; b++ )
+        if ( ( *st->h_gs_flag >> b ) & 1u )
+            st->gs_fallback_reason[ b ]++;
     PPC_CK( cudaMemsetAsync( st->gs_flags, 0, sizeof( uint32_t ), st->stream ) );
     PPC_LAUNCH( k_rec_to_positions, div_up( n, STREAM_THREADS ), STREAM_THREADS, 0, st->stream, (const float4 *)st->rec_a, st->set[ st->cur ].pv, n );
     resolve_exact( st, n, st->gs_pending_grid, st->gs_pending_dt, 1 );
@@ -1471,6 +1475,14 @@ extern "C" int ppc_debug_gs_params( struct Particles_t *p, int out[ 4 ] ) {
 
 // Substeps of this store on which "resolve"=3 fell back to the exact resolve because a sub-tile overflowed the tile kernel.
 extern "C" unsigned long long ppc_gs_fallbacks( struct Particles_t *p ) { return store_of( p )->gs_fallbacks; }
+// ... by cause (a substep may have several): a one-column strip of a tile held more particles than shared memory takes; more contacts
+// in one sub-tile than its contact pool holds; more than 127 owned contacts in one cell or more than 32 pair-colours around one pair;
+// pair-record buffer full.
+extern "C" void ppc_gs_fallback_reasons( struct Particles_t *p, unsigned long long out[ 4 ] ) {
+    const Store *st = store_of( p );
+    for ( int b = 0; b < 4; b++ )
+        out[ b ] = st->gs_fallback_reason[ b ];
+}
 
 // =================================================================================================================
 // Part 3: multi-GPU slab decomposition (one store per rank; the caller moves the exchange buffers, e.g. with

@@ -299,7 +299,7 @@ def test_thousand_substeps_on_the_dense_pile_within_the_references_own_spread(or
         sensitivity = max(sensitivity, spread["reversed"]["ke"], spread["shuffled"]["ke"])
         assert dev["ke"] <= sensitivity, (f"substep {upto}: kinetic energy off by {100 * dev['ke']:.2f}%, more than the reference moves under a "
                                           f"reordering of its own pair list anywhere in this run ({100 * sensitivity:.2f}%)")
-    print(f"\ndense pile: {p.gs_fallbacks()} of {done} substeps fell back to the exact resolve (a sub-tile overflowed the tile kernel)")
+    print(f"\ndense pile: {p.gs_fallbacks()} of {done} substeps fell back to the exact resolve (a sub-tile overflowed the tile kernel): {p.gs_fallback_reasons()}")
     assert p.gs_fallbacks() < done // 4
     p.Free()
 
