@@ -65,3 +65,19 @@ def test_reference_arm_line_shape(monkeypatch, capsys):
     assert line["cpu_baseline"]["kind"] == "reference" and line["higher_is_better"] is True and line["config"]["full_field"] is False
     bench.run_reference(A, 1)   # other ranks print nothing
     assert capsys.readouterr().out == ""
+
+
+def test_host_binding_and_nccl_options_degrade_gracefully():
+    """Without a GPU / NVML the rank stays unbound and says so; the NCCL options object, where torch provides it, asks for a
+    high-priority stream (the neighbour exchange runs beside the interior integrate pass)."""
+    sys.path.insert(0, ROOT)
+    import os
+    import bench
+    before = os.sched_getaffinity(0)
+    note = bench.bind_to_gpu_numa_node(0)
+    assert isinstance(note, str) and note
+    assert os.sched_getaffinity(0) <= before and os.sched_getaffinity(0)   # never widened, never emptied
+    os.sched_setaffinity(0, before)
+    o = bench.nccl_options()
+    assert o is None or o.is_high_priority_stream is True
+
